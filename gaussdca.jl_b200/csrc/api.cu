@@ -1,0 +1,627 @@
+// api.cu -- the C ABI of libgdca_b200.so (include/gdca_b200.h).  Host-side orchestration only:
+// argument checks, buffer management, stage ordering, CUDA-event timers.  No arithmetic of the
+// hot path runs on the CPU; without an sm_100 device gdca_create() fails (no fallback).
+#include <math.h>
+#include <string.h>
+
+#include <new>
+
+#include "gdca_internal.cuh"
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+enum { EV_BEGIN = 0, EV_H2D, EV_PACK, EV_THETA, EV_WEIGHTS, EV_COV, EV_CHOL, EV_SCORE, EV_APC, EV_RANK, EV_D2H, EV_COUNT };
+
+int32_t set_device(gdca_ctx *ctx) {
+  GDCA_CUDA(ctx, cudaSetDevice(ctx->device));
+  return GDCA_OK;
+}
+
+int32_t rec(gdca_ctx *ctx, int which) {
+  GDCA_CUDA(ctx, cudaEventRecord(ctx->ev[which], ctx->stream));
+  return GDCA_OK;
+}
+
+int planes_for_q(int q) {
+  int p = 1;
+  while ((1 << p) <= q) ++p;  // q needs p bits
+  return p;
+}
+
+// shape bookkeeping once q is known
+void set_shape(gdca_ctx *ctx, int64_t L, int64_t M, int q) {
+  ctx->L = L;
+  ctx->M = M;
+  ctx->q = q;
+  ctx->s = q - 1;
+  ctx->nplanes = planes_for_q(q);
+  ctx->Mpad = (M + GDCA_TILE - 1) / GDCA_TILE * GDCA_TILE;
+  ctx->nwords = (L + 31) / 32;
+  ctx->n = (int64_t)(q - 1) * L;
+  ctx->npad = (ctx->n + GDCA_NB - 1) / GDCA_NB * GDCA_NB;
+  ctx->stats.L = L;
+  ctx->stats.M = M;
+  ctx->stats.n = ctx->n;
+  ctx->stats.q = q;
+}
+
+int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
+  // q = max(Z)  (src/GaussDCA.jl:25-26)
+  ctx->L = L;
+  ctx->M = M;
+  GDCA_TRY(gdca_k_maxq(ctx));
+  int q = 0;
+  GDCA_CUDA(ctx, cudaMemcpyAsync(&q, ctx->dQ, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (q >= 32) {
+    char b[96];
+    snprintf(b, sizeof b, "parameter q=%d is too big (max 31 is allowed)", q);
+    ctx->err = b;
+    return GDCA_ERR_Q_TOO_BIG;
+  }
+  if (q < 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "alignment has q = max(Z) < 2: nothing to couple");
+  set_shape(ctx, L, M, q);
+  GDCA_TRY(gdca_k_pack(ctx));
+  ctx->have_alignment = true;
+  ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  return GDCA_OK;
+}
+
+int32_t check_LM(gdca_ctx *ctx, const void *Z, int64_t L, int64_t M) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!Z) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "Z is NULL");
+  if (L < 1 || M < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "alignment must have L >= 1 and M >= 1");
+  if (L >= 65536) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "L must be < 65536");
+  if (M >= (1ll << 31) - GDCA_TILE) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "M must be < 2^31");
+  return GDCA_OK;
+}
+
+// theta / weights on the loaded alignment.  theta < 0 => :auto.
+int32_t weights_stage(gdca_ctx *ctx, double theta) {
+  gdca_stats_t &st = ctx->stats;
+  st.theta_passes = 0;
+  st.ident_sum = 0;
+  if (theta < 0) {
+    // speculative single sweep: estimate thresh from a 1/64 sample of the tiles, then count for
+    // thresh-1, thresh, thresh+1 while accumulating the exact hamming sum.
+    unsigned long long hs[2] = {0, 0};
+    const long long T = ctx->Mpad / GDCA_TILE;
+    int stride = (int)((T * (T + 1) / 2) / (64 * (long long)ctx->num_sms));
+    if (stride > 64) stride = 64;
+    int64_t guess = -1;
+    if (stride >= 2) {
+      GDCA_TRY(gdca_k_pair_pass(ctx, 0, 0, stride));
+      GDCA_CUDA(ctx, cudaMemcpyAsync(hs, ctx->dHam, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
+      GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (hs[1] > 0) {
+        const double np = (double)hs[1];
+        const double mean_ident = (np * (double)ctx->L - (double)hs[0]) / (double)ctx->L / np;
+        const double th = fmin(0.5, 0.38 * 0.32 / mean_ident);
+        guess = (int64_t)floor(th * (double)ctx->L);
+      }
+    }
+    if (guess >= 0) {
+      GDCA_TRY(gdca_k_pair_pass(ctx, 2, (int)guess, 1));
+      st.theta_passes = 1;
+    } else {
+      GDCA_TRY(gdca_k_pair_pass(ctx, 0, 0, 1));
+      st.theta_passes = 1;
+    }
+    GDCA_CUDA(ctx, cudaMemcpyAsync(hs, ctx->dHam, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
+    GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double th;
+    int64_t thresh;
+    uint64_t ident;
+    GDCA_TRY(gdca_theta_from_ham_sum(ctx->L, ctx->M, hs[0], &th, &thresh, &ident));
+    st.theta = th;
+    st.thresh = thresh;
+    st.ident_sum = ident;
+    GDCA_TRY(rec(ctx, EV_THETA));
+    if (guess >= 0 && thresh >= guess - 1 && thresh <= guess + 1) {
+      GDCA_TRY(gdca_k_finish_weights(ctx, (int)(thresh - (guess - 1))));
+    } else {
+      GDCA_TRY(gdca_k_pair_pass(ctx, 1, (int)thresh, 1));
+      st.theta_passes += 1;
+      GDCA_TRY(gdca_k_finish_weights(ctx, 0));
+    }
+  } else {
+    st.theta = theta;
+    GDCA_TRY(rec(ctx, EV_THETA));
+    if (theta == 0.0) {
+      st.thresh = 0;
+      GDCA_TRY(gdca_k_finish_weights(ctx, -1));
+    } else {
+      st.thresh = (int64_t)floor(theta * (double)ctx->L);
+      GDCA_TRY(gdca_k_pair_pass(ctx, 1, (int)st.thresh, 1));
+      GDCA_TRY(gdca_k_finish_weights(ctx, 0));
+    }
+  }
+  st.meff = ctx->meff;
+  GDCA_TRY(rec(ctx, EV_WEIGHTS));
+  return GDCA_OK;
+}
+
+float ev_ms(gdca_ctx *ctx, int a, int b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) {
+    cudaGetLastError();
+    return 0.f;
+  }
+  return ms;
+}
+
+int32_t upload_padded(gdca_ctx *ctx, double *dst, int64_t npad, const double *src_host, int64_t n) {
+  GDCA_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)npad * npad * sizeof(double), ctx->stream));
+  GDCA_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)npad * sizeof(double), src_host, (size_t)n * sizeof(double),
+                                   (size_t)n * sizeof(double), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  return GDCA_OK;
+}
+
+int32_t download_padded(gdca_ctx *ctx, double *dst_host, const double *src, int64_t npad, int64_t n) {
+  GDCA_CUDA(ctx, cudaMemcpy2DAsync(dst_host, (size_t)n * sizeof(double), src, (size_t)npad * sizeof(double),
+                                   (size_t)n * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GDCA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t gdca_abi_version(void) { return GDCA_ABI_VERSION; }
+
+const char *gdca_status_string(int32_t status) {
+  switch (status) {
+    case GDCA_OK: return "ok";
+    case GDCA_ERR_INVALID_ARG: return "invalid argument";
+    case GDCA_ERR_Q_TOO_BIG: return "q too big";
+    case GDCA_ERR_NOT_SPD: return "matrix is not positive definite";
+    case GDCA_ERR_CUDA: return "CUDA error";
+    case GDCA_ERR_OOM: return "out of device memory";
+    case GDCA_ERR_NO_DEVICE: return "no usable sm_100 device";
+    case GDCA_ERR_STATE: return "stage called out of order";
+    default: return "unknown status";
+  }
+}
+
+const char *gdca_last_error(const gdca_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t gdca_create(gdca_ctx **out, int32_t device) {
+  if (!out) return GDCA_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                     "); libgdca_b200 has no CPU fallback";
+    return GDCA_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "device ordinal out of range";
+    return GDCA_ERR_INVALID_ARG;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return GDCA_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    char b[160];
+    snprintf(b, sizeof b, "device %d is sm_%d%d; libgdca_b200 is built for sm_100a only (no fallback)", device, prop.major,
+             prop.minor);
+    g_create_error = b;
+    return GDCA_ERR_NO_DEVICE;
+  }
+  gdca_ctx *ctx = new (std::nothrow) gdca_ctx();
+  if (!ctx) return GDCA_ERR_OOM;
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  auto fail = [&](cudaError_t err) {
+    g_create_error = cudaGetErrorString(err);
+    delete ctx;
+    return GDCA_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dHam, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dQ, sizeof(int))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dMeff, 2 * sizeof(double))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dInfo, sizeof(int))) != cudaSuccess) return fail(e);
+  for (int i = 0; i < EV_COUNT; ++i)
+    if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return fail(e);
+  *out = ctx;
+  return GDCA_OK;
+}
+
+void gdca_destroy(gdca_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (!ctx->dZ_borrowed) cudaFree(ctx->dZ);
+  void *bufs[] = {ctx->dZt,  ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
+                  ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
+                  ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR};
+  for (void *b : bufs)
+    if (b) cudaFree(b);
+  for (int i = 0; i < EV_COUNT; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int32_t gdca_set_shard(gdca_ctx *ctx, int32_t rank, int32_t world) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (world < 1 || rank < 0 || rank >= world) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_shard: need 0 <= rank < world");
+  ctx->shard_rank = rank;
+  ctx->shard_world = world;
+  return GDCA_OK;
+}
+
+int64_t gdca_ranking_length(int64_t L, int64_t min_separation) {
+  const int64_t d = L - min_separation;
+  return d > 0 ? d * (d + 1) / 2 : 0;
+}
+
+int32_t gdca_theta_from_ham_sum(int64_t L, int64_t M, uint64_t ham_sum, double *theta, int64_t *thresh,
+                                uint64_t *ident_sum) {
+  if (L < 1 || M < 2) return GDCA_ERR_INVALID_ARG;
+  const uint64_t npairs = (uint64_t)M * (uint64_t)(M - 1) / 2;
+  const uint64_t ident = npairs * (uint64_t)L - ham_sum;
+  // same IEEE operations, same order, as oracle theta_from_ident_sum
+  const double meanfracid = ((double)ident / (double)L) / (0.5 * (double)M * (double)(M - 1));
+  const double th = fmin(0.5, 0.38 * 0.32 / meanfracid);
+  if (theta) *theta = th;
+  if (thresh) *thresh = (int64_t)floor(th * (double)L);
+  if (ident_sum) *ident_sum = ident;
+  return GDCA_OK;
+}
+
+// ------------------------------------------------------------------ device-resident stages
+int32_t gdca_dev_load(gdca_ctx *ctx, const int8_t *Z_host, int64_t L, int64_t M) {
+  GDCA_TRY(check_LM(ctx, Z_host, L, M));
+  GDCA_TRY(set_device(ctx));
+  if (ctx->dZ_borrowed) {
+    ctx->dZ = nullptr;
+    ctx->capZ = 0;
+    ctx->dZ_borrowed = false;
+  }
+  GDCA_TRY(rec(ctx, EV_BEGIN));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dZ, ctx->capZ, (size_t)L * M + 16));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dZ, Z_host, (size_t)L * M, cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_TRY(rec(ctx, EV_H2D));
+  GDCA_TRY(load_common(ctx, L, M));
+  GDCA_TRY(rec(ctx, EV_PACK));
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_load_resident(gdca_ctx *ctx, const int8_t *Z_dev, int64_t L, int64_t M) {
+  GDCA_TRY(check_LM(ctx, Z_dev, L, M));
+  GDCA_TRY(set_device(ctx));
+  if (!ctx->dZ_borrowed && ctx->dZ) {
+    GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GDCA_CUDA(ctx, cudaFree(ctx->dZ));
+  }
+  ctx->dZ = const_cast<int8_t *>(Z_dev);
+  ctx->capZ = 0;
+  ctx->dZ_borrowed = true;
+  GDCA_TRY(rec(ctx, EV_BEGIN));
+  GDCA_TRY(rec(ctx, EV_H2D));
+  GDCA_TRY(load_common(ctx, L, M));
+  GDCA_TRY(rec(ctx, EV_PACK));
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_pair_pass(gdca_ctx *ctx, int32_t mode, int64_t thresh) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  return gdca_k_pair_pass(ctx, mode, (int)thresh, 1);
+}
+
+int32_t gdca_dev_pair_sample(gdca_ctx *ctx, int32_t stride) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  return gdca_k_pair_pass(ctx, 0, 0, stride);
+}
+
+void *gdca_dev_ham_sum_ptr(gdca_ctx *ctx) { return ctx ? ctx->dHam : nullptr; }
+void *gdca_dev_counts_ptr(gdca_ctx *ctx) { return ctx ? ctx->dCounts : nullptr; }
+int64_t gdca_dev_counts_stride(gdca_ctx *ctx) { return ctx ? ctx->Mpad : 0; }
+void *gdca_dev_C_ptr(gdca_ctx *ctx) { return ctx ? ctx->dC : nullptr; }
+void *gdca_dev_mJ_ptr(gdca_ctx *ctx) { return ctx ? ctx->dmJ : nullptr; }
+void *gdca_dev_S_ptr(gdca_ctx *ctx) { return ctx ? ctx->dS2 : nullptr; }
+void *gdca_dev_W_ptr(gdca_ctx *ctx) { return ctx ? ctx->dW : nullptr; }
+void *gdca_dev_stream(gdca_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int64_t gdca_dev_kernel_launches(gdca_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t gdca_dev_npad(gdca_ctx *ctx) { return ctx ? ctx->npad : 0; }
+
+int32_t gdca_dev_finish_weights(gdca_ctx *ctx, int32_t which, double *meff) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  GDCA_TRY(gdca_k_finish_weights(ctx, which));
+  ctx->stats.meff = ctx->meff;
+  if (meff) *meff = ctx->meff;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_set_weights(gdca_ctx *ctx, const double *W_host, double meff) {
+  if (!ctx || !W_host) return GDCA_ERR_INVALID_ARG;
+  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "set_weights: no alignment loaded");
+  GDCA_TRY(set_device(ctx));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dW, ctx->capW, (size_t)ctx->Mpad));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dW, W_host, (size_t)ctx->M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const double mm[2] = {meff, 0.0};
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dMeff, mm, sizeof mm, cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->meff = meff;
+  ctx->stats.meff = meff;
+  ctx->have_weights = true;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_covariance(gdca_ctx *ctx, double pseudocount) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!(pseudocount >= 0.0 && pseudocount <= 1.0))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid pseudocount value (must be between 0 and 1)");
+  GDCA_TRY(set_device(ctx));
+  return gdca_k_covariance(ctx, pseudocount);
+}
+
+int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  if (!ctx->have_cov) return gdca_fail(ctx, GDCA_ERR_STATE, "inverse: covariance not computed");
+  GDCA_TRY(gdca_k_symmetrize_C(ctx));
+  const int32_t st = gdca_k_inverse(ctx);
+  if (info) *info = ctx->stats.posdef_info;
+  return st;
+}
+
+int32_t gdca_dev_score_rank(gdca_ctx *ctx, int32_t score, int64_t min_separation, gdca_rank_t *R_host, int64_t R_len) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  GDCA_TRY(gdca_k_score(ctx, score));
+  GDCA_TRY(gdca_k_apc(ctx));
+  GDCA_TRY(gdca_k_rank(ctx, min_separation, R_len));
+  if (R_host && R_len > 0) {
+    GDCA_CUDA(ctx, cudaMemcpyAsync(R_host, ctx->dR, (size_t)R_len * sizeof(gdca_rank_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_sync(gdca_ctx *ctx) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_copy_to_host(gdca_ctx *ctx, void *dst_host, const void *src_dev, int64_t nbytes) {
+  if (!ctx || !dst_host || !src_dev || nbytes < 0) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_get_stats(gdca_ctx *ctx, gdca_stats_t *stats) {
+  if (!ctx || !stats) return GDCA_ERR_INVALID_ARG;
+  *stats = ctx->stats;
+  return GDCA_OK;
+}
+
+// ------------------------------------------------------------------ fused run
+int32_t gdca_run(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, double pseudocount, int32_t score,
+                 int64_t min_separation, gdca_rank_t *R, int64_t R_len, gdca_stats_t *stats) {
+  GDCA_TRY(check_LM(ctx, Z, L, M));
+  // the reference's check_arguments ranges (src/GaussDCA.jl:49-65); theta < 0 encodes :auto
+  if (!(pseudocount >= 0.0 && pseudocount <= 1.0))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid pseudocount value (must be between 0 and 1)");
+  if (!(theta < 0.0) && !(theta >= 0.0 && theta <= 1.0))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid theta value (must be :auto, or a number between 0 and 1)");
+  if (score != GDCA_SCORE_FROB && score != GDCA_SCORE_DI)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid score value (must be either :DI or :frob)");
+  if (min_separation < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid min_separation value (must be >= 1)");
+  if (R_len != gdca_ranking_length(L, min_separation))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R_len != (L-min_separation)*(L-min_separation+1)/2");
+  if (R_len > 0 && !R) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R is NULL");
+  if (M < 2 && theta < 0) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "theta = :auto needs at least 2 sequences");
+  ctx->stats = gdca_stats_t{};
+  const int32_t saved_rank = ctx->shard_rank, saved_world = ctx->shard_world;
+  ctx->shard_rank = 0;
+  ctx->shard_world = 1;
+  auto body = [&]() -> int32_t {
+    GDCA_TRY(gdca_dev_load(ctx, Z, L, M));
+    GDCA_TRY(weights_stage(ctx, theta));
+    GDCA_TRY(gdca_k_covariance(ctx, pseudocount));
+    GDCA_TRY(gdca_k_symmetrize_C(ctx));
+    GDCA_TRY(rec(ctx, EV_COV));
+    GDCA_TRY(gdca_k_inverse(ctx));
+    GDCA_TRY(rec(ctx, EV_CHOL));
+    GDCA_TRY(gdca_k_score(ctx, score));
+    GDCA_TRY(rec(ctx, EV_SCORE));
+    GDCA_TRY(gdca_k_apc(ctx));
+    GDCA_TRY(rec(ctx, EV_APC));
+    GDCA_TRY(gdca_k_rank(ctx, min_separation, R_len));
+    GDCA_TRY(rec(ctx, EV_RANK));
+    if (R_len > 0)
+      GDCA_CUDA(ctx, cudaMemcpyAsync(R, ctx->dR, (size_t)R_len * sizeof(gdca_rank_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GDCA_TRY(rec(ctx, EV_D2H));
+    GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GDCA_OK;
+  };
+  const int32_t status = body();
+  ctx->shard_rank = saved_rank;
+  ctx->shard_world = saved_world;
+  gdca_stats_t &st = ctx->stats;
+  if (status == GDCA_OK) {
+    st.ms_h2d = ev_ms(ctx, EV_BEGIN, EV_H2D);
+    st.ms_pack = ev_ms(ctx, EV_H2D, EV_PACK);
+    st.ms_theta = ev_ms(ctx, EV_PACK, EV_THETA);
+    st.ms_weights = ev_ms(ctx, EV_THETA, EV_WEIGHTS);
+    st.ms_cov = ev_ms(ctx, EV_WEIGHTS, EV_COV);
+    st.ms_chol = ev_ms(ctx, EV_COV, EV_CHOL);
+    st.ms_inv = 0.f;
+    st.ms_score = ev_ms(ctx, EV_CHOL, EV_SCORE);
+    st.ms_apc = ev_ms(ctx, EV_SCORE, EV_APC);
+    st.ms_rank = ev_ms(ctx, EV_APC, EV_RANK);
+    st.ms_d2h = ev_ms(ctx, EV_RANK, EV_D2H);
+    st.ms_total = ev_ms(ctx, EV_BEGIN, EV_D2H);
+  }
+  if (stats) *stats = st;
+  return status;
+}
+
+// ------------------------------------------------------------------ staged, host buffers
+int32_t gdca_compute_weights(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, int32_t *counts,
+                             double *W, double *meff, double *theta_used, int64_t *thresh, uint64_t *ident_sum) {
+  GDCA_TRY(check_LM(ctx, Z, L, M));
+  if (!(theta < 0.0) && !(theta >= 0.0 && theta <= 1.0))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid theta value (must be :auto, or a number between 0 and 1)");
+  if (M < 2 && theta < 0) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "theta = :auto needs at least 2 sequences");
+  ctx->stats = gdca_stats_t{};
+  GDCA_TRY(gdca_dev_load(ctx, Z, L, M));
+  GDCA_TRY(weights_stage(ctx, theta));
+  if (W) GDCA_CUDA(ctx, cudaMemcpyAsync(W, ctx->dW, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (counts) {
+    if (ctx->counts_row < 0) {
+      for (int64_t k = 0; k < M; ++k) counts[k] = 1;
+    } else {
+      GDCA_CUDA(ctx, cudaMemcpy(counts, ctx->dCounts + (size_t)ctx->counts_row * ctx->Mpad, (size_t)M * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost));
+      for (int64_t k = 0; k < M; ++k) counts[k] += 1;  // the sequence itself
+    }
+  }
+  if (meff) *meff = ctx->stats.meff;
+  if (theta_used) *theta_used = ctx->stats.theta;
+  if (thresh) *thresh = ctx->stats.thresh;
+  if (ident_sum) *ident_sum = ctx->stats.ident_sum;
+  return GDCA_OK;
+}
+
+int32_t gdca_compute_covariance(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, const double *W, double meff,
+                                double pseudocount, double *C, double *Pi, int32_t *q_out) {
+  GDCA_TRY(check_LM(ctx, Z, L, M));
+  if (!W || !C) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "W and C must not be NULL");
+  if (!(pseudocount >= 0.0 && pseudocount <= 1.0))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid pseudocount value (must be between 0 and 1)");
+  GDCA_TRY(gdca_dev_load(ctx, Z, L, M));
+  GDCA_TRY(gdca_dev_set_weights(ctx, W, meff));
+  GDCA_TRY(gdca_k_covariance(ctx, pseudocount));
+  GDCA_TRY(gdca_k_symmetrize_C(ctx));
+  if (Pi) GDCA_CUDA(ctx, cudaMemcpyAsync(Pi, ctx->dPi, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_TRY(download_padded(ctx, C, ctx->dC, ctx->npad, ctx->n));
+  if (q_out) *q_out = ctx->q;
+  return GDCA_OK;
+}
+
+int32_t gdca_inverse(gdca_ctx *ctx, const double *C, int64_t n, double *mJ, int32_t *info) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!C || !mJ || n < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "inverse: C, mJ must not be NULL and n >= 1");
+  GDCA_TRY(set_device(ctx));
+  ctx->n = n;
+  ctx->npad = (n + GDCA_NB - 1) / GDCA_NB * GDCA_NB;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)ctx->npad * ctx->npad));
+  GDCA_TRY(upload_padded(ctx, ctx->dC, ctx->npad, C, n));
+  ctx->have_cov = true;
+  ctx->have_alignment = false;
+  const int32_t st = gdca_k_inverse(ctx);
+  if (info) *info = ctx->stats.posdef_info;
+  if (st != GDCA_OK) return st;
+  return download_padded(ctx, mJ, ctx->dmJ, ctx->npad, n);
+}
+
+int32_t gdca_score(gdca_ctx *ctx, const double *mJ, const double *C, int64_t n, int32_t q, int32_t score, double *S) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!mJ || !S) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "score: mJ and S must not be NULL");
+  if (q < 2 || q >= 32 || n < 1 || n % (q - 1) != 0)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "score: need 2 <= q <= 31 and n divisible by q-1");
+  if (score == GDCA_SCORE_DI && !C) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "score: DI needs C");
+  GDCA_TRY(set_device(ctx));
+  ctx->n = n;
+  ctx->npad = (n + GDCA_NB - 1) / GDCA_NB * GDCA_NB;
+  ctx->q = q;
+  ctx->s = q - 1;
+  ctx->L = n / (q - 1);
+  ctx->have_alignment = false;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dmJ, ctx->capmJ, (size_t)ctx->npad * ctx->npad));
+  GDCA_TRY(upload_padded(ctx, ctx->dmJ, ctx->npad, mJ, n));
+  if (score == GDCA_SCORE_DI) {
+    GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)ctx->npad * ctx->npad));
+    GDCA_TRY(upload_padded(ctx, ctx->dC, ctx->npad, C, n));
+    GDCA_TRY(gdca_k_extract_diag(ctx));
+  }
+  ctx->have_inv = true;
+  ctx->have_cov = false;
+  GDCA_TRY(gdca_k_score(ctx, score));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(S, ctx->dS, (size_t)ctx->L * ctx->L * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GDCA_OK;
+}
+
+int32_t gdca_apc(gdca_ctx *ctx, const double *S, int64_t L, double *S_out) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!S || !S_out || L < 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "apc: S, S_out must not be NULL and L >= 2");
+  GDCA_TRY(set_device(ctx));
+  ctx->L = L;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dS, ctx->capS, (size_t)L * L));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dS, S, (size_t)L * L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_TRY(gdca_k_apc(ctx));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(S_out, ctx->dS2, (size_t)L * L * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GDCA_OK;
+}
+
+int32_t gdca_ranking(gdca_ctx *ctx, const double *S, int64_t L, int64_t min_separation, gdca_rank_t *R, int64_t R_len) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!S || L < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "ranking: S must not be NULL and L >= 1");
+  if (R_len > 0 && !R) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R is NULL");
+  GDCA_TRY(set_device(ctx));
+  ctx->L = L;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dS2, ctx->capS2, (size_t)L * L));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dS2, S, (size_t)L * L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_TRY(gdca_k_rank(ctx, min_separation, R_len));
+  if (R_len > 0)
+    GDCA_CUDA(ctx, cudaMemcpyAsync(R, ctx->dR, (size_t)R_len * sizeof(gdca_rank_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GDCA_OK;
+}
+
+// ------------------------------------------------------------------ synthetic data, probes
+int32_t gdca_synth_alignment_dev(gdca_ctx *ctx, int8_t *Z_dev, int64_t L, int64_t M, uint64_t seed) {
+  GDCA_TRY(check_LM(ctx, Z_dev, L, M));
+  GDCA_TRY(set_device(ctx));
+  GDCA_TRY(gdca_k_synth(ctx, Z_dev, L, M, seed));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GDCA_OK;
+}
+
+int32_t gdca_synth_alignment(gdca_ctx *ctx, int8_t *Z_host, int64_t L, int64_t M, uint64_t seed) {
+  GDCA_TRY(check_LM(ctx, Z_host, L, M));
+  GDCA_TRY(set_device(ctx));
+  int8_t *tmp = nullptr;
+  GDCA_CUDA(ctx, cudaMalloc((void **)&tmp, (size_t)L * M));
+  int32_t st = gdca_k_synth(ctx, tmp, L, M, seed);
+  if (st == GDCA_OK) {
+    cudaError_t e = cudaMemcpyAsync(Z_host, tmp, (size_t)L * M, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = cudaGetErrorString(e);
+      st = GDCA_ERR_CUDA;
+    }
+  }
+  cudaFree(tmp);
+  return st;
+}
+
+int32_t gdca_probe_peaks(gdca_ctx *ctx, double *lop3_tops, double *popc_tops, double *dmma_tflops, double *dfma_tflops) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  return gdca_k_probe(ctx, lop3_tops, popc_tops, dmma_tflops, dfma_tflops);
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+// chol.cu -- K5: mJ = inv(cholesky(C))  (reference src/GaussDCA.jl:34: LAPACK dpotrf + dpotri + symmetrise).
+//
+// Hand-written blocked factorisation and inversion, FP64 throughout, all matrix products on the
+// FP64 tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4; tcgen05 has no FP64 kind):
+//
+//   potrf  right-looking, NB = 128:   A[k,k] -> L[k,k] and inv(L[k,k])        (one CTA, shared memory)
+//                                     L[I,k] = A[I,k] * inv(L[k,k])'          (GEMM, replaces TRSM)
+//                                     A[I,J] -= L[I,k] * L[J,k]'   (I>=J>k)   (GEMM, lower tiles only)
+//   trtri  X = L^-1 by recursive doubling: X21 = -X22 * (L21 * X11), batched over the diagonal;
+//          every level is two GEMMs with full-chip parallelism (no sequential column sweep).
+//   lauum  mJ = X' X, lower tiles only, k >= i (X is lower triangular), then mirrored.
+//
+// The matrix is padded to a multiple of 128 with an identity block, so no kernel here has edge
+// cases: inv([[C,0],[0,I]]) = [[inv(C),0],[0,I]].  All matrices are row-major with ld = npad.
+// A non-positive pivot records the 1-based order of the failing leading minor (PosDefException.info).
+#include "gdca_internal.cuh"
+
+namespace {
+
+constexpr int NB = GDCA_NB;  // 128
+constexpr int BK = 16;
+constexpr int GSTAGES = 3;
+constexpr int LDS_N = BK + 4;    // [row][k] tile stride (doubles): conflict-free 64-bit fragment loads
+constexpr int LDS_T = NB + 8;    // [k][row] tile stride
+constexpr int TILE_D = NB * LDS_N;  // 2560 doubles >= BK*LDS_T = 2176
+constexpr int GTHREADS = 256;
+
+enum : int {
+  G_LOWER_OUT = 1,  // skip output tiles strictly above the block diagonal
+  G_KBEG_N = 2,     // k starts at n0      (B operand lower triangular as [k][n])
+  G_KBEG_M = 4,     // k starts at m0      (A operand lower triangular as [k][m])
+  G_KEND_M = 8      // k ends at m0 + NB   (A operand lower triangular as [m][k])
+};
+
+struct GemmP {
+  const double *A, *B;
+  double *C;
+  long long lda, ldb, ldc;
+  long long strideA, strideB, strideC;  // per blockIdx.z
+  int m, n, k;
+  int flags;
+  double alpha, beta;
+};
+
+__device__ __forceinline__ void cp16(void *smem, const void *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// C[m x n] = beta*C + alpha * opA * opB,  opA(m,k) = AT ? A[k][m] : A[m][k],  opB(k,n) = BT ? B[k][n] : B[n][k]
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(GemmP p) {
+  extern __shared__ __align__(16) double sm[];
+  const int m0 = blockIdx.y * NB, n0 = blockIdx.x * NB;
+  if ((p.flags & G_LOWER_OUT) && n0 > m0) return;
+  int kbeg = 0, kend = p.k;
+  if (p.flags & G_KBEG_N) kbeg = max(kbeg, n0);
+  if (p.flags & G_KBEG_M) kbeg = max(kbeg, m0);
+  if (p.flags & G_KEND_M) kend = min(kend, m0 + NB);
+  const int nk = (kend - kbeg) / BK;
+
+  const double *A = p.A + blockIdx.z * p.strideA;
+  const double *B = p.B + blockIdx.z * p.strideB;
+  double *C = p.C + blockIdx.z * p.strideC;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;  // warp tile: rows wm*64.., cols wn*32..
+
+  auto load_stage = [&](int kt) {
+    if (kt < nk) {
+      const int k0 = kbeg + kt * BK;
+      double *As = sm + (size_t)(kt % GSTAGES) * 2 * TILE_D;
+      double *Bs = As + TILE_D;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int ch = tid + it * GTHREADS;  // 0..1023 chunks of 2 doubles
+        if (!AT) {
+          const int row = ch >> 3, cc = ch & 7;
+          cp16(As + row * LDS_N + cc * 2, A + (long long)(m0 + row) * p.lda + k0 + cc * 2);
+        } else {
+          const int row = ch >> 6, cc = ch & 63;
+          cp16(As + row * LDS_T + cc * 2, A + (long long)(k0 + row) * p.lda + m0 + cc * 2);
+        }
+        if (!BT) {
+          const int row = ch >> 3, cc = ch & 7;
+          cp16(Bs + row * LDS_N + cc * 2, B + (long long)(n0 + row) * p.ldb + k0 + cc * 2);
+        } else {
+          const int row = ch >> 6, cc = ch & 63;
+          cp16(Bs + row * LDS_T + cc * 2, B + (long long)(k0 + row) * p.ldb + n0 + cc * 2);
+        }
+      }
+    }
+    cp_commit();
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  load_stage(0);
+  load_stage(1);
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_wait<GSTAGES - 2>();
+    __syncthreads();
+    load_stage(kt + GSTAGES - 1);
+    const double *As = sm + (size_t)(kt % GSTAGES) * 2 * TILE_D;
+    const double *Bs = As + TILE_D;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[8], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+        a[mi] = AT ? As[(kk * 4 + c) * LDS_T + wm * 64 + mi * 8 + g] : As[(wm * 64 + mi * 8 + g) * LDS_N + kk * 4 + c];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+        b[ni] = BT ? Bs[(kk * 4 + c) * LDS_T + wn * 32 + ni * 8 + g] : Bs[(wn * 32 + ni * 8 + g) * LDS_N + kk * 4 + c];
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+  }
+  cp_wait<0>();
+
+  // epilogue: thread owns (row g, cols 2c,2c+1) of every 8x8 atom
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi) {
+    const long long row = m0 + wm * 64 + mi * 8 + g;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const long long col = n0 + wn * 32 + ni * 8 + 2 * c;
+      double2 *dst = reinterpret_cast<double2 *>(C + row * p.ldc + col);
+      double2 v;
+      v.x = p.alpha * acc[mi][ni][0];
+      v.y = p.alpha * acc[mi][ni][1];
+      if (p.beta != 0.0) {
+        const double2 old = *dst;
+        v.x += p.beta * old.x;
+        v.y += p.beta * old.y;
+      }
+      *dst = v;
+    }
+  }
+}
+
+// ---- diagonal block: A[k,k] (lower) -> inv(chol(A[k,k])) written to X[k,k] (lower, zeros above) ----
+constexpr int DT = 512;
+constexpr int DLD = NB + 1;
+
+__global__ void __launch_bounds__(DT) diag_block_kernel(const double *__restrict__ Akk, long long lda,
+                                                        double *__restrict__ Xkk, long long ldx, int col0,
+                                                        int n_true, int *__restrict__ info) {
+  extern __shared__ double S[];  // [NB][DLD]
+  __shared__ double colbuf[NB];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += DT) {
+    const int r = e >> 7, cc = e & 127;
+    S[r * DLD + cc] = (cc <= r) ? Akk[(long long)r * lda + cc] : 0.0;
+  }
+  __syncthreads();
+  // ---- unblocked right-looking Cholesky, lower ----
+  for (int j = 0; j < NB; ++j) {
+    const double d = S[j * DLD + j];
+    if (!(d > 0.0)) {  // also catches NaN
+      if (tid == 0 && col0 + j < n_true) atomicCAS(info, 0, col0 + j + 1);
+    }
+    const double sj = sqrt(d);
+    __syncthreads();  // everyone has read the pivot
+    for (int i = j + tid; i < NB; i += DT) S[i * DLD + j] = (i == j) ? sj : S[i * DLD + j] / sj;
+    __syncthreads();
+    // trailing update of the lower triangle: rows i > j, cols j < cc <= i
+    const int rem = NB - 1 - j;
+    for (int e = tid; e < rem * rem; e += DT) {
+      const int ii = e / rem, cj = e - ii * rem;
+      if (cj <= ii) {
+        const int i = j + 1 + ii, cc = j + 1 + cj;
+        S[i * DLD + cc] -= S[i * DLD + j] * S[cc * DLD + j];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- in-place inverse of the lower-triangular factor (columns right to left) ----
+  for (int j = NB - 1; j >= 0; --j) {
+    const double xjj = 1.0 / S[j * DLD + j];
+    // t_i = sum_{k=j+1..i} X[i][k] * L[k][j], i > j: 4 threads per row, strided over k
+    const int i = j + 1 + (tid >> 2), part = tid & 3;
+    double t = 0.0;
+    if (i < NB) {
+      for (int k = j + 1 + part; k <= i; k += 4) t += S[i * DLD + k] * S[k * DLD + j];
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    __syncthreads();  // all reads of column j done
+    if (i < NB && part == 0) colbuf[i] = -t * xjj;
+    if (tid == 0) colbuf[j] = xjj;
+    __syncthreads();
+    for (int r = j + tid; r < NB; r += DT) S[r * DLD + j] = colbuf[r];
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += DT) {
+    const int r = e >> 7, cc = e & 127;
+    Xkk[(long long)r * ldx + cc] = (cc <= r) ? S[r * DLD + cc] : 0.0;
+  }
+}
+
+__global__ void pad_identity_kernel(double *__restrict__ C, long long n, long long npad) {
+  const long long r = n + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < npad) C[r * npad + r] = 1.0;
+}
+
+// upper <- lower (plain mirror), 32x32 tiles
+__global__ void mirror_lower_kernel(double *__restrict__ A, long long n, long long ld) {
+  __shared__ double tile[32][33];
+  const int tr = blockIdx.y, tc = blockIdx.x;
+  if (tc > tr) return;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  for (int yy = ly; yy < 32; yy += 8) {
+    const long long rr = (long long)tr * 32 + yy, cc = (long long)tc * 32 + lx;
+    tile[yy][lx] = (rr < n && cc < n) ? A[rr * ld + cc] : 0.0;
+  }
+  __syncthreads();
+  for (int yy = ly; yy < 32; yy += 8) {
+    const long long rr = (long long)tc * 32 + yy, cc = (long long)tr * 32 + lx;  // transposed position
+    if (rr < n && cc < n && rr < cc) A[rr * ld + cc] = tile[lx][yy];
+  }
+}
+
+template <bool AT, bool BT>
+int32_t gemm(gdca_ctx *ctx, const GemmP &p, int batch) {
+  if (p.m <= 0 || p.n <= 0 || batch <= 0) return GDCA_OK;
+  static bool configured = false;
+  const size_t smem = (size_t)GSTAGES * 2 * TILE_D * sizeof(double);
+  if (!configured) {
+    GDCA_CUDA(ctx, cudaFuncSetAttribute(dgemm_kernel<AT, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((unsigned)(p.n / NB), (unsigned)(p.m / NB), (unsigned)batch);
+  dgemm_kernel<AT, BT><<<grid, GTHREADS, smem, ctx->stream>>>(p);
+  GDCA_LAUNCH_CHECK(ctx);
+  return GDCA_OK;
+}
+
+}  // namespace
+
+int32_t gdca_k_inverse(gdca_ctx *ctx) {
+  if (!ctx->have_cov) return gdca_fail(ctx, GDCA_ERR_STATE, "inverse: covariance not computed");
+  const long long np = ctx->npad, n = ctx->n;
+  const int nb = (int)(np / NB);
+  GDCA_TRY(gdca_reserve(ctx, ctx->dX, ctx->capX, (size_t)np * np));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dT, ctx->capT, (size_t)np * np));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dmJ, ctx->capmJ, (size_t)np * np));
+  double *A = ctx->dC, *X = ctx->dX, *T = ctx->dT, *J = ctx->dmJ;
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dInfo, 0, sizeof(int), ctx->stream));
+  GDCA_CUDA(ctx, cudaMemsetAsync(X, 0, (size_t)np * np * sizeof(double), ctx->stream));
+  if (np > n) {
+    pad_identity_kernel<<<(unsigned)((np - n + 127) / 128), 128, 0, ctx->stream>>>(A, n, np);
+    GDCA_LAUNCH_CHECK(ctx);
+  }
+  const size_t dsmem = (size_t)NB * DLD * sizeof(double);
+  static bool dconf = false;
+  if (!dconf) {
+    GDCA_CUDA(ctx, cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+    dconf = true;
+  }
+  auto blk = [&](double *base, int I, int Jb) { return base + ((long long)I * NB) * np + (long long)Jb * NB; };
+
+  // ---------------- potrf ----------------
+  for (int k = 0; k < nb; ++k) {
+    diag_block_kernel<<<1, DT, dsmem, ctx->stream>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
+    GDCA_LAUNCH_CHECK(ctx);
+    const int rem = nb - k - 1;
+    if (rem == 0) break;
+    GemmP p{};
+    // panel: L[I,k] = A[I,k] * X[k,k]'   (in place)
+    p.A = blk(A, k + 1, k); p.lda = np;
+    p.B = blk(X, k, k);     p.ldb = np;
+    p.C = blk(A, k + 1, k); p.ldc = np;
+    p.m = rem * NB; p.n = NB; p.k = NB; p.flags = 0; p.alpha = 1.0; p.beta = 0.0;
+    GDCA_TRY((gemm<false, false>(ctx, p, 1)));
+    // trailing: A[I,J] -= L[I,k] L[J,k]'  for I >= J > k
+    GemmP t{};
+    t.A = blk(A, k + 1, k); t.lda = np;
+    t.B = blk(A, k + 1, k); t.ldb = np;
+    t.C = blk(A, k + 1, k + 1); t.ldc = np;
+    t.m = rem * NB; t.n = rem * NB; t.k = NB; t.flags = G_LOWER_OUT; t.alpha = -1.0; t.beta = 1.0;
+    GDCA_TRY((gemm<false, false>(ctx, t, 1)));
+  }
+
+  // ---------------- trtri by recursive doubling ----------------
+  for (int h = 1; h < nb; h *= 2) {
+    // groups start at g = 0, 2h, 4h, ...; top = [g, g+h), bottom = [g+h, min(g+2h, nb))
+    const int ngroups_full = nb / (2 * h);            // groups whose bottom part is complete
+    const int rest = nb - ngroups_full * 2 * h;       // blocks left after the full groups
+    const long long gstride = (long long)2 * h * NB * (np + 1);  // along the diagonal
+    auto level = [&](int g0, int mb, int batch) -> int32_t {  // mb = bottom blocks
+      GemmP a{};
+      // T[bottom, top] = L[bottom, top] * X[top, top]         (B as [k][n], lower triangular: k >= n0)
+      a.A = blk(A, g0 + h, g0); a.lda = np; a.strideA = gstride;
+      a.B = blk(X, g0, g0);     a.ldb = np; a.strideB = gstride;
+      a.C = blk(T, g0 + h, g0); a.ldc = np; a.strideC = gstride;
+      a.m = mb * NB; a.n = h * NB; a.k = h * NB; a.flags = G_KBEG_N; a.alpha = 1.0; a.beta = 0.0;
+      GDCA_TRY((gemm<false, true>(ctx, a, batch)));
+      GemmP b{};
+      // X[bottom, top] = - X[bottom, bottom] * T[bottom, top] (A lower triangular: k < m0 + NB)
+      b.A = blk(X, g0 + h, g0 + h); b.lda = np; b.strideA = gstride;
+      b.B = blk(T, g0 + h, g0);     b.ldb = np; b.strideB = gstride;
+      b.C = blk(X, g0 + h, g0);     b.ldc = np; b.strideC = gstride;
+      b.m = mb * NB; b.n = h * NB; b.k = mb * NB; b.flags = G_KEND_M; b.alpha = -1.0; b.beta = 0.0;
+      GDCA_TRY((gemm<false, true>(ctx, b, batch)));
+      return GDCA_OK;
+    };
+    if (ngroups_full > 0) GDCA_TRY(level(0, h, ngroups_full));
+    if (rest > h) GDCA_TRY(level(ngroups_full * 2 * h, rest - h, 1));
+  }
+
+  // ---------------- lauum: mJ = X' X (lower tiles), then mirror ----------------
+  {
+    GemmP l{};
+    l.A = X; l.lda = np;
+    l.B = X; l.ldb = np;
+    l.C = J; l.ldc = np;
+    l.m = (int)np; l.n = (int)np; l.k = (int)np; l.flags = G_LOWER_OUT | G_KBEG_M; l.alpha = 1.0; l.beta = 0.0;
+    GDCA_TRY((gemm<true, true>(ctx, l, 1)));
+    const unsigned nt = (unsigned)((np + 31) / 32);
+    mirror_lower_kernel<<<dim3(nt, nt), 256, 0, ctx->stream>>>(J, np, np);
+    GDCA_LAUNCH_CHECK(ctx);
+  }
+  int info = 0;
+  GDCA_CUDA(ctx, cudaMemcpyAsync(&info, ctx->dInfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stats.posdef_info = info;
+  ctx->have_cov = false;  // dC now holds the factor, not C
+  if (info != 0) {
+    char b[128];
+    snprintf(b, sizeof b, "matrix is not positive definite; Cholesky factorization failed (info=%d)", info);
+    ctx->err = b;
+    return GDCA_ERR_NOT_SPD;
+  }
+  ctx->have_inv = true;
+  return GDCA_OK;
+}

@@ -1,0 +1,267 @@
+// cov.cu -- K4: weighted two-point frequencies + pseudocount + covariance, fused.
+//
+// Replaces, in one pass over the alignment:
+//   DCAUtils compute_freqs   (Pi_true, Pij_true; un-vendored, reference call site src/GaussDCA.jl:28)
+//   DCAUtils add_pseudocount (call site src/GaussDCA.jl:30)
+//   compute_C(Pi, Pij) = Pij - Pi*Pi'            (src/GaussDCA.jl:32,76)
+//
+// Pij_true = X' W X / Meff with X the M x n one-hot matrix.  As a dense FP64 contraction that is
+// M*n^2 = 2e13 flop at L=500, M=200k (0.5 s at DMMA peak) -- but X has exactly one 1 per site, so only
+// 1/400 of the products are non-zero.  This kernel does the M*L^2/2 = 2.5e10 useful additions directly:
+//
+//   1. per site i, sequence ids are grouped by the state at i (stable counting sort -> list(i,a));
+//   2. one CTA owns output row (i,a) x a chunk of 128 sites j; thread t owns site j.  For every k in
+//      list(i,a) it adds W[k] to a PRIVATE shared-memory accumulator acc[Z[j,k]][t].  No atomics, no
+//      bank conflicts (thread t always hits bank pair t mod 16), every element is summed in ascending
+//      sequence order, so the result is deterministic and bit-identical for (r,c) and (c,r);
+//   3. the epilogue applies 1/Meff, the pseudocount mix and "- Pi Pi'" and writes the row chunk.
+//
+// Only site blocks j >= i are computed; symmetrize_C mirrors them.  The bound is shared-memory
+// bandwidth (one 8-byte read-modify-write per addition), not the FP64 pipe and not HBM.
+#include "gdca_internal.cuh"
+
+namespace {
+
+constexpr int JT = 128;      // sites (threads) per covariance CTA
+constexpr int LB = 256;      // threads of the list-building CTA
+constexpr int NSTATE = 32;   // states are 1..31 (q <= 31)
+
+// ---- Z [M][L]  ->  Zt [L][M]  (site-major) so one site's column can be streamed coalesced ----
+__global__ void transpose_Z_kernel(const int8_t *__restrict__ Z, long long L, long long M, int8_t *__restrict__ Zt) {
+  __shared__ int8_t tile[64][65];
+  const long long k0 = (long long)blockIdx.x * 64, i0 = (long long)blockIdx.y * 64;
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    const int kk = e >> 6, ii = e & 63;
+    if (k0 + kk < M && i0 + ii < L) tile[kk][ii] = Z[(k0 + kk) * L + i0 + ii];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    const int ii = e >> 6, kk = e & 63;
+    if (k0 + kk < M && i0 + ii < L) Zt[(i0 + ii) * M + k0 + kk] = tile[kk][ii];
+  }
+}
+
+// ---- per-site stable counting sort of sequence ids by state ----
+__global__ void __launch_bounds__(LB) build_lists_kernel(const int8_t *__restrict__ Zt, long long M,
+                                                         int32_t *__restrict__ list, int32_t *__restrict__ listoff) {
+  __shared__ int hist[NSTATE];
+  __shared__ int running[NSTATE];
+  __shared__ int wcnt[LB / 32][NSTATE];
+  const long long i = blockIdx.x;
+  const int8_t *z = Zt + i * M;
+  int32_t *out = list + i * M;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < NSTATE) hist[tid] = 0;
+  __syncthreads();
+  for (long long k = tid; k < M; k += LB) atomicAdd(&hist[(unsigned)z[k] & 31u], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int v = 0; v < NSTATE; ++v) {
+      running[v] = run;
+      listoff[i * (NSTATE + 1) + v] = run;
+      run += hist[v];
+    }
+    listoff[i * (NSTATE + 1) + NSTATE] = run;
+  }
+  for (long long base = 0; base < M; base += LB) {
+    (&wcnt[0][0])[tid] = 0;  // LB == (LB/32)*NSTATE
+    __syncthreads();
+    const long long k = base + tid;
+    const bool valid = k < M;
+    const unsigned v = valid ? ((unsigned)z[k] & 31u) : 32u + (unsigned)lane;  // invalid lanes match nobody
+    const unsigned m = __match_any_sync(0xffffffffu, v);
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    if (valid && rank == 0) wcnt[warp][v] = __popc(m);
+    __syncthreads();
+    if (valid) {
+      int pos = running[v] + rank;
+      for (int w = 0; w < warp; ++w) pos += wcnt[w][v];
+      out[pos] = (int32_t)k;
+    }
+    __syncthreads();
+    if (tid < NSTATE) {
+      int add = 0;
+#pragma unroll
+      for (int w = 0; w < LB / 32; ++w) add += wcnt[w][tid];
+      running[tid] += add;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- Pi[(i,a)] = (1-pc) * sum_{k in list(i,a)} W[k] / Meff + pc/q  (deterministic tree) ----
+__global__ void __launch_bounds__(256) pi_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ listoff,
+                                                 const double *__restrict__ W, const double *__restrict__ meff,
+                                                 long long M, int q, double pc, double *__restrict__ Pi) {
+  const long long i = blockIdx.x;
+  const int s = q - 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double Meff = meff[0];
+  for (int a = 1 + warp; a <= s; a += (int)(blockDim.x >> 5)) {
+    const int beg = listoff[i * (NSTATE + 1) + a], end = listoff[i * (NSTATE + 1) + a + 1];
+    const int32_t *l = list + i * M;
+    double acc = 0.0;
+    for (int e = beg + lane; e < end; e += 32) acc += W[l[e]];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) Pi[i * s + (a - 1)] = (1.0 - pc) * (acc / Meff) + pc / q;
+  }
+}
+
+struct CovParams {
+  const int8_t *Z;  // [M][L]
+  const int32_t *list, *listoff;
+  const double *W, *meff, *Pi;
+  double *C;  // [npad][npad], leading dimension ld
+  long long L, M, n, ld;
+  int q, s, nchunks;
+  int rank, world;
+  double pc;
+};
+
+constexpr int UNR = 8;
+
+__global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
+  extern __shared__ double acc[];  // [q][JT]; row s is the dump slot for state q / padding
+  const int r = blockIdx.y;        // output row (i, a)
+  const int i = r / P.s, a = r - i * P.s + 1;
+  const int jc = blockIdx.x;
+  if ((jc + 1) * JT <= i) return;                 // chunk entirely left of the diagonal block
+  if (P.world > 1 && (i % P.world) != P.rank) return;  // rows are dealt to ranks by site
+  const int t = threadIdx.x;
+  const long long j = (long long)jc * JT + t;
+  const bool jvalid = j < P.L;
+  for (int b = 0; b < P.q; ++b) acc[b * JT + t] = 0.0;
+  // (private columns: no barrier needed before the accumulation loop)
+
+  const int beg = P.listoff[(long long)i * (NSTATE + 1) + a], end = P.listoff[(long long)i * (NSTATE + 1) + a + 1];
+  const int32_t *l = P.list + (long long)i * P.M;
+  const int8_t *Zj = P.Z + (jvalid ? j : 0);
+  for (int base = beg; base < end; base += UNR) {
+    int k[UNR];
+    double w[UNR];
+    int st[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) k[u] = (base + u < end) ? l[base + u] : -1;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      w[u] = (k[u] >= 0) ? P.W[k[u]] : 0.0;
+      st[u] = (k[u] >= 0 && jvalid) ? (int)Zj[(long long)k[u] * P.L] : P.q;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int slot = (st[u] >= 1 && st[u] <= P.s) ? st[u] - 1 : P.s;
+      acc[slot * JT + t] += w[u];
+    }
+  }
+  __syncthreads();
+
+  // ---- epilogue: row r, columns (j, b) of this chunk, coalesced over (j, b) ----
+  const double Meff = P.meff[0];
+  const double pir = P.Pi[r];
+  const double pcq = P.pc / P.q, pcqq = pcq / P.q, omp = 1.0 - P.pc;
+  double *Crow = P.C + (long long)r * P.ld;
+  for (int e = t; e < JT * P.s; e += JT) {
+    const int jl = e / P.s, b = e - jl * P.s;
+    const long long jj = (long long)jc * JT + jl;
+    if (jj >= P.L || jj < i) continue;
+    const long long c = jj * P.s + b;
+    const double ptrue = acc[b * JT + jl] / Meff;
+    double pij;
+    if (jj == i)
+      pij = omp * ptrue + ((b == a - 1) ? pcq : 0.0);
+    else
+      pij = omp * ptrue + pcqq;
+    Crow[c] = pij - pir * P.Pi[c];
+  }
+}
+
+// lower site blocks <- transpose of the upper ones (diagonal blocks are already complete)
+__global__ void symmetrize_kernel(double *__restrict__ C, long long n, long long ld, int s) {
+  __shared__ double tile[32][33];
+  const int tr = blockIdx.y, tc = blockIdx.x;
+  if (tc > tr) return;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8
+  // load tile (tc, tr): rows tc*32.., cols tr*32..
+  for (int yy = ly; yy < 32; yy += 8) {
+    const long long rr = (long long)tc * 32 + yy, cc = (long long)tr * 32 + lx;
+    tile[yy][lx] = (rr < n && cc < n) ? C[rr * ld + cc] : 0.0;
+  }
+  __syncthreads();
+  for (int yy = ly; yy < 32; yy += 8) {
+    const long long rr = (long long)tr * 32 + yy, cc = (long long)tc * 32 + lx;
+    if (rr < n && cc < n && (rr / s) > (cc / s)) C[rr * ld + cc] = tile[lx][yy];
+  }
+}
+
+__global__ void extract_diag_blocks_kernel(const double *__restrict__ C, long long ld, int s, double *__restrict__ out) {
+  const long long i = blockIdx.x;
+  for (int e = threadIdx.x; e < s * s; e += blockDim.x) {
+    const int a = e / s, b = e - a * s;
+    out[i * s * s + e] = C[(i * s + a) * ld + i * s + b];
+  }
+}
+
+}  // namespace
+
+int32_t gdca_k_symmetrize_C(gdca_ctx *ctx) {
+  const long long n = ctx->n;
+  const unsigned nt = (unsigned)((n + 31) / 32);
+  symmetrize_kernel<<<dim3(nt, nt), 256, 0, ctx->stream>>>(ctx->dC, n, ctx->npad, ctx->s);
+  GDCA_LAUNCH_CHECK(ctx);
+  return gdca_k_extract_diag(ctx);
+}
+
+int32_t gdca_k_extract_diag(gdca_ctx *ctx) {
+  GDCA_TRY(gdca_reserve(ctx, ctx->dCdiag, ctx->capCdiag, (size_t)ctx->L * ctx->s * ctx->s));
+  extract_diag_blocks_kernel<<<(unsigned)ctx->L, 128, 0, ctx->stream>>>(ctx->dC, ctx->npad, ctx->s, ctx->dCdiag);
+  GDCA_LAUNCH_CHECK(ctx);
+  return GDCA_OK;
+}
+
+int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
+  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "covariance: no alignment loaded");
+  if (!ctx->have_weights) return gdca_fail(ctx, GDCA_ERR_STATE, "covariance: weights not computed");
+  const long long L = ctx->L, M = ctx->M, n = ctx->n;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dList, ctx->capList, (size_t)L * M));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dListOff, ctx->capListOff, (size_t)L * (NSTATE + 1)));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dPi, ctx->capPi, (size_t)n));
+  const long long npad = ctx->npad;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)npad * npad));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dZt, ctx->capZt, (size_t)L * M));
+  int8_t *Zt = ctx->dZt;
+
+  transpose_Z_kernel<<<dim3((unsigned)((M + 63) / 64), (unsigned)((L + 63) / 64)), 256, 0, ctx->stream>>>(ctx->dZ, L, M, Zt);
+  GDCA_LAUNCH_CHECK(ctx);
+  build_lists_kernel<<<(unsigned)L, LB, 0, ctx->stream>>>(Zt, M, ctx->dList, ctx->dListOff);
+  GDCA_LAUNCH_CHECK(ctx);
+  pi_kernel<<<(unsigned)L, 256, 0, ctx->stream>>>(ctx->dList, ctx->dListOff, ctx->dW, ctx->dMeff, M, ctx->q, pc, ctx->dPi);
+  GDCA_LAUNCH_CHECK(ctx);
+  // zero everything: padding rows/cols, the not-yet-mirrored lower part, and other shards' rows
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dC, 0, (size_t)npad * npad * sizeof(double), ctx->stream));
+
+  CovParams P;
+  P.Z = ctx->dZ;
+  P.list = ctx->dList;
+  P.listoff = ctx->dListOff;
+  P.W = ctx->dW;
+  P.meff = ctx->dMeff;
+  P.Pi = ctx->dPi;
+  P.C = ctx->dC;
+  P.L = L;
+  P.M = M;
+  P.n = n;
+  P.ld = npad;
+  P.q = ctx->q;
+  P.s = ctx->s;
+  P.nchunks = (int)((L + JT - 1) / JT);
+  P.rank = ctx->shard_rank;
+  P.world = ctx->shard_world;
+  P.pc = pc;
+  const size_t smem = (size_t)ctx->q * JT * sizeof(double);
+  cov_rows_kernel<<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
+  GDCA_LAUNCH_CHECK(ctx);
+  ctx->pseudocount = pc;
+  ctx->have_cov = true;
+  ctx->have_inv = false;
+  return GDCA_OK;
+}

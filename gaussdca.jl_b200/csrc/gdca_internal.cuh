@@ -1,0 +1,117 @@
+// gdca_internal.cuh -- shared declarations of the gDCA B200 library (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/gdca_b200.h"
+
+#define GDCA_NUM_SMS_DEFAULT 148
+#define GDCA_TILE 128          // sequences per pair-sweep tile edge
+#define GDCA_MAX_PLANES 5      // q <= 31  ->  5 bit planes
+#define GDCA_NB 128            // Cholesky / GEMM block
+
+struct gdca_ctx {
+  int device = 0;
+  int num_sms = GDCA_NUM_SMS_DEFAULT;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int32_t shard_rank = 0, shard_world = 1;
+  int64_t launches = 0;
+
+  // ---- problem state ----
+  int64_t L = 0, M = 0, Mpad = 0, n = 0, npad = 0;  // npad: n rounded up to the Cholesky block (ld of dC/dX/dT/dmJ)
+  int32_t q = 0, s = 0, nplanes = 0;
+  int64_t nwords = 0;  // ceil(L/32)
+
+  // ---- device buffers (grown on demand, never shrunk) ----
+  int8_t *dZ = nullptr;  size_t capZ = 0;      // [M][L] sequence-major (as uploaded)
+  bool dZ_borrowed = false;                    // dZ points at caller memory (load_resident)
+  int8_t *dZt = nullptr; size_t capZt = 0;     // [L][M] site-major copy (list building)
+  uint32_t *dPlanes = nullptr; size_t capPlanes = 0;  // [nwords][nplanes][Mpad]
+  int32_t *dCounts = nullptr; size_t capCounts = 0;   // [3][Mpad]
+  unsigned long long *dHam = nullptr;          // [2] sum of hamming distances, pairs visited
+  int *dQ = nullptr;                           // [1] max(Z)
+  double *dW = nullptr; size_t capW = 0;       // [M]
+  double *dMeff = nullptr;                     // [2] double-double
+  int32_t *dList = nullptr; size_t capList = 0;    // [L][M] sequence ids grouped by state at site
+  int32_t *dListOff = nullptr; size_t capListOff = 0;  // [L][32+1]
+  double *dPi = nullptr; size_t capPi = 0;     // [n] (with pseudocount)
+  double *dC = nullptr; size_t capC = 0;       // [npad][npad], padded with identity
+  double *dX = nullptr; size_t capX = 0;       // [npad][npad] L^-1
+  double *dmJ = nullptr; size_t capmJ = 0;     // [npad][npad]
+  double *dCdiag = nullptr; size_t capCdiag = 0;  // [L][s][s] diagonal blocks of C (for DI)
+  double *dT = nullptr; size_t capT = 0;       // [npad][npad] GEMM workspace (trtri)
+  int *dInfo = nullptr;                        // [1] not-SPD info
+  double *dS = nullptr; size_t capS = 0;       // [L][L] raw score
+  double *dS2 = nullptr; size_t capS2 = 0;     // [L][L] APC-corrected
+  double *dRed = nullptr; size_t capRed = 0;   // reductions for APC
+  unsigned long long *dKeys = nullptr; size_t capKeys = 0;
+  uint32_t *dVals = nullptr; size_t capVals = 0;
+  gdca_rank_t *dR = nullptr; size_t capR = 0;
+
+  // ---- state flags ----
+  bool have_alignment = false, have_weights = false, have_cov = false, have_inv = false;
+  double meff = 0.0, pseudocount = 0.0;
+  int counts_row = -1;  // row of dCounts the weights came from (-1: theta == 0)
+  gdca_stats_t stats{};
+  cudaEvent_t ev[16] = {};
+};
+
+#define GDCA_CUDA(ctx, expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      char _b[512];                                                                               \
+      snprintf(_b, sizeof _b, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      (ctx)->err = _b;                                                                            \
+      return (_e == cudaErrorMemoryAllocation) ? GDCA_ERR_OOM : GDCA_ERR_CUDA;                    \
+    }                                                                                             \
+  } while (0)
+
+#define GDCA_TRY(expr)                 \
+  do {                                 \
+    int32_t _s = (expr);               \
+    if (_s != GDCA_OK) return _s;      \
+  } while (0)
+
+#define GDCA_LAUNCH_CHECK(ctx)                    \
+  do {                                            \
+    (ctx)->launches++;                            \
+    GDCA_CUDA(ctx, cudaGetLastError());           \
+  } while (0)
+
+template <typename T>
+static inline int32_t gdca_reserve(gdca_ctx *ctx, T *&ptr, size_t &cap, size_t count) {
+  if (count <= cap && ptr) return GDCA_OK;
+  if (ptr) {
+    GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GDCA_CUDA(ctx, cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+  }
+  GDCA_CUDA(ctx, cudaMalloc((void **)&ptr, count * sizeof(T)));
+  cap = count;
+  return GDCA_OK;
+}
+
+static inline int32_t gdca_fail(gdca_ctx *ctx, int32_t status, const char *msg) {
+  if (ctx) ctx->err = msg;
+  return status;
+}
+
+// ---- stage entry points implemented across the .cu files ----
+int32_t gdca_k_maxq(gdca_ctx *ctx);                       // pack.cu: dQ <- max(Z)
+int32_t gdca_k_pack(gdca_ctx *ctx);                       // pack.cu: dZ -> dPlanes
+int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride);   // pairs.cu
+int32_t gdca_k_finish_weights(gdca_ctx *ctx, int which);  // weights.cu
+int32_t gdca_k_covariance(gdca_ctx *ctx, double pc);      // cov.cu
+int32_t gdca_k_symmetrize_C(gdca_ctx *ctx);               // cov.cu: mirror upper site blocks, save diag blocks
+int32_t gdca_k_extract_diag(gdca_ctx *ctx);               // cov.cu: save the s x s diagonal blocks of dC
+int32_t gdca_k_inverse(gdca_ctx *ctx);                    // chol.cu
+int32_t gdca_k_score(gdca_ctx *ctx, int score);           // score.cu
+int32_t gdca_k_apc(gdca_ctx *ctx);                        // rank.cu
+int32_t gdca_k_rank(gdca_ctx *ctx, int64_t min_sep, int64_t R_len);  // rank.cu
+int32_t gdca_k_synth(gdca_ctx *ctx, int8_t *Zdev, int64_t L, int64_t M, uint64_t seed);  // synth.cu
+int32_t gdca_k_probe(gdca_ctx *ctx, double *lop3, double *popc, double *dmma, double *dfma);  // probe.cu

@@ -1,0 +1,322 @@
+// pairs.cu -- K2/K3: the M x M pairwise-identity sweep (theta :auto and sequence weights).
+//
+// Replaces DCAUtils compute_theta and compute_weights (un-vendored; both reached from
+// compute_weighted_frequencies, reference call site src/GaussDCA.jl:28):
+//   theta  = min(0.5, 0.38*0.32 / meanfracid),  meanfracid = mean over k<l of ident(k,l)/L
+//   count[k] = 1 + #{l != k : hamming(k,l) < floor(theta*L)},  W[k] = 1/count[k]
+// ident = L - hamming, gap == gap counts as identical.  Everything here is exact integer work.
+//
+// Design (B200): INT32-ALU bound, not HBM bound -- the packed alignment (<= 64 MB at L=500, M=200k)
+// lives in L2.  The bit-plane layout of pack.cu makes 32 sites of one pair cost 5 LOP3 + 1 POPC + 1 ADD.
+//   * CTA tile 128 x 128 sequences, 256 threads, 8 x 8 register tile of pairs per thread.
+//   * operands staged through shared memory with cp.async, 3-stage ring, the ring runs across tile
+//     boundaries so the next tile's first chunk is already in flight during this tile's epilogue.
+//   * only tiles bi <= bj of the symmetric pair matrix are visited; a hit credits both sequences.
+//   * persistent grid (one CTA per SM), items strided over (rank, world) for multi-GPU sharding.
+//   * mode 2 evaluates thresh-1, thresh, thresh+1 and the hamming sum in ONE sweep, so theta=:auto
+//     needs a single pass when the sampled estimate of thresh is within +-1 of the exact one.
+#include "gdca_internal.cuh"
+
+namespace {
+
+constexpr int TILE = GDCA_TILE;  // 128
+constexpr int WC = 4;            // 32-site words per pipeline stage
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// linear item t in [0, T(T+1)/2)  ->  (bi, bj), bi <= bj, rows enumerated bi = 0..T-1
+__device__ __forceinline__ void item_to_tile(long long t, int T, int &bi, int &bj) {
+  // row bi starts at off(bi) = bi*T - bi*(bi-1)/2
+  double Td = (double)T + 0.5;
+  int b = (int)(Td - sqrt(Td * Td - 2.0 * (double)t));
+  if (b < 0) b = 0;
+  if (b > T - 1) b = T - 1;
+  while (true) {
+    long long off = (long long)b * T - (long long)b * (b - 1) / 2;
+    if (off > t) {
+      --b;
+      continue;
+    }
+    long long nxt = off + (T - b);
+    if (t >= nxt) {
+      ++b;
+      continue;
+    }
+    bi = b;
+    bj = b + (int)(t - off);
+    return;
+  }
+}
+
+struct PairParams {
+  const uint32_t *planes;
+  long long Mpad, M;
+  int nwords, nchunks, T;
+  long long n_items;   // T(T+1)/2
+  int rank, world;
+  int thresh;
+  int32_t *counts;     // [3][Mpad]
+  unsigned long long *ham_sum;  // [0] sum of hamming distances, [1] pairs visited
+};
+
+template <int NPL, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  // ring: [STAGES][2 operands][WC][NPL][TILE]
+  constexpr int OP_WORDS = WC * NPL * TILE;
+  constexpr int STAGE_WORDS = 2 * OP_WORDS;
+  __shared__ int s_row[3][TILE], s_col[3][TILE];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int ty = (warp >> 1) * 4 + (lane >> 3);  // 0..15 -> rows ty*4.. and 64+ty*4..
+  const int tx = (warp & 1) * 8 + (lane & 7);    // 0..15 -> cols tx*4.. and 64+tx*4..
+
+  // items of this CTA: local index it -> global item (blockIdx.x + it*gridDim.x)*world + rank
+  const long long my_first = (long long)blockIdx.x;
+  const long long per_rank_items = (P.n_items - P.rank + P.world - 1) / P.world;  // items t with t%world==rank
+  long long n_my = 0;
+  if (my_first < per_rank_items) n_my = (per_rank_items - my_first + gridDim.x - 1) / gridDim.x;
+  const long long n_flat = n_my * P.nchunks;
+
+  auto issue_load = [&](long long f) {
+    if (f < n_flat) {
+      const long long it = f / P.nchunks;
+      const int c = (int)(f - it * P.nchunks);
+      const long long t = (my_first + it * gridDim.x) * P.world + P.rank;
+      int bi, bj;
+      item_to_tile(t, P.T, bi, bj);
+      uint32_t *dst = smem + (size_t)(f % STAGES) * STAGE_WORDS;
+      // 2 operands x WC*NPL rows x 32 chunks of 16 bytes
+      constexpr int CHUNKS = 2 * WC * NPL * (TILE / 4);
+      for (int ch = tid; ch < CHUNKS; ch += NTHREADS) {
+        const int op = ch / (WC * NPL * (TILE / 4));
+        const int rem = ch - op * (WC * NPL * (TILE / 4));
+        const int row = rem / (TILE / 4);  // w*NPL + p within the chunk
+        const int col = rem - row * (TILE / 4);
+        const int w = c * WC + row / NPL;
+        const int p = row - (row / NPL) * NPL;
+        const bool valid = w < P.nwords;
+        const long long seq0 = (long long)(op == 0 ? bi : bj) * TILE + col * 4;
+        const uint32_t *src = P.planes + ((long long)(valid ? w : 0) * NPL + p) * P.Mpad + seq0;
+        cp_async16(dst + op * OP_WORDS + row * TILE + col * 4, src, valid);
+      }
+    }
+    cp_async_commit();
+  };
+
+  unsigned acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0;
+  unsigned long long ham_local = 0, pairs_local = 0;
+
+  for (int i = tid; i < 3 * TILE; i += NTHREADS) {
+    (&s_row[0][0])[i] = 0;
+    (&s_col[0][0])[i] = 0;
+  }
+
+  issue_load(0);
+  issue_load(1);
+
+  for (long long f = 0; f < n_flat; ++f) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();            // stage f landed for everyone; everyone is done with stage f-1
+    issue_load(f + STAGES - 1); // refill the slot freed by f-1
+
+    const uint32_t *A = smem + (size_t)(f % STAGES) * STAGE_WORDS;
+    const uint32_t *B = A + OP_WORDS;
+#pragma unroll
+    for (int w = 0; w < WC; ++w) {
+      unsigned x[8][8];
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) {
+        const uint4 a0 = *reinterpret_cast<const uint4 *>(A + (w * NPL + p) * TILE + ty * 4);
+        const uint4 a1 = *reinterpret_cast<const uint4 *>(A + (w * NPL + p) * TILE + 64 + ty * 4);
+        const uint4 b0 = *reinterpret_cast<const uint4 *>(B + (w * NPL + p) * TILE + tx * 4);
+        const uint4 b1 = *reinterpret_cast<const uint4 *>(B + (w * NPL + p) * TILE + 64 + tx * 4);
+        const unsigned a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const unsigned b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[i][j] = (p == 0) ? (a[i] ^ b[j]) : (x[i][j] | (a[i] ^ b[j]));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += __popc(x[i][j]);
+    }
+
+    const long long it = f / P.nchunks;
+    if (f - it * P.nchunks == P.nchunks - 1) {
+      // ---- tile epilogue: acc[i][j] = hamming(row r_i, col c_j) ----
+      const long long t = (my_first + it * gridDim.x) * P.world + P.rank;
+      int bi, bj;
+      item_to_tile(t, P.T, bi, bj);
+      const bool diag = (bi == bj);
+      int rh[3][8], chh[3][8];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rh[k][i] = 0, chh[k][i] = 0;
+      unsigned any = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+        const long long gr = (long long)bi * TILE + rl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int cl = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+          const long long gc = (long long)bj * TILE + cl;
+          const bool valid = (gr < P.M) && (gc < P.M) && (!diag || rl < cl);
+          const int d = (int)acc[i][j];
+          if (MODE == 0 || MODE == 2) {
+            ham_local += valid ? (unsigned)d : 0u;
+            pairs_local += valid ? 1u : 0u;
+          }
+          if (MODE == 1) {
+            const int h = (valid && d < P.thresh) ? 1 : 0;
+            rh[0][i] += h;
+            chh[0][j] += h;
+            any |= h;
+          }
+          if (MODE == 2) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const int h = (valid && d < P.thresh - 1 + k) ? 1 : 0;
+              rh[k][i] += h;
+              chh[k][j] += h;
+              any |= h;
+            }
+          }
+          acc[i][j] = 0;
+        }
+      }
+      if (MODE != 0) {
+        // most tiles contain no neighbour pair at all: skip the reduction entirely then
+        const int block_any = __syncthreads_or((int)any);
+        if (block_any) {
+          constexpr int NK = (MODE == 2) ? 3 : 1;
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              int v = rh[k][i];  // same rows across the 8 lanes sharing lane>>3
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              const int rl = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+              if ((lane & 7) == 0 && v) atomicAdd(&s_row[k][rl], v);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              int v = chh[k][j];  // same cols across the 4 lanes sharing lane&7
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              const int cl = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+              if ((lane >> 3) == 0 && v) atomicAdd(&s_col[k][cl], v);
+            }
+          }
+          __syncthreads();
+          for (int e = tid; e < NK * 2 * TILE; e += NTHREADS) {
+            const int k = e / (2 * TILE);
+            const int r = e - k * 2 * TILE;
+            if (r < TILE) {
+              const int v = s_row[k][r];
+              if (v) {
+                atomicAdd(P.counts + (long long)k * P.Mpad + (long long)bi * TILE + r, v);
+                s_row[k][r] = 0;
+              }
+            } else {
+              const int v = s_col[k][r - TILE];
+              if (v) {
+                atomicAdd(P.counts + (long long)k * P.Mpad + (long long)bj * TILE + (r - TILE), v);
+                s_col[k][r - TILE] = 0;
+              }
+            }
+          }
+          // the __syncthreads at the top of the next iteration orders these resets before reuse
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  if (MODE == 0 || MODE == 2) {
+    for (int o = 16; o; o >>= 1) {
+      ham_local += __shfl_xor_sync(0xffffffffu, ham_local, o);
+      pairs_local += __shfl_xor_sync(0xffffffffu, pairs_local, o);
+    }
+    if (lane == 0 && pairs_local) {
+      atomicAdd(P.ham_sum, ham_local);
+      atomicAdd(P.ham_sum + 1, pairs_local);
+    }
+  }
+}
+
+template <int NPL>
+int32_t launch_pairs(gdca_ctx *ctx, int mode, const PairParams &P) {
+  const size_t smem = (size_t)STAGES * 2 * WC * NPL * TILE * sizeof(uint32_t);
+  const int grid = ctx->num_sms;
+#define GDCA_PAIR_LAUNCH(MODE)                                                                                      \
+  do {                                                                                                              \
+    GDCA_CUDA(ctx, cudaFuncSetAttribute(pair_sweep_kernel<NPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                        (int)smem));                                                                \
+    pair_sweep_kernel<NPL, MODE><<<grid, NTHREADS, smem, ctx->stream>>>(P);                                         \
+  } while (0)
+  if (mode == 0)
+    GDCA_PAIR_LAUNCH(0);
+  else if (mode == 1)
+    GDCA_PAIR_LAUNCH(1);
+  else
+    GDCA_PAIR_LAUNCH(2);
+#undef GDCA_PAIR_LAUNCH
+  GDCA_LAUNCH_CHECK(ctx);
+  return GDCA_OK;
+}
+
+}  // namespace
+
+int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride) {
+  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "pair_pass: no alignment loaded");
+  if (mode < 0 || mode > 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "pair_pass: mode must be 0, 1 or 2");
+  GDCA_TRY(gdca_reserve(ctx, ctx->dCounts, ctx->capCounts, (size_t)3 * ctx->Mpad));
+  if (mode != 0) GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dCounts, 0, (size_t)3 * ctx->Mpad * sizeof(int32_t), ctx->stream));
+  if (mode != 1) GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dHam, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  if (sample_stride < 1) sample_stride = 1;
+
+  PairParams P;
+  P.planes = ctx->dPlanes;
+  P.Mpad = ctx->Mpad;
+  P.M = ctx->M;
+  P.nwords = (int)ctx->nwords;
+  P.nchunks = (int)((ctx->nwords + WC - 1) / WC);
+  P.T = (int)(ctx->Mpad / TILE);
+  P.n_items = (long long)P.T * (P.T + 1) / 2;
+  // a sampled sweep visits every sample_stride-th item of this shard: items t = rank (mod world*stride)
+  P.rank = ctx->shard_rank;
+  P.world = ctx->shard_world * sample_stride;
+  P.thresh = thresh;
+  P.counts = ctx->dCounts;
+  P.ham_sum = ctx->dHam;
+  switch (ctx->nplanes) {
+    case 1: return launch_pairs<1>(ctx, mode, P);
+    case 2: return launch_pairs<2>(ctx, mode, P);
+    case 3: return launch_pairs<3>(ctx, mode, P);
+    case 4: return launch_pairs<4>(ctx, mode, P);
+    default: return launch_pairs<5>(ctx, mode, P);
+  }
+}

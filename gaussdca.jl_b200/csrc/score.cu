@@ -1,0 +1,211 @@
+// score.cu -- K6/K7: per site-pair block scores from mJ = inv(C).
+//
+//   K6 compute_FN       (DCAUtils, un-vendored; reference call site src/GaussDCA.jl:39)
+//        B = mJ[block i, block j] (s x s);  K = B - rowmean - colmean + mean  (means over the s x s block)
+//        FN[i,j] = FN[j,i] = ||K||_F ;  zero diagonal
+//   K7 compute_DI_gauss (DCAUtils, un-vendored; reference call site src/GaussDCA.jl:37)
+//        V = (sqrt(C_ii) mJ_ij sqrt(C_jj)) (.)';  DI = s/2 log(1/2) + 1/2 sum_k log(1 + sqrt(1 + 4 lambda_k(V)))
+//      evaluated through the equivalent form lambda_k = sigma_k(Lc_i' mJ_ij Lc_j)^2 with C_ii = Lc_i Lc_i'
+//      (similarity transform; removes the per-site matrix square root).  Singular values come from a
+//      one-sided Jacobi iteration held entirely in shared memory, one warp per (i,j) block.
+//
+// One warp per (i<j) block; a CTA is 4 warps sharing site i.  FN is HBM-bound (3200 B read per
+// block at s = 20); DI adds ~3e5 FP64 flop per block on the plain FP64 pipe.
+#include "gdca_internal.cuh"
+
+namespace {
+
+constexpr int SW = 4;  // warps (blocks j) per CTA
+
+__global__ void __launch_bounds__(SW * 32) fn_kernel(const double *__restrict__ mJ, long long ld, int L, int s,
+                                                     double *__restrict__ S) {
+  extern __shared__ double sm[];  // [SW][s*s + 2*s]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.y, j = blockIdx.x * SW + warp;
+  if (j <= i || j >= L) return;
+  double *Bk = sm + (size_t)warp * (s * s + 2 * s);
+  double *rs = Bk + s * s, *cs = rs + s;
+  const int ss = s * s;
+  double tot = 0.0;
+  for (int e = lane; e < ss; e += 32) {
+    const int a = e / s, b = e - a * s;
+    const double v = mJ[((long long)i * s + a) * ld + (long long)j * s + b];
+    Bk[e] = v;
+    tot += v;
+  }
+  for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  __syncwarp();
+  if (lane < s) {
+    double r = 0.0, c = 0.0;
+    for (int k = 0; k < s; ++k) {
+      r += Bk[lane * s + k];
+      c += Bk[k * s + lane];
+    }
+    rs[lane] = r / s;
+    cs[lane] = c / s;
+  }
+  __syncwarp();
+  const double mean = tot / ss;
+  double acc = 0.0;
+  for (int e = lane; e < ss; e += 32) {
+    const int a = e / s, b = e - a * s;
+    const double k = Bk[e] - rs[a] - cs[b] + mean;
+    acc += k * k;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const double f = sqrt(acc);
+    S[(long long)i * L + j] = f;
+    S[(long long)j * L + i] = f;
+  }
+}
+
+__global__ void zero_diag_kernel(double *__restrict__ S, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) S[(long long)i * L + i] = 0.0;
+}
+
+// ---- per-site Cholesky of the diagonal blocks of C: Lc[i] lower, zeros above ----
+__global__ void site_chol_kernel(const double *__restrict__ Cdiag, int s, double *__restrict__ Lc) {
+  extern __shared__ double sm[];  // [s][s]
+  const int i = blockIdx.x, lane = threadIdx.x;
+  const int ss = s * s;
+  for (int e = lane; e < ss; e += 32) sm[e] = Cdiag[(long long)i * ss + e];
+  __syncwarp();
+  for (int j = 0; j < s; ++j) {
+    const double d = sqrt(sm[j * s + j]);
+    __syncwarp();
+    for (int r = j + lane; r < s; r += 32) sm[r * s + j] = (r == j) ? d : sm[r * s + j] / d;
+    __syncwarp();
+    for (int e = lane; e < (s - 1 - j) * (s - 1 - j); e += 32) {
+      const int rr = j + 1 + e / (s - 1 - j), cc = j + 1 + e % (s - 1 - j);
+      if (cc <= rr) sm[rr * s + cc] -= sm[rr * s + j] * sm[cc * s + j];
+    }
+    __syncwarp();
+  }
+  for (int e = lane; e < ss; e += 32) {
+    const int a = e / s, b = e - a * s;
+    Lc[(long long)i * ss + e] = (b <= a) ? sm[e] : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(SW * 32) di_kernel(const double *__restrict__ mJ, long long ld,
+                                                     const double *__restrict__ Lc, int L, int s,
+                                                     double *__restrict__ S) {
+  extern __shared__ double sm[];  // Li[s*s] + SW * (G[s*(s+1)] + Lj[s*s] + T1[s*s])
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.y, j = blockIdx.x * SW + warp;
+  const int ss = s * s, gs = s + 1;
+  double *Li = sm;
+  for (int e = threadIdx.x; e < ss; e += SW * 32) Li[e] = Lc[(long long)i * ss + e];
+  __syncthreads();
+  if (j <= i || j >= L) return;
+  double *G = sm + ss + (size_t)warp * (s * gs + 2 * ss);
+  double *Lj = G + s * gs, *T1 = Lj + ss;
+  // B (row-major, temporarily in G) and Lj
+  for (int e = lane; e < ss; e += 32) {
+    const int a = e / s, b = e - a * s;
+    G[e] = mJ[((long long)i * s + a) * ld + (long long)j * s + b];
+    Lj[e] = Lc[(long long)j * ss + e];
+  }
+  __syncwarp();
+  // T1 = B * Lj      (Lj lower: k >= b)
+  for (int e = lane; e < ss; e += 32) {
+    const int a = e / s, b = e - a * s;
+    double t = 0.0;
+    for (int k = b; k < s; ++k) t += G[a * s + k] * Lj[k * s + b];
+    T1[e] = t;
+  }
+  __syncwarp();
+  // A = Li' * T1     (Li lower: k >= a);  stored column-major in G with stride gs
+  for (int e = lane; e < ss; e += 32) {
+    const int a = e / s, b = e - a * s;
+    double t = 0.0;
+    for (int k = a; k < s; ++k) t += Li[k * s + a] * T1[k * s + b];
+    G[b * gs + a] = t;  // column b, row a
+  }
+  __syncwarp();
+  // ---- one-sided Jacobi: orthogonalise the columns of G; sigma_k^2 = ||g_k||^2 ----
+  const int nc = (s + 1) & ~1;  // even number of players (last one is a bye when s is odd)
+  const int half = nc >> 1;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    bool rotated = false;
+    for (int r = 0; r < nc - 1; ++r) {
+      int p = -1, q2 = -1;
+      if (lane < half) {
+        if (lane == 0) {
+          p = nc - 1;
+          q2 = r;
+        } else {
+          p = (r + lane) % (nc - 1);
+          q2 = (r - lane + (nc - 1)) % (nc - 1);
+        }
+      }
+      if (p >= 0 && p < s && q2 < s) {
+        double *gp = G + p * gs, *gq = G + q2 * gs;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int k = 0; k < s; ++k) {
+          const double x = gp[k], y = gq[k];
+          al += x * x;
+          be += y * y;
+          ga += x * y;
+        }
+        if (fabs(ga) > 1e-16 * sqrt(al * be) && ga != 0.0) {
+          const double zeta = (be - al) / (2.0 * ga);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cth = 1.0 / sqrt(1.0 + t * t), sth = cth * t;
+          for (int k = 0; k < s; ++k) {
+            const double x = gp[k], y = gq[k];
+            gp[k] = cth * x - sth * y;
+            gq[k] = sth * x + cth * y;
+          }
+          rotated = true;
+        }
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, rotated)) break;
+  }
+  double part = 0.0;
+  if (lane < s) {
+    const double *gk = G + lane * gs;
+    double lam = 0.0;
+    for (int k = 0; k < s; ++k) lam += gk[k] * gk[k];
+    part = log(1.0 + sqrt(1.0 + 4.0 * lam));
+  }
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) {
+    const double di = 0.5 * s * log(0.5) + 0.5 * part;
+    S[(long long)i * L + j] = di;
+    S[(long long)j * L + i] = di;
+  }
+}
+
+}  // namespace
+
+int32_t gdca_k_score(gdca_ctx *ctx, int score) {
+  if (!ctx->have_inv) return gdca_fail(ctx, GDCA_ERR_STATE, "score: inverse not computed");
+  const int L = (int)ctx->L, s = ctx->s;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dS, ctx->capS, (size_t)L * L));
+  dim3 grid((unsigned)((L + SW - 1) / SW), (unsigned)L);
+  if (score == GDCA_SCORE_FROB) {
+    const size_t smem = (size_t)SW * (s * s + 2 * s) * sizeof(double);
+    fn_kernel<<<grid, SW * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, L, s, ctx->dS);
+    GDCA_LAUNCH_CHECK(ctx);
+  } else if (score == GDCA_SCORE_DI) {
+    // Lc lives behind the saved diagonal blocks
+    GDCA_TRY(gdca_reserve(ctx, ctx->dRed, ctx->capRed, (size_t)L * s * s + 4096));
+    double *Lc = ctx->dRed;
+    site_chol_kernel<<<(unsigned)L, 32, (size_t)s * s * sizeof(double), ctx->stream>>>(ctx->dCdiag, s, Lc);
+    GDCA_LAUNCH_CHECK(ctx);
+    const size_t smem = ((size_t)s * s + (size_t)SW * (s * (s + 1) + 2 * s * s)) * sizeof(double);
+    GDCA_CUDA(ctx, cudaFuncSetAttribute(di_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    di_kernel<<<grid, SW * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, Lc, L, s, ctx->dS);
+    GDCA_LAUNCH_CHECK(ctx);
+  } else {
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "score: must be 0 (frob) or 1 (DI)");
+  }
+  zero_diag_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->dS, L);
+  GDCA_LAUNCH_CHECK(ctx);
+  return GDCA_OK;
+}

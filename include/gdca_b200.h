@@ -1,0 +1,158 @@
+/*
+ * gdca_b200.h -- C ABI of libgdca_b200.so: the gDCA hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (carlobaldassi/GaussDCA.jl) has no FFI: its only boundary is the Julia call
+ * surface gDCA(filename; ...) -> Vector{Tuple{Int,Int,Float64}} (src/GaussDCA.jl:8-47).  This
+ * library replaces everything between the encoded alignment Z (src/GaussDCA.jl:24) and the
+ * ranking R (src/GaussDCA.jl:44).  The Julia wrapper (julia/GaussDCA.jl) keeps
+ * lines :18-23 (argument check, FASTA parse, dedup) on the host and ccall's gdca_run().
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *  - Layouts are Julia's: column-major.  Z is L x M Int8 with ONE SEQUENCE PER COLUMN, i.e. sequence
+ *    k occupies bytes [k*L, (k+1)*L).  Symmetric matrices (C, mJ, S) are written full.
+ *  - (site i, state a), 1-based, lives at matrix index (i-1)*s + a, s = q-1 (state q is dropped).
+ *  - Host buffers are caller-owned; the library never retains or frees them.
+ *  - Every entry point returns a gdca_status_t; gdca_last_error() gives the text.
+ *  - There is no CPU fallback: without a usable sm_100 device gdca_create() fails.
+ *  - One caller thread per context at a time (the reference is single-caller).
+ */
+#ifndef GDCA_B200_H
+#define GDCA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDCA_ABI_VERSION 1
+
+typedef enum {
+  GDCA_OK = 0,
+  GDCA_ERR_INVALID_ARG = 1, /* ArgumentError-class: bad shape / range (src/GaussDCA.jl:49-65)          */
+  GDCA_ERR_Q_TOO_BIG = 2,   /* q >= 32: error("parameter q=$q is too big ...") (src/GaussDCA.jl:26)     */
+  GDCA_ERR_NOT_SPD = 3,     /* PosDefException from cholesky(C) (src/GaussDCA.jl:34); info in stats    */
+  GDCA_ERR_CUDA = 4,
+  GDCA_ERR_OOM = 5,
+  GDCA_ERR_NO_DEVICE = 6,
+  GDCA_ERR_STATE = 7 /* staged call issued before the stage it depends on                       */
+} gdca_status_t;
+
+typedef enum { GDCA_SCORE_FROB = 0, GDCA_SCORE_DI = 1 } gdca_score_t;
+
+/* One ranking row.  Bit-compatible with Julia's isbits Tuple{Int,Int,Float64} (24 bytes, offsets
+ * 0/8/16), so a preallocated Vector{Tuple{Int,Int,Float64}} is passed straight through.
+ * Replaces the element type built at src/GaussDCA.jl:90-97.  i < j, 1-based. */
+typedef struct {
+  int64_t i;
+  int64_t j;
+  double score;
+} gdca_rank_t;
+
+/* Per-call diagnostics (the reference prints theta/threshold/Meff from DCAUtils; it has no timers). */
+typedef struct {
+  int64_t L, M, n;      /* columns, sequences, n = (q-1)*L                                           */
+  int32_t q;            /* alphabet size used, = max(Z) (src/GaussDCA.jl:25)                          */
+  int32_t posdef_info;  /* 0, or the 1-based order of the leading minor that is not SPD              */
+  double theta;         /* theta used (the :auto value when requested)                               */
+  int64_t thresh;       /* floor(theta*L); neighbours have hamming < thresh                          */
+  double meff;          /* sum_k 1/count[k], correctly rounded from the count histogram              */
+  uint64_t ident_sum;   /* sum_{k<l} #identical positions (only when theta == :auto)                 */
+  int32_t theta_passes; /* pair sweeps executed (1 when the speculative threshold held, else 2)      */
+  int32_t reserved;
+  /* device milliseconds per stage, CUDA events on the library's stream */
+  float ms_h2d, ms_pack, ms_theta, ms_weights, ms_cov, ms_chol, ms_inv, ms_score, ms_apc, ms_rank, ms_d2h, ms_total;
+} gdca_stats_t;
+
+typedef struct gdca_ctx gdca_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int32_t gdca_abi_version(void);
+/* device: CUDA ordinal.  Owns one stream, all device memory, reusable across calls. */
+int32_t gdca_create(gdca_ctx **out, int32_t device);
+void gdca_destroy(gdca_ctx *ctx);
+const char *gdca_last_error(const gdca_ctx *ctx); /* ctx may be NULL: error of a failed gdca_create */
+const char *gdca_status_string(int32_t status);
+/* Work partition for one-process-per-GPU drivers: this context computes shard `rank` of `world`
+ * in the sharded stages (pair sweep tiles, covariance row blocks).  Default (0,1). */
+int32_t gdca_set_shard(gdca_ctx *ctx, int32_t rank, int32_t world);
+
+/* ---- fused hot path: src/GaussDCA.jl:24-44 ---------------------------------------------------
+ * theta < 0 means :auto.  score: gdca_score_t.  R_len must equal
+ * (L-min_separation)*(L-min_separation+1)/2 (src/GaussDCA.jl:90).  stats may be NULL. */
+int32_t gdca_run(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, double pseudocount,
+                 int32_t score, int64_t min_separation, gdca_rank_t *R, int64_t R_len, gdca_stats_t *stats);
+int64_t gdca_ranking_length(int64_t L, int64_t min_separation);
+
+/* ---- staged entry points, HOST buffers (parity tests; DCAUtils-shaped pieces) ------------------ */
+/* compute_theta + compute_weights (call site src/GaussDCA.jl:28).  theta < 0 => :auto.
+ * counts int32[M], W f64[M] (= 1/count); either may be NULL. */
+int32_t gdca_compute_weights(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, int32_t *counts,
+                             double *W, double *meff, double *theta_used, int64_t *thresh, uint64_t *ident_sum);
+/* frequencies + add_pseudocount + compute_C fused (src/GaussDCA.jl:28-32).  q = max(Z) is computed
+ * by the library.  C is n x n, Pi (with pseudocount) is n; Pi may be NULL. */
+int32_t gdca_compute_covariance(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, const double *W, double meff,
+                                double pseudocount, double *C, double *Pi, int32_t *q_out);
+/* mJ = inv(cholesky(C)) (src/GaussDCA.jl:34).  info: 0 or failing leading minor (1-based). */
+int32_t gdca_inverse(gdca_ctx *ctx, const double *C, int64_t n, double *mJ, int32_t *info);
+/* compute_FN (src/GaussDCA.jl:39) / compute_DI_gauss (:37).  C is only read for DI (may be NULL for FROB).
+ * S is L x L, L = n/(q-1), zero diagonal. */
+int32_t gdca_score(gdca_ctx *ctx, const double *mJ, const double *C, int64_t n, int32_t q, int32_t score, double *S);
+/* correct_APC (src/GaussDCA.jl:78-86) */
+int32_t gdca_apc(gdca_ctx *ctx, const double *S, int64_t L, double *S_out);
+/* compute_ranking (src/GaussDCA.jl:88-99): stable descending sort of (i, j, S[j,i]). */
+int32_t gdca_ranking(gdca_ctx *ctx, const double *S, int64_t L, int64_t min_separation, gdca_rank_t *R,
+                     int64_t R_len);
+
+/* ---- staged entry points, DEVICE-resident state ------------------------------------------------
+ * For one-process-per-GPU drivers (torch.distributed / NCCL does the exchange on the exposed device
+ * buffers) and for timing with inputs already in HBM.  Order: load -> pair_pass(es) ->
+ * finish_weights -> covariance -> inverse -> score -> rank.  Nothing here synchronises the host
+ * except where a scalar result is returned. */
+int32_t gdca_dev_load(gdca_ctx *ctx, const int8_t *Z_host, int64_t L, int64_t M); /* H2D + q + bit-plane pack */
+int32_t gdca_dev_load_resident(gdca_ctx *ctx, const int8_t *Z_dev, int64_t L, int64_t M); /* Z already on device */
+/* One sweep over this shard's tiles of the M x M pair matrix.
+ * mode 0: accumulate sum of hamming distances (theta :auto);  mode 1: neighbour counts for `thresh`;
+ * mode 2: both in one sweep, counts for the three thresholds thresh-1, thresh, thresh+1 (speculative). */
+int32_t gdca_dev_pair_pass(gdca_ctx *ctx, int32_t mode, int64_t thresh);
+/* mode-0 sweep over every stride-th tile of this shard (cheap estimate of the mean identity). */
+int32_t gdca_dev_pair_sample(gdca_ctx *ctx, int32_t stride);
+/* partial results of this shard, device pointers: u64[2] {hamming sum, pairs visited}; int32[3*Mpad] counts (row t = thresh-1+t
+ * in mode 2, row 0 only in mode 1), NOT including the self count. */
+void *gdca_dev_ham_sum_ptr(gdca_ctx *ctx);
+void *gdca_dev_counts_ptr(gdca_ctx *ctx);
+int64_t gdca_dev_counts_stride(gdca_ctx *ctx);
+/* theta from the (all-reduced) hamming sum -- host arithmetic identical to the oracle's. */
+int32_t gdca_theta_from_ham_sum(int64_t L, int64_t M, uint64_t ham_sum, double *theta, int64_t *thresh,
+                                uint64_t *ident_sum);
+/* counts (all-reduced, row `which` of the counts buffer) -> W = 1/(1+count), Meff.  theta == 0 path: which = -1. */
+int32_t gdca_dev_finish_weights(gdca_ctx *ctx, int32_t which, double *meff);
+int32_t gdca_dev_set_weights(gdca_ctx *ctx, const double *W_host, double meff);
+/* this shard's rows of C (others zero); sum over shards == C.  Device pointer to n x n f64. */
+int32_t gdca_dev_covariance(gdca_ctx *ctx, double pseudocount);
+void *gdca_dev_C_ptr(gdca_ctx *ctx);  /* [npad][npad] f64, leading dimension gdca_dev_npad() */
+int64_t gdca_dev_npad(gdca_ctx *ctx);
+void *gdca_dev_W_ptr(gdca_ctx *ctx);  /* f64[M] */
+int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info); /* C -> mJ on this device */
+void *gdca_dev_mJ_ptr(gdca_ctx *ctx);
+int32_t gdca_dev_score_rank(gdca_ctx *ctx, int32_t score, int64_t min_separation, gdca_rank_t *R_host, int64_t R_len);
+void *gdca_dev_S_ptr(gdca_ctx *ctx); /* L x L APC-corrected scores after gdca_dev_score_rank */
+int32_t gdca_dev_sync(gdca_ctx *ctx);
+/* stream-ordered D2H copy of any exposed device buffer, then sync (hosts without a CUDA binding) */
+int32_t gdca_dev_copy_to_host(gdca_ctx *ctx, void *dst_host, const void *src_dev, int64_t nbytes);
+int32_t gdca_dev_get_stats(gdca_ctx *ctx, gdca_stats_t *stats);
+void *gdca_dev_stream(gdca_ctx *ctx); /* cudaStream_t the library launches on (for CUDA-event timing) */
+int64_t gdca_dev_kernel_launches(gdca_ctx *ctx); /* kernels launched by this context so far */
+
+/* ---- synthetic alignment of SURVEY 8(d) (bench / tests): fills Z_dev (L*M int8, device) ---------- */
+int32_t gdca_synth_alignment_dev(gdca_ctx *ctx, int8_t *Z_dev, int64_t L, int64_t M, uint64_t seed);
+int32_t gdca_synth_alignment(gdca_ctx *ctx, int8_t *Z_host, int64_t L, int64_t M, uint64_t seed);
+
+/* ---- measured-peak helpers (bench only): raw pipe throughput probes --------------------------- */
+int32_t gdca_probe_peaks(gdca_ctx *ctx, double *lop3_tops, double *popc_tops, double *dmma_tflops, double *dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDCA_B200_H */
