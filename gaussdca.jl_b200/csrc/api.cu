@@ -84,11 +84,12 @@ int32_t weights_stage(gdca_ctx *ctx, double theta) {
   st.theta_passes = 0;
   st.ident_sum = 0;
   if (theta < 0) {
-    // speculative single sweep: estimate thresh from a 1/64 sample of the tiles, then count for
-    // thresh-1, thresh, thresh+1 while accumulating the exact hamming sum.
+    // speculative single sweep: estimate thresh from a sample of the tiles (every stride-th item, at
+    // least ~2 tiles per SM, at most 1/2 and at least 1/64 of the sweep), then count for thresh-1,
+    // thresh, thresh+1 while accumulating the exact hamming sum.  Always verified against the exact value.
     unsigned long long hs[2] = {0, 0};
     const long long T = ctx->Mpad / GDCA_TILE;
-    int stride = (int)((T * (T + 1) / 2) / (64 * (long long)ctx->num_sms));
+    int stride = (int)((T * (T + 1) / 2) / (2 * (long long)ctx->num_sms));
     if (stride > 64) stride = 64;
     int64_t guess = -1;
     if (stride >= 2) {

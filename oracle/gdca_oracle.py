@@ -176,6 +176,8 @@ def theta_from_ident_sum(total_ident: int, L: int, M: int) -> float:
     """theta = min(0.5, 0.38*0.32/meanfracid), meanfracid = (sum ident / L) / (M(M-1)/2)."""
     npairs = 0.5 * M * (M - 1)
     meanfracid = (total_ident / L) / npairs
+    if meanfracid == 0.0:  # Julia: 0.1216/0.0 == Inf, min(0.5, Inf) == 0.5
+        return 0.5
     return min(0.5, 0.38 * 0.32 / meanfracid)
 
 
@@ -334,7 +336,11 @@ def compute_ranking(S, min_separation: int = 5):
     if not ii:
         return []
     ii, jj, vv = np.concatenate(ii), np.concatenate(jj), np.concatenate(vv)
-    order = np.argsort(-vv, kind="stable")
+    # Julia sorts with isless (a total order: -0.0 < 0.0), stable, rev=true.  Map doubles to integers
+    # that sort the same way, complement for descending, and let a stable argsort keep enumeration order on ties.
+    u = np.ascontiguousarray(vv, dtype=np.float64).view(np.uint64)
+    asc = np.where((u >> np.uint64(63)).astype(bool), ~u, u | np.uint64(1 << 63))
+    order = np.argsort(~asc, kind="stable")
     return [(int(ii[o]) + 1, int(jj[o]) + 1, float(vv[o])) for o in order]
 
 
