@@ -8,9 +8,11 @@
 //
 // Design (B200): INT32-ALU bound, not HBM bound -- the packed alignment (<= 64 MB at L=500, M=200k)
 // lives in L2.  The bit-plane layout of pack.cu makes 32 sites of one pair cost 5 LOP3 + 1 POPC + 1 ADD.
-//   * CTA tile 128 x 128 sequences, 256 threads, 8 x 8 register tile of pairs per thread.
-//   * operands staged through shared memory with cp.async, 3-stage ring, the ring runs across tile
-//     boundaries so the next tile's first chunk is already in flight during this tile's epilogue.
+//   * CTA tile 128 x 128 sequences, 512 threads (4 warps per scheduler), 4 x 8 register tile of pairs
+//     per thread, <= 128 registers; the popcount accumulation runs on the otherwise idle FMA pipe.
+//   * operands staged through shared memory with cp.async: a 2-slot ring of 16-word stages (a whole
+//     tile for L <= 512 -> one barrier per tile); the ring runs across tile boundaries, so the next
+//     tile is in flight while this one is computed.
 //   * only tiles bi <= bj of the symmetric pair matrix are visited; a hit credits both sequences.
 //   * persistent grid (one CTA per SM), items strided over (rank, world) for multi-GPU sharding.
 //   * mode 2 evaluates thresh-1, thresh, thresh+1 and the hamming sum in ONE sweep, so theta=:auto
@@ -20,9 +22,9 @@
 namespace {
 
 constexpr int TILE = GDCA_TILE;  // 128
-constexpr int WC = 4;            // 32-site words per pipeline stage
-constexpr int STAGES = 3;
-constexpr int NTHREADS = 256;
+constexpr int WC = 16;           // 32-site words per pipeline stage (L <= 512: one stage per tile, one barrier per tile)
+constexpr int STAGES = 2;
+constexpr int NTHREADS = 512;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -70,18 +72,28 @@ struct PairParams {
   unsigned long long *ham_sum;  // [0] sum of hamming distances, [1] pairs visited
 };
 
+// acc += pc on the FMA pipe: a 3-register IMAD (multiplier held in a register so ptxas cannot
+// fold it into an ALU-pipe IADD3).  The ALU pipe is the bound of this kernel; FMA is idle.
+__device__ __forceinline__ void add_on_fma_pipe(unsigned &acc, unsigned pc, unsigned one) {
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(pc), "r"(one));
+}
+
 template <int NPL, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
   extern __shared__ __align__(16) uint32_t smem[];
   // ring: [STAGES][2 operands][WC][NPL][TILE]
   constexpr int OP_WORDS = WC * NPL * TILE;
   constexpr int STAGE_WORDS = 2 * OP_WORDS;
+  constexpr int CHUNKS = 2 * WC * NPL * (TILE / 4);          // 16-byte chunks per stage
+  constexpr int CPT = (CHUNKS + NTHREADS - 1) / NTHREADS;    // chunks per thread
   __shared__ int s_row[3][TILE], s_col[3][TILE];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int ty = (warp >> 1) * 4 + (lane >> 3);  // 0..15 -> rows ty*4.. and 64+ty*4..
+  // 512 threads = 32 (ty) x 16 (tx); thread tile 4 rows x 8 cols; a warp is 4 (ty) x 8 (tx)
+  const int ty = (warp >> 1) * 4 + (lane >> 3);  // 0..31 -> rows ty*4 .. ty*4+3
   const int tx = (warp & 1) * 8 + (lane & 7);    // 0..15 -> cols tx*4.. and 64+tx*4..
+  const unsigned one = (unsigned)(P.T > 0);      // == 1 at run time, unknown at compile time
 
   // items of this CTA: local index it -> global item (blockIdx.x + it*gridDim.x)*world + rank
   const long long my_first = (long long)blockIdx.x;
@@ -90,35 +102,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
   if (my_first < per_rank_items) n_my = (per_rank_items - my_first + gridDim.x - 1) / gridDim.x;
   const long long n_flat = n_my * P.nchunks;
 
-  auto issue_load = [&](long long f) {
-    if (f < n_flat) {
-      const long long it = f / P.nchunks;
-      const int c = (int)(f - it * P.nchunks);
-      const long long t = (my_first + it * gridDim.x) * P.world + P.rank;
-      int bi, bj;
-      item_to_tile(t, P.T, bi, bj);
-      uint32_t *dst = smem + (size_t)(f % STAGES) * STAGE_WORDS;
-      // 2 operands x WC*NPL rows x 32 chunks of 16 bytes
-      constexpr int CHUNKS = 2 * WC * NPL * (TILE / 4);
-      for (int ch = tid; ch < CHUNKS; ch += NTHREADS) {
-        const int op = ch / (WC * NPL * (TILE / 4));
-        const int rem = ch - op * (WC * NPL * (TILE / 4));
-        const int row = rem / (TILE / 4);  // w*NPL + p within the chunk
-        const int col = rem - row * (TILE / 4);
-        const int w = c * WC + row / NPL;
-        const int p = row - (row / NPL) * NPL;
-        const bool valid = w < P.nwords;
-        const long long seq0 = (long long)(op == 0 ? bi : bj) * TILE + col * 4;
-        const uint32_t *src = P.planes + ((long long)(valid ? w : 0) * NPL + p) * P.Mpad + seq0;
-        cp_async16(dst + op * OP_WORDS + row * TILE + col * 4, src, valid);
+  // per-thread copy plan, fixed for the whole kernel: chunk ch -> (operand, row = w*NPL+p, 4-sequence column)
+  int cp_dst[CPT], cp_wl[CPT], cp_op[CPT];
+  long long cp_src[CPT];
+#pragma unroll
+  for (int u = 0; u < CPT; ++u) {
+    const int ch = tid + u * NTHREADS;
+    const int op = ch / (WC * NPL * (TILE / 4));
+    const int rem = ch - op * (WC * NPL * (TILE / 4));
+    const int row = rem / (TILE / 4), col = rem - row * (TILE / 4);
+    const int wl = row / NPL, p = row - wl * NPL;
+    cp_op[u] = (ch < CHUNKS) ? op : -1;
+    cp_wl[u] = wl;
+    cp_dst[u] = op * OP_WORDS + row * TILE + col * 4;
+    cp_src[u] = (long long)p * P.Mpad + col * 4;  // + (w*NPL)*Mpad + tile*TILE at issue time
+  }
+
+  // flat pipeline position of the loader: tile coordinates are advanced incrementally
+  long long ld_f = 0;
+  int ld_c = 0, ld_bi = 0, ld_bj = 0;
+  if (n_flat > 0) item_to_tile(my_first * P.world + P.rank, P.T, ld_bi, ld_bj);
+  const long long item_step = (long long)gridDim.x * P.world;
+
+  auto issue_load = [&]() {
+    if (ld_f < n_flat) {
+      uint32_t *dst = smem + (size_t)(ld_f % STAGES) * STAGE_WORDS;
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) {
+        if (cp_op[u] >= 0) {
+          const int w = ld_c * WC + cp_wl[u];
+          const bool valid = w < P.nwords;
+          const long long seq0 = (long long)(cp_op[u] == 0 ? ld_bi : ld_bj) * TILE;
+          const uint32_t *src = P.planes + (long long)(valid ? w : 0) * NPL * P.Mpad + cp_src[u] + seq0;
+          cp_async16(dst + cp_dst[u], src, valid);
+        }
+      }
+      ++ld_f;
+      if (++ld_c == P.nchunks) {
+        ld_c = 0;
+        if (ld_f < n_flat) {
+          const long long it = ld_f / P.nchunks;
+          item_to_tile((my_first + it * gridDim.x) * P.world + P.rank, P.T, ld_bi, ld_bj);
+        }
       }
     }
     cp_async_commit();
   };
+  (void)item_step;
 
-  unsigned acc[8][8];
+  unsigned acc[4][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0;
   unsigned long long ham_local = 0, pairs_local = 0;
@@ -128,102 +162,114 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
     (&s_col[0][0])[i] = 0;
   }
 
-  issue_load(0);
-  issue_load(1);
+  issue_load();
 
+  int cur_c = 0;
+  long long cur_it = 0;
   for (long long f = 0; f < n_flat; ++f) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();            // stage f landed for everyone; everyone is done with stage f-1
-    issue_load(f + STAGES - 1); // refill the slot freed by f-1
+    cp_async_wait<0>();
+    __syncthreads();  // stage f landed for everyone; everyone is done with stage f-1
+    issue_load();     // prefetch stage f+1 into the slot freed by f-1 while f is being computed
 
     const uint32_t *A = smem + (size_t)(f % STAGES) * STAGE_WORDS;
     const uint32_t *B = A + OP_WORDS;
-#pragma unroll
-    for (int w = 0; w < WC; ++w) {
-      unsigned x[8][8];
+    const int wcount = min(WC, P.nwords - cur_c * WC);  // words really present in this stage
+#pragma unroll 4
+    for (int w = 0; w < wcount; ++w) {
+      unsigned x[4][8];
 #pragma unroll
       for (int p = 0; p < NPL; ++p) {
         const uint4 a0 = *reinterpret_cast<const uint4 *>(A + (w * NPL + p) * TILE + ty * 4);
-        const uint4 a1 = *reinterpret_cast<const uint4 *>(A + (w * NPL + p) * TILE + 64 + ty * 4);
         const uint4 b0 = *reinterpret_cast<const uint4 *>(B + (w * NPL + p) * TILE + tx * 4);
         const uint4 b1 = *reinterpret_cast<const uint4 *>(B + (w * NPL + p) * TILE + 64 + tx * 4);
-        const unsigned a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const unsigned a[4] = {a0.x, a0.y, a0.z, a0.w};
         const unsigned b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[i][j] = (p == 0) ? (a[i] ^ b[j]) : (x[i][j] | (a[i] ^ b[j]));
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] += __popc(x[i][j]);
+        for (int j = 0; j < 8; ++j) add_on_fma_pipe(acc[i][j], (unsigned)__popc(x[i][j]), one);
     }
 
-    const long long it = f / P.nchunks;
-    if (f - it * P.nchunks == P.nchunks - 1) {
+    if (++cur_c == P.nchunks) {
+      cur_c = 0;
       // ---- tile epilogue: acc[i][j] = hamming(row r_i, col c_j) ----
-      const long long t = (my_first + it * gridDim.x) * P.world + P.rank;
+      const long long t = (my_first + cur_it * gridDim.x) * P.world + P.rank;
+      ++cur_it;
       int bi, bj;
       item_to_tile(t, P.T, bi, bj);
       const bool diag = (bi == bj);
-      int rh[3][8], chh[3][8];
+      const int hi_thresh = (MODE == 2) ? P.thresh + 1 : P.thresh;
+      unsigned tile_ham = 0, tile_pairs = 0, any = 0;
+      const bool interior = !diag && ((long long)(bj + 1) * TILE <= P.M);  // bi < bj: rows are in range too
+      if (interior) {
+        // fast path (all but O(T) of the T^2/2 tiles): every pair is valid
+        unsigned dmin = 0x7fffffffu;
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rh[k][i] = 0, chh[k][i] = 0;
-      unsigned any = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rl = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
-        const long long gr = (long long)bi * TILE + rl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int cl = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
-          const long long gc = (long long)bj * TILE + cl;
-          const bool valid = (gr < P.M) && (gc < P.M) && (!diag || rl < cl);
-          const int d = (int)acc[i][j];
-          if (MODE == 0 || MODE == 2) {
-            ham_local += valid ? (unsigned)d : 0u;
-            pairs_local += valid ? 1u : 0u;
+          for (int j = 0; j < 8; ++j) {
+            if (MODE != 1) add_on_fma_pipe(tile_ham, acc[i][j], one);
+            if (MODE != 0) dmin = min(dmin, acc[i][j]);
           }
-          if (MODE == 1) {
-            const int h = (valid && d < P.thresh) ? 1 : 0;
-            rh[0][i] += h;
-            chh[0][j] += h;
-            any |= h;
-          }
-          if (MODE == 2) {
+        tile_pairs = 32;
+        any = ((int)dmin < hi_thresh) ? 1u : 0u;
+      } else {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const int h = (valid && d < P.thresh - 1 + k) ? 1 : 0;
-              rh[k][i] += h;
-              chh[k][j] += h;
-              any |= h;
+        for (int i = 0; i < 4; ++i) {
+          const int rl = ty * 4 + i;
+          const bool rvalid = (long long)bi * TILE + rl < P.M;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int cl = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+            const bool valid = rvalid && ((long long)bj * TILE + cl < P.M) && (!diag || rl < cl);
+            const unsigned d = valid ? acc[i][j] : 0x7fffffffu;  // invalid pairs can never be neighbours
+            acc[i][j] = d;
+            if (MODE != 1) {
+              tile_ham += valid ? d : 0u;
+              tile_pairs += valid ? 1u : 0u;
             }
+            if (MODE != 0) any |= ((int)d < hi_thresh) ? 1u : 0u;
           }
-          acc[i][j] = 0;
         }
       }
+      ham_local += tile_ham;
+      pairs_local += tile_pairs;
       if (MODE != 0) {
-        // most tiles contain no neighbour pair at all: skip the reduction entirely then
-        const int block_any = __syncthreads_or((int)any);
-        if (block_any) {
+        // most tiles contain no neighbour pair at all: one vote, then skip the counting entirely
+        if (__syncthreads_or((int)any)) {
           constexpr int NK = (MODE == 2) ? 3 : 1;
 #pragma unroll
           for (int k = 0; k < NK; ++k) {
+            const int th = (MODE == 2) ? P.thresh - 1 + k : P.thresh;
+            int rh[4], chh[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              int v = rh[k][i];  // same rows across the 8 lanes sharing lane>>3
+            for (int i = 0; i < 4; ++i) rh[i] = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) chh[j] = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int h = ((int)acc[i][j] < th) ? 1 : 0;
+                rh[i] += h;
+                chh[j] += h;
+              }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              int v = rh[i];  // same rows across the 8 lanes sharing lane>>3
               v += __shfl_xor_sync(0xffffffffu, v, 1);
               v += __shfl_xor_sync(0xffffffffu, v, 2);
               v += __shfl_xor_sync(0xffffffffu, v, 4);
-              const int rl = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
-              if ((lane & 7) == 0 && v) atomicAdd(&s_row[k][rl], v);
+              if ((lane & 7) == 0 && v) atomicAdd(&s_row[k][ty * 4 + i], v);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              int v = chh[k][j];  // same cols across the 4 lanes sharing lane&7
+              int v = chh[j];  // same cols across the 4 lanes sharing lane&7
               v += __shfl_xor_sync(0xffffffffu, v, 8);
               v += __shfl_xor_sync(0xffffffffu, v, 16);
               const int cl = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
@@ -251,6 +297,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
           // the __syncthreads at the top of the next iteration orders these resets before reuse
         }
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0;
     }
   }
   cp_async_wait<0>();
