@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- gDCA hot path on B200: the BASELINE.json metric on the BASELINE.json config.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C|B|...]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the whole hot path (encoded alignment -> ranking, reference
+src/GaussDCA.jl:24-44) over one synthetic alignment.  Workload = BASELINE.json configs[2]: synthetic
+L=500, M=200k, theta=:auto, :frob, pseudocount 0.8 (fits one GPU).  One JSON line on stdout (rank 0).
+
+  value   seconds per gDCA with Z already resident in HBM (CUDA events on the library's stream)
+  e2e     seconds per gDCA through the C ABI call gdca_run() with pinned HOST buffers: H2D of Z and
+          D2H of the ranking are inside the timed region
+  roofline / cpu_baseline / stages: see DESIGN.md section 6
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+WORKLOADS = {
+    # name: (L, M, score, pseudocount)      BASELINE.json configs[...]
+    "B": (200, 50_000, "frob", 0.8),      # configs[1]
+    "C": (500, 200_000, "frob", 0.8),     # configs[2]  <- headline, metric is quoted on this
+    "D": (500, 200_000, "DI", 0.2),       # configs[3]
+    "S": (100, 20_000, "frob", 0.8),      # small smoke shape
+}
+SEED = 20140321
+METRIC = "gDCA end-to-end s @L=500,M=200k"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(L, M, score, pc, budget_s=20.0):
+    """The oracle port (oracle/, C + OpenMP + LAPACK via SciPy) timed on this box's host cores on a BOUNDED
+    sample of the same workload, extrapolated to the full workload by the exact work ratios."""
+    import numpy as np
+    orc = graft.load_oracle()
+    orc.build()
+    lib = orc.lib()
+    cores = int(lib.oracle_max_threads())
+    Ms = min(M, 20_000)                      # sample alignment: first Ms sequences of the same generator
+    Z = orc.synth_alignment(L, M, SEED)[:Ms].copy() if M <= 200_000 else orc.synth_alignment(L, Ms, SEED)
+    t0 = time.perf_counter()
+    cZ = orc.compress_Z(Z)
+    t_pack = time.perf_counter() - t0
+    # pair sweep: theta pass + threshold pass over rows [0, k1) x all later sequences of the sample
+    k1 = min(Ms, 4000)
+    t0 = time.perf_counter()
+    lib.oracle_ident_sum_packed_range(orc._ptr(cZ), L, Ms, 0, k1)
+    t_theta = time.perf_counter() - t0
+    counts = np.empty(Ms, dtype=np.int32)
+    t0 = time.perf_counter()
+    lib.oracle_neighbour_counts_packed_range(orc._ptr(cZ), L, Ms, int(0.5 * L), 0, k1, orc._ptr(counts))
+    t_cnt = time.perf_counter() - t0
+    pairs_sample = k1 * Ms - k1 * (k1 + 1) // 2
+    pairs_full = M * (M - 1) // 2
+    t_pairs_full = (t_theta + t_cnt) * pairs_full / pairs_sample
+    # frequencies: all sites, a slice of the sequences
+    q = 21
+    n = (q - 1) * L
+    ks = min(Ms, max(200, int(2.0e9 / (L * L))))
+    W = np.ones(Ms)
+    Pi = np.empty(n); Pij = np.empty((n, n))
+    t0 = time.perf_counter()
+    lib.oracle_weighted_freqs_range(orc._ptr(Z), L, Ms, q, orc._ptr(W), float(Ms), 0, ks, orc._ptr(Pi), orc._ptr(Pij))
+    t_freq = time.perf_counter() - t0
+    t_freq_full = t_freq * M / ks
+    # inversion: LAPACK dpotrf + dpotri at a reduced n, scaled by n^3
+    ns = min(n, 4000)
+    A = np.random.default_rng(0).standard_normal((ns, ns + 8))
+    Cs = A @ A.T / ns + np.eye(ns)
+    t0 = time.perf_counter()
+    orc.inv_cholesky(Cs)
+    t_inv = time.perf_counter() - t0
+    t_inv_full = t_inv * (n / ns) ** 3
+    total = t_pack * M / Ms + t_pairs_full + t_freq_full + t_inv_full
+    return {
+        "value": total, "unit": "s", "cores": cores, "kind": "port",
+        "pairs_per_s": 2 * pairs_sample / (t_theta + t_cnt),
+        "stages_s": {"pair_sweeps_x2": t_pairs_full, "frequencies": t_freq_full, "chol_inverse": t_inv_full},
+        "sample": (f"oracle port (C/OpenMP + SciPy LAPACK), {cores} threads: pair sweeps on rows [0,{k1}) of the first {Ms} "
+                   f"sequences ({pairs_sample:.3g} pairs x 2 passes, scaled by pair count); frequencies on {ks} sequences "
+                   f"(scaled by M); dpotrf+dpotri at n={ns} (scaled by n^3); measured {t_theta + t_cnt + t_freq + t_inv:.1f} s "
+                   f"of CPU work, extrapolated to L={L}, M={M}"),
+    }
+
+
+def run_reference(args, L, M, score, pc):
+    """--impl reference: the reference's own CPU path.  Julia + DCAUtils are not installed in this image
+    (probed; no network), so this times the oracle port with all host threads on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_baseline(L, M, score, pc, 5.0)
+    cb = None
+    for _ in range(max(1, min(args.steps, 3))):
+        cb = cpu_baseline(L, M, score, pc)
+        vals.append(cb["value"])
+    v = sum(vals) / len(vals)
+    cb["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": 1, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic L={L} M={M} theta=auto score={score} pseudocount={pc}", "seed": SEED,
+                   "note": "julia/DCAUtils absent: oracle port on host cores, bounded sample extrapolated"},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    L, M, score, pc = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, L, M, score, pc)
+
+    import numpy as np
+    import torch
+    pkg = graft.load_package()
+    from gaussdca_jl_b200 import _lib as glib
+    from gaussdca_jl_b200 import dist as gdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(1, args.gpus) and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pkg.Context(local)   # raises loudly without the CUDA library / a B200
+    lib = ctx.lib
+    stream = torch.cuda.ExternalStream(int(lib.gdca_dev_stream(ctx.h)), device=local)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    # synthetic alignment, generated on the device (identical bytes to oracle_synth_alignment)
+    Zd = torch.empty((M, L), dtype=torch.int8, device=f"cuda:{local}")
+    ctx.check(lib.gdca_synth_alignment_dev(ctx.h, ctypes.c_void_p(Zd.data_ptr()), L, M, SEED))
+    n_out = int(lib.gdca_ranking_length(L, 5))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+
+    def l2_flush():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    st = glib.Stats()
+    theta_code = -1.0
+    launches0 = lib.gdca_dev_kernel_launches(ctx.h)
+
+    def step_resident():
+        if world == 1:
+            ctx.check(lib.gdca_run_resident(ctx.h, ctypes.c_void_p(Zd.data_ptr()), L, M, theta_code, pc,
+                                            glib.SCORE_CODES[score], 5, None, n_out, ctypes.byref(st)))
+            return None
+        return gdist.gdca_sharded(Zd, pc, "auto", score, 5, ctx=ctx, resident=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, per-step CUDA events on the library stream, L2 flushed between steps
+    for _ in range(W):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches1 = lib.gdca_dev_kernel_launches(ctx.h)
+    stage_acc = {}
+    barrier()
+    for a, b in ev:
+        l2_flush()
+        a.record(stream)
+        step_resident()
+        b.record(stream)
+        if world == 1:
+            for k, v in st.asdict().items():
+                if k.startswith("ms_"):
+                    stage_acc[k] = stage_acc.get(k, 0.0) + v / K
+    barrier()
+    launches2 = lib.gdca_dev_kernel_launches(ctx.h)
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / K
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    stats = st.asdict()
+
+    # ---- e2e: gdca_run() with pinned host buffers (H2D of Z, D2H of R inside the timed region)
+    e2e = None
+    if world == 1:
+        Zh = torch.empty((M, L), dtype=torch.int8).pin_memory()
+        Zh.copy_(Zd)
+        Rh = torch.empty(n_out * 24, dtype=torch.uint8).pin_memory()
+        e_ms = []
+        for it in range(2 + K):
+            l2_flush()
+            torch.cuda.synchronize()
+            ctx.check(lib.gdca_run(ctx.h, ctypes.c_void_p(Zh.data_ptr()), L, M, theta_code, pc, glib.SCORE_CODES[score], 5,
+                                   ctypes.c_void_p(Rh.data_ptr()), n_out, ctypes.byref(st)))
+            if it >= 2:
+                e_ms.append(st.ms_total)   # CUDA events: before the H2D copy .. after the D2H copy
+        e2e = {"value": sum(e_ms) / len(e_ms) / 1e3, "unit": "s", "h2d_bytes_per_step": L * M,
+               "d2h_bytes_per_step": n_out * 24}
+        R = np.frombuffer(Rh.numpy(), dtype=glib.RANK_DTYPE)
+        top = [int(R["i"][0]), int(R["j"][0]), float(R["score"][0])]
+    else:
+        top = None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (pair sweep), measured live
+    roof, stages = None, None
+    pk = peaks()
+    if world == 1:
+        lop3, popc, dmma, dfma = (ctypes.c_double() for _ in range(4))
+        ctx.check(lib.gdca_probe_peaks(ctx.h, ctypes.byref(lop3), ctypes.byref(popc), ctypes.byref(dmma), ctypes.byref(dfma)))
+        # time the sweep kernel alone: mode-2 launch (hamming sum + counts for 3 thresholds)
+        ctx.check(lib.gdca_dev_load_resident(ctx.h, ctypes.c_void_p(Zd.data_ptr()), L, M))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        thr = int(stats["thresh"])
+        tk = []
+        for it in range(4):
+            l2_flush()
+            a.record(stream)
+            ctx.check(lib.gdca_dev_pair_pass(ctx.h, 2, thr))
+            b.record(stream)
+            stream.synchronize()
+            if it:
+                tk.append(a.elapsed_time(b))
+        t_pair = sum(tk) / len(tk) / 1e3
+        npairs = M * (M - 1) // 2
+        nwords = (L + 31) // 32
+        alu_ops = npairs * nwords * 5 * 32            # 5 LOP3 per 32-site word per pair, per lane-op
+        hbm_bytes = 4 * nwords * 5 * ((M + 127) // 128 * 128) + 3 * 4 * M   # packed planes once + counts
+        roof = {
+            "kernel": "pair_sweep_kernel<5,2> (theta:auto + neighbour counts, one sweep)",
+            "bound": "int32_alu",
+            "achieved": alu_ops / 32 / t_pair / 1e12 * 32, "peak": lop3.value, "unit": "Tlop3/s",
+            "frac": (alu_ops / t_pair / 1e12) / lop3.value,
+            "peak_source": "measured live: gdca_probe_peaks LOP3 issue rate (MEASURED_PEAKS.json has no INT32 figure)",
+            "ms_per_launch": t_pair * 1e3, "pairs_per_s": npairs / t_pair,
+            "traffic": None,
+            "hbm": {"achieved": hbm_bytes / t_pair / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                    "frac": hbm_bytes / t_pair / 1e9 / pk["hbm_gbs"] if pk.get("hbm_gbs") else None,
+                    "note": "compulsory bytes only; the sweep is ALU-bound, operands live in L2"},
+            "survey_floor_ops_per_pair": 5 * ((L + 5) // 6),
+        }
+        n = 20 * L
+        t_cov, t_chol = stage_acc.get("ms_cov", 0) / 1e3, stage_acc.get("ms_chol", 0) / 1e3
+        stages = {
+            "ms": {k: round(v, 4) for k, v in stage_acc.items()},
+            "theta_passes": stats["theta_passes"],
+            "weights_pairs_per_s": npairs / ((stage_acc.get("ms_theta", 0) + stage_acc.get("ms_weights", 0)) / 1e3),
+            "cov_fp64_equiv_tflops": M * n * (n + 1) / t_cov / 1e12 if t_cov else None,
+            "chol_inv_tflops": n ** 3 / t_chol / 1e12 if t_chol else None,
+            "cov_plus_inv_fp64_equiv_tflops": (M * n * (n + 1) + n ** 3) / (t_cov + t_chol) / 1e12 if t_cov else None,
+            "dmma_peak_tflops_measured": dmma.value, "dfma_peak_tflops_measured": dfma.value,
+            "chol_inv_frac_of_dmma_peak": (n ** 3 / t_chol / 1e12) / dmma.value if t_chol else None,
+        }
+
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(L, M, score, pc)
+
+    line = {
+        "metric": METRIC, "value": ms_step / 1e3, "unit": "s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic L={L} M={M} theta=auto score={score} pseudocount={pc} min_separation=5 "
+                               f"(BASELINE.json configs[{'BCD'.find(args.workload) + 1}])",
+                   "seed": SEED, "generator": "SURVEY 8(d) clustered SplitMix64", "l2": "256 MiB flush write between steps",
+                   "sharding": ("single GPU" if world == 1 else f"pair tiles + covariance rows over {world} ranks, "
+                                "NCCL all-reduce(int32 counts)/reduce(f64 C); inverse+scores on rank 0")},
+        "theta": stats["theta"] if world == 1 else None, "thresh": stats["thresh"] if world == 1 else None,
+        "meff": stats["meff"] if world == 1 else None, "top_pair": top,
+        "e2e": e2e, "gpu_launches": int(launches2 - launches1),
+        "clocks": clocks, "roofline": roof, "stages": stages, "cpu_baseline": cb,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

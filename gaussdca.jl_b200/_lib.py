@@ -61,6 +61,8 @@ SIGNATURES = {
     "gdca_set_shard": (_i32, [_p, _i32, _i32]),
     "gdca_run": (_i32, [_p, _p, _i64, _i64, _dbl, _dbl, _i32, _i64, _p, _i64, ctypes.POINTER(Stats)]),
     "gdca_ranking_length": (_i64, [_i64, _i64]),
+    "gdca_run_resident": (_i32, [_p, _p, _i64, _i64, _dbl, _dbl, _i32, _i64, _p, _i64, ctypes.POINTER(Stats)]),
+    "gdca_dev_R_ptr": (_p, [_p]),
     "gdca_compute_weights": (_i32, [_p, _p, _i64, _i64, _dbl, _p, _p, _pdbl, _pdbl, _pi64, _pu64]),
     "gdca_compute_covariance": (_i32, [_p, _p, _i64, _i64, _p, _dbl, _dbl, _p, _p, _pi32]),
     "gdca_inverse": (_i32, [_p, _p, _i64, _p, _pi32]),

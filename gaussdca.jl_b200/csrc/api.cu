@@ -415,8 +415,9 @@ int32_t gdca_dev_get_stats(gdca_ctx *ctx, gdca_stats_t *stats) {
 }
 
 // ------------------------------------------------------------------ fused run
-int32_t gdca_run(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, double pseudocount, int32_t score,
-                 int64_t min_separation, gdca_rank_t *R, int64_t R_len, gdca_stats_t *stats) {
+static int32_t run_impl(gdca_ctx *ctx, const int8_t *Z, bool resident, int64_t L, int64_t M, double theta,
+                        double pseudocount, int32_t score, int64_t min_separation, gdca_rank_t *R, int64_t R_len,
+                        gdca_stats_t *stats) {
   GDCA_TRY(check_LM(ctx, Z, L, M));
   // the reference's check_arguments ranges (src/GaussDCA.jl:49-65); theta < 0 encodes :auto
   if (!(pseudocount >= 0.0 && pseudocount <= 1.0))
@@ -428,14 +429,17 @@ int32_t gdca_run(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double th
   if (min_separation < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid min_separation value (must be >= 1)");
   if (R_len != gdca_ranking_length(L, min_separation))
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R_len != (L-min_separation)*(L-min_separation+1)/2");
-  if (R_len > 0 && !R) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R is NULL");
+  if (R_len > 0 && !R && !resident) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R is NULL");
   if (M < 2 && theta < 0) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "theta = :auto needs at least 2 sequences");
   ctx->stats = gdca_stats_t{};
   const int32_t saved_rank = ctx->shard_rank, saved_world = ctx->shard_world;
   ctx->shard_rank = 0;
   ctx->shard_world = 1;
   auto body = [&]() -> int32_t {
-    GDCA_TRY(gdca_dev_load(ctx, Z, L, M));
+    if (resident)
+      GDCA_TRY(gdca_dev_load_resident(ctx, Z, L, M));
+    else
+      GDCA_TRY(gdca_dev_load(ctx, Z, L, M));
     GDCA_TRY(weights_stage(ctx, theta));
     GDCA_TRY(gdca_k_covariance(ctx, pseudocount));
     GDCA_TRY(gdca_k_symmetrize_C(ctx));
@@ -448,7 +452,7 @@ int32_t gdca_run(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double th
     GDCA_TRY(rec(ctx, EV_APC));
     GDCA_TRY(gdca_k_rank(ctx, min_separation, R_len));
     GDCA_TRY(rec(ctx, EV_RANK));
-    if (R_len > 0)
+    if (R_len > 0 && R)
       GDCA_CUDA(ctx, cudaMemcpyAsync(R, ctx->dR, (size_t)R_len * sizeof(gdca_rank_t), cudaMemcpyDeviceToHost, ctx->stream));
     GDCA_TRY(rec(ctx, EV_D2H));
     GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -475,6 +479,19 @@ int32_t gdca_run(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double th
   if (stats) *stats = st;
   return status;
 }
+
+int32_t gdca_run(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, double pseudocount, int32_t score,
+                 int64_t min_separation, gdca_rank_t *R, int64_t R_len, gdca_stats_t *stats) {
+  return run_impl(ctx, Z, false, L, M, theta, pseudocount, score, min_separation, R, R_len, stats);
+}
+
+int32_t gdca_run_resident(gdca_ctx *ctx, const int8_t *Z_dev, int64_t L, int64_t M, double theta, double pseudocount,
+                          int32_t score, int64_t min_separation, gdca_rank_t *R_host_or_null, int64_t R_len,
+                          gdca_stats_t *stats) {
+  return run_impl(ctx, Z_dev, true, L, M, theta, pseudocount, score, min_separation, R_host_or_null, R_len, stats);
+}
+
+void *gdca_dev_R_ptr(gdca_ctx *ctx) { return ctx ? ctx->dR : nullptr; }
 
 // ------------------------------------------------------------------ staged, host buffers
 int32_t gdca_compute_weights(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, int32_t *counts,

@@ -1,0 +1,211 @@
+"""One-process-per-GPU driver for the stages of gDCA that shard.
+
+The reference has no multi-device path (one Julia process, shared-memory threads, README.md:92-94);
+this is new.  Work partition, chosen so that every exchanged quantity is an exact integer or a
+sum with zeros (results are bit-identical for any number of ranks):
+
+  pair sweep   tiles (bi <= bj) of the M x M pair matrix dealt round-robin to ranks; every rank holds the
+               whole packed alignment.  Exchange: all-reduce(sum) of int32 counts[3][Mpad] and of the
+               u64 {hamming sum, pairs visited}  -- 2.4 MB at M = 200k.
+  covariance   output rows dealt to ranks by site (i mod world); each rank writes its rows of C into a
+               zeroed n x n buffer.  Exchange: reduce(sum) to rank 0 -- adding zeros is exact.
+  inverse, scores, APC, ranking: rank 0 (n^3 flop on one GPU; the block scores are HBM-bound
+               microseconds).  Other ranks wait at the closing barrier.
+
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing only: the collectives run on
+buffers owned by libgdca_b200.so, enqueued on the library's own CUDA stream.
+
+The control flow lives in `run_sharded`, written against a small backend interface so that the
+host logic (speculative threshold, row selection, who does what) is testable on CPU with gloo.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+
+def theta_from_ham(L: int, M: int, ham_sum: int):
+    """Host arithmetic of gdca_theta_from_ham_sum (same IEEE operations in the same order)."""
+    npairs = M * (M - 1) // 2
+    ident = npairs * L - ham_sum
+    meanfracid = (ident / L) / (0.5 * M * (M - 1))
+    theta = 0.5 if meanfracid == 0.0 else min(0.5, 0.38 * 0.32 / meanfracid)
+    return theta, int(math.floor(theta * L)), ident
+
+
+def sample_stride(M: int, n_units: int, tile: int = 128) -> int:
+    """Every stride-th tile of a shard is visited by the sampling sweep (0: problem too small to sample)."""
+    T = (M + tile - 1) // tile
+    stride = (T * (T + 1) // 2) // (2 * n_units)
+    return min(stride, 64) if stride >= 2 else 0
+
+
+def run_sharded(be, dist, L: int, M: int, theta, pseudocount: float, score: str, min_separation: int):
+    """gDCA from the loaded alignment on `dist.get_world_size()` ranks.  `be` is a backend (below).
+    Returns (R or None, info) -- R on rank 0 only."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    be.set_shard(rank, world)
+    info = {"passes": 0}
+    auto = isinstance(theta, str)
+    if auto:
+        guess = -1
+        stride = sample_stride(M, be.n_units() * world)
+        if stride:
+            be.pair_sample(stride)
+            ham = be.ham_tensor()
+            dist.all_reduce(ham)
+            h, npairs = (int(v) for v in be.to_host(ham))
+            if npairs > 0:
+                mean_ident = (npairs * float(L) - float(h)) / float(L) / float(npairs)
+                th = 0.5 if mean_ident == 0.0 else min(0.5, 0.38 * 0.32 / mean_ident)
+                guess = int(math.floor(th * L))
+        be.pair_pass(2 if guess >= 0 else 0, max(guess, 0))
+        info["passes"] = 1
+        ham = be.ham_tensor()
+        dist.all_reduce(ham)
+        if guess >= 0:
+            dist.all_reduce(be.counts_tensor())
+        h, npairs = (int(v) for v in be.to_host(ham))
+        assert npairs == M * (M - 1) // 2, (npairs, M)
+        th, thresh, ident = theta_from_ham(L, M, h)
+        info.update(theta=th, thresh=thresh, ident_sum=ident)
+        if guess >= 0 and guess - 1 <= thresh <= guess + 1:
+            which = thresh - (guess - 1)
+        else:
+            be.pair_pass(1, thresh)
+            dist.all_reduce(be.counts_tensor())
+            info["passes"] += 1
+            which = 0
+    else:
+        th = float(theta)
+        thresh = int(math.floor(th * L))
+        info.update(theta=th, thresh=thresh)
+        if th == 0.0:
+            which = -1
+        else:
+            be.pair_pass(1, thresh)
+            dist.all_reduce(be.counts_tensor())
+            info["passes"] = 1
+            which = 0
+    info["meff"] = be.finish_weights(which)      # every rank: W = 1/count, Meff (identical everywhere)
+    be.covariance(pseudocount)                   # this rank's rows of C, zeros elsewhere
+    if world > 1:
+        dist.reduce(be.C_tensor(), dst=0)
+    R = None
+    if rank == 0:
+        be.inverse()
+        R = be.score_rank(score, min_separation)
+    dist.barrier()
+    return R, info
+
+
+class GpuBackend:
+    """The real thing: libgdca_b200.so on this rank's GPU; tensors are views of the library's buffers."""
+
+    def __init__(self, ctx):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.stream = torch.cuda.ExternalStream(int(self.lib.gdca_dev_stream(ctx.h)), device=ctx.device)
+        self.L = self.M = 0
+
+    # -- views of library-owned device memory (no copies)
+    def _view(self, ptr, shape, typestr):
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                      "strides": None}
+        return self.torch.as_tensor(h, device=f"cuda:{self.ctx.device}")
+
+    def n_units(self):
+        return self.torch.cuda.get_device_properties(self.ctx.device).multi_processor_count
+
+    def load(self, Z, resident=False):
+        M, L = Z.shape
+        self.L, self.M = L, M
+        if resident:   # Z: torch int8 tensor on this device
+            self.ctx.check(self.lib.gdca_dev_load_resident(self.ctx.h, ctypes.c_void_p(Z.data_ptr()), L, M))
+        else:
+            self.ctx.check(self.lib.gdca_dev_load(self.ctx.h, Z.ctypes.data_as(ctypes.c_void_p), L, M))
+
+    def set_shard(self, rank, world):
+        self.ctx.check(self.lib.gdca_set_shard(self.ctx.h, rank, world))
+
+    def pair_sample(self, stride):
+        self.ctx.check(self.lib.gdca_dev_pair_sample(self.ctx.h, stride))
+
+    def pair_pass(self, mode, thresh):
+        self.ctx.check(self.lib.gdca_dev_pair_pass(self.ctx.h, mode, thresh))
+
+    def ham_tensor(self):
+        return self._view(self.lib.gdca_dev_ham_sum_ptr(self.ctx.h), (2,), "<i8")
+
+    def counts_tensor(self):
+        return self._view(self.lib.gdca_dev_counts_ptr(self.ctx.h), (3 * self.lib.gdca_dev_counts_stride(self.ctx.h),), "<i4")
+
+    def C_tensor(self):
+        npad = self.lib.gdca_dev_npad(self.ctx.h)
+        return self._view(self.lib.gdca_dev_C_ptr(self.ctx.h), (npad * npad,), "<f8")
+
+    def to_host(self, t):
+        with self.torch.cuda.stream(self.stream):   # ordered after the collective on the library stream
+            return t.cpu().tolist()
+
+    def finish_weights(self, which):
+        meff = ctypes.c_double()
+        self.ctx.check(self.lib.gdca_dev_finish_weights(self.ctx.h, which, ctypes.byref(meff)))
+        return meff.value
+
+    def covariance(self, pc):
+        self.ctx.check(self.lib.gdca_dev_covariance(self.ctx.h, float(pc)))
+
+    def inverse(self):
+        info = ctypes.c_int32()
+        self.ctx.check(self.lib.gdca_dev_inverse(self.ctx.h, ctypes.byref(info)))
+
+    def score_rank(self, score, min_separation, to_host=True):
+        from ._lib import RANK_DTYPE, SCORE_CODES, ptr
+        n_out = int(self.lib.gdca_ranking_length(self.L, int(min_separation)))
+        R = np.empty(n_out, dtype=RANK_DTYPE) if to_host else None
+        self.ctx.check(self.lib.gdca_dev_score_rank(self.ctx.h, SCORE_CODES[score], int(min_separation), ptr(R), n_out))
+        return R
+
+
+class _StreamDist:
+    """torch.distributed with every collective enqueued on the library's CUDA stream."""
+
+    def __init__(self, dist, torch, stream):
+        self.d, self.torch, self.stream = dist, torch, stream
+
+    def get_rank(self):
+        return self.d.get_rank()
+
+    def get_world_size(self):
+        return self.d.get_world_size()
+
+    def all_reduce(self, t):
+        with self.torch.cuda.stream(self.stream):
+            self.d.all_reduce(t)
+
+    def reduce(self, t, dst=0):
+        with self.torch.cuda.stream(self.stream):
+            self.d.reduce(t, dst=dst)
+
+    def barrier(self):
+        self.stream.synchronize()
+        self.d.barrier()
+
+
+def gdca_sharded(Z, pseudocount=0.8, theta="auto", score="frob", min_separation=5, *, ctx, resident=False):
+    """Run gDCA on all ranks of the default process group (NCCL).  Every rank passes the same Z.
+    -> (R structured array on rank 0 / None elsewhere, info)."""
+    import torch
+    import torch.distributed as dist
+    be = GpuBackend(ctx)
+    be.load(Z, resident=resident)
+    sd = _StreamDist(dist, torch, be.stream)
+    return run_sharded(be, sd, be.L, be.M, theta, pseudocount, score, min_separation)

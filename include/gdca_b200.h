@@ -84,6 +84,12 @@ int32_t gdca_set_shard(gdca_ctx *ctx, int32_t rank, int32_t world);
 int32_t gdca_run(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, double pseudocount,
                  int32_t score, int64_t min_separation, gdca_rank_t *R, int64_t R_len, gdca_stats_t *stats);
 int64_t gdca_ranking_length(int64_t L, int64_t min_separation);
+/* Same pipeline with Z already resident in device memory (L*M int8).  The ranking stays on the device
+ * (gdca_dev_R_ptr) and is also copied to R_host_or_null when that is not NULL. */
+int32_t gdca_run_resident(gdca_ctx *ctx, const int8_t *Z_dev, int64_t L, int64_t M, double theta, double pseudocount,
+                          int32_t score, int64_t min_separation, gdca_rank_t *R_host_or_null, int64_t R_len,
+                          gdca_stats_t *stats);
+void *gdca_dev_R_ptr(gdca_ctx *ctx); /* gdca_rank_t[R_len] on the device after a run / score_rank */
 
 /* ---- staged entry points, HOST buffers (parity tests; DCAUtils-shaped pieces) ------------------ */
 /* compute_theta + compute_weights (call site src/GaussDCA.jl:28).  theta < 0 => :auto.
