@@ -1,0 +1,152 @@
+"""CPU: host-side logic of the product and the C-ABI surface (no GPU, no compute calls)."""
+import ctypes
+import io
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_path
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "gdca_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gdca_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    """The in-tree .so loads and exports everything include/gdca_b200.h declares; the ctypes table covers it."""
+    from gaussdca_jl_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = pkg.load()
+    names = header_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} declared in the header but not bound in _lib.SIGNATURES"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.gdca_abi_version() == 1
+    assert lib.gdca_ranking_length(53, 5) == 48 * 49 // 2 == 1176           # src/GaussDCA.jl:90
+    assert lib.gdca_ranking_length(53, 4) == 1225 and lib.gdca_ranking_length(400, 5) == 78210
+    assert lib.gdca_ranking_length(5, 5) == 0 and lib.gdca_ranking_length(3, 5) == 0
+    assert lib.gdca_status_string(3) == b"matrix is not positive definite"
+
+
+def test_struct_layouts_match_the_header(pkg, tmp_path):
+    from gaussdca_jl_b200 import _lib
+    c = tmp_path / "sz.c"
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gdca_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu",'
+                 'sizeof(gdca_rank_t),offsetof(gdca_rank_t,j),offsetof(gdca_rank_t,score),sizeof(gdca_stats_t),'
+                 'offsetof(gdca_stats_t,theta),offsetof(gdca_stats_t,ms_h2d));return 0;}')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    S = _lib.Stats
+    assert got == [24, 8, 16, ctypes.sizeof(S), S.theta.offset, S.ms_h2d.offset]
+    assert _lib.RANK_DTYPE.itemsize == 24 and _lib.RANK_DTYPE.fields["j"][1] == 8 and _lib.RANK_DTYPE.fields["score"][1] == 16
+
+
+def test_theta_host_arithmetic_matches_oracle(pkg, orc):
+    """gdca_theta_from_ham_sum is host code in the library: same IEEE operations as the oracle."""
+    from gaussdca_jl_b200.dist import theta_from_ham
+    lib = pkg.load()
+    rng = np.random.default_rng(0)
+    for L, M in [(53, 106), (400, 94), (500, 200000), (1500, 1000000), (1, 2)]:
+        npairs = M * (M - 1) // 2
+        for frac in (0.0, 0.05, 0.3123, 0.9, 1.0):
+            ident = int(npairs * L * frac) + int(rng.integers(0, 3)) * (frac not in (0.0, 1.0))
+            ham = npairs * L - ident
+            th, thr, ids = ctypes.c_double(), ctypes.c_int64(), ctypes.c_uint64()
+            assert lib.gdca_theta_from_ham_sum(L, M, ham, ctypes.byref(th), ctypes.byref(thr), ctypes.byref(ids)) == 0
+            want = orc.theta_from_ident_sum(ident, L, M)
+            assert th.value == want and ids.value == ident and thr.value == int(np.floor(want * L))
+            assert theta_from_ham(L, M, ham) == (want, thr.value, ident)
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a GPU the product refuses to run (it must never route through the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.GdcaError, match="no CPU fallback"):
+        pkg.Context(0)
+    with pytest.raises(pkg.GdcaError):
+        pkg.gDCA(golden_path("small.fasta.gz"))
+    src = "".join(open(os.path.join(ROOT, "gaussdca.jl_b200", f)).read()
+                  for f in ("__init__.py", "api.py", "_lib.py", "fasta.py", "dist.py"))
+    assert "oracle" not in src.replace("oracle/", "").replace("the oracle", "").replace("oracle's", "").replace("oracle theta", "")
+
+
+def test_check_arguments_messages(pkg):
+    """src/GaussDCA.jl:49-65: same conditions, same messages."""
+    fa = golden_path("small.fasta.gz")
+    ok = dict(filename=fa, pseudocount=0.8, theta="auto", max_gap_fraction=0.9, score="frob", min_separation=5)
+    assert pkg.check_arguments(**ok) is True
+    cases = [
+        (dict(pseudocount=-0.1), "invalid pseudocount value: -0.1 (must be between 0 and 1)"),
+        (dict(theta=1.5), "invalid θ value: 1.5 (must be either :auto, or a number between 0 and 1)"),
+        (dict(theta="automatic"), "invalid θ value: automatic"),
+        (dict(max_gap_fraction=2), "invalid max_gap_fraction value: 2 (must be between 0 and 1)"),
+        (dict(score="mi"), "invalid score value: mi (must be either :DI or :frob)"),
+        (dict(min_separation=0), "invalid min_separation value: 0 (must be >= 1)"),
+        (dict(filename="/nonexistent.fasta"), "cannot open file /nonexistent.fasta"),
+    ]
+    for kw, msg in cases:
+        with pytest.raises(ValueError) as e:
+            pkg.check_arguments(**{**ok, **kw})
+        assert msg in str(e.value)
+    for th in (0, 0.0, 1, 0.37):
+        assert pkg.check_arguments(**{**ok, "theta": th})
+
+
+def test_fasta_reader_and_dedup_match_oracle(pkg, orc, tmp_path):
+    for fa, mg in [("small.fasta.gz", 0.9), ("small.fasta.gz", 0.8), ("large.fasta.gz", 0.9), ("large.fasta.gz", 0.5)]:
+        Z, Zo = pkg.read_fasta_alignment(golden_path(fa), mg), orc.read_fasta_alignment(golden_path(fa), mg)
+        assert Z.dtype == np.int8 and Z.flags.c_contiguous and np.array_equal(Z, Zo)
+        Zd, keep = pkg.remove_duplicate_sequences(Z)
+        assert np.array_equal(Zd, orc.remove_duplicate_sequences(Zo)) and np.array_equal(Zd, Z[keep])
+    assert pkg.read_fasta_alignment(golden_path("small.fasta.gz"), 0.9).shape == (106, 53)
+    Zl = pkg.read_fasta_alignment(golden_path("large.fasta.gz"), 0.9)
+    assert Zl.shape == (97, 400) and pkg.remove_duplicate_sequences(Zl)[0].shape == (94, 400)
+    # insert columns ('.' and lowercase) are skipped; odd letters map to 21; plain-text files work
+    p = tmp_path / "t.fasta"
+    p.write_text(">a\nAC.dE-\n>b\nXZ.fBY\n>c\n--.g--\n")
+    Z = pkg.read_fasta_alignment(str(p), 0.9)
+    assert Z.tolist() == [[1, 2, 4, 21], [21, 21, 21, 20]]            # third sequence is all gaps -> filtered
+    assert np.array_equal(Z, orc.read_fasta_alignment(str(p), 0.9))
+    assert pkg.read_fasta_alignment(str(p), 1.0).shape == (3, 4)
+    p.write_text(">a\nACD\n>b\nAC\n")
+    with pytest.raises(ValueError, match="not aligned"):
+        pkg.read_fasta_alignment(str(p), 0.9)
+
+
+def test_printrank_format(pkg, orc, tmp_path):
+    R = [(11, 35, 3.6494745366789094), (9, 37, 1.676179e+00), (1, 6, -2.5e-05)]
+    buf = io.StringIO()
+    pkg.printrank(buf, R)
+    assert buf.getvalue() == "11 35 3.649475e+00\n9 37 1.676179e+00\n1 6 -2.500000e-05\n" == orc.format_rank(R)
+    out = tmp_path / "r.txt"
+    pkg.printrank(str(out), R)
+    assert out.read_text() == buf.getvalue()
+    from gaussdca_jl_b200._lib import RANK_DTYPE
+    arr = np.array(R, dtype=RANK_DTYPE)
+    buf2 = io.StringIO()
+    pkg.printrank(buf2, arr)
+    assert buf2.getvalue() == buf.getvalue()
+
+
+def test_julia_wrapper_is_consistent_with_header():
+    """Julia is absent here, so the wrapper is checked statically: every ccall names an exported symbol and
+    the public surface of src/GaussDCA.jl:3,8-16,67-74 is present."""
+    jl = open(os.path.join(ROOT, "gaussdca.jl_b200", "julia", "GaussDCA.jl")).read()
+    called = set(re.findall(r"ccall\(\(:(gdca_[A-Za-z0-9_]+)", jl))
+    assert called and called <= set(header_functions())
+    assert {"gdca_create", "gdca_run", "gdca_last_error", "gdca_ranking_length"} <= called
+    assert "export gDCA, printrank" in jl
+    for kw in ("pseudocount::Real = 0.8", "θ = :auto", "max_gap_fraction::Real = 0.9", "score::Symbol = :frob",
+               "min_separation::Integer = 5", "remove_dups::Bool = false"):
+        assert kw in jl
+    assert "Vector{Tuple{Int,Int,Float64}}" in jl and "PosDefException" in jl
