@@ -3,7 +3,7 @@
 // Hand-written blocked factorisation and inversion, FP64 throughout, all matrix products on the
 // FP64 tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4; tcgen05 has no FP64 kind):
 //
-//   potrf  right-looking, NB = 128:   A[k,k] -> L[k,k] and inv(L[k,k])        (one CTA, shared memory)
+//   potrf  right-looking, NB = 128:   A[k,k] -> L[k,k] and inv(L[k,k])        (one CTA, registers)
 //                                     L[I,k] = A[I,k] * inv(L[k,k])'          (GEMM, replaces TRSM)
 //                                     A[I,J] -= L[I,k] * L[J,k]'   (I>=J>k)   (GEMM, lower tiles only)
 //   trtri  X = L^-1 by recursive doubling: X21 = -X22 * (L21 * X11), batched over the diagonal;
@@ -157,63 +157,118 @@ __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(GemmP p) {
 }
 
 // ---- diagonal block: A[k,k] (lower) -> inv(chol(A[k,k])) written to X[k,k] (lower, zeros above) ----
+// One CTA, 512 threads as 16 (ty) x 32 (tx).  Thread (ty,tx) keeps the 32 elements
+// (i = ty + 16a, c = tx + 32b), a < 8, b < 4, in REGISTERS.  Both phases are right-looking rank-1
+// sweeps with one barrier per column: the owners publish column j (raw, un-scaled) / row k through a
+// double-buffered shared line, everybody updates its registers from it.
 constexpr int DT = 512;
 constexpr int DLD = NB + 1;
 
-__global__ void __launch_bounds__(DT) diag_block_kernel(const double *__restrict__ Akk, long long lda,
-                                                        double *__restrict__ Xkk, long long ldx, int col0,
-                                                        int n_true, int *__restrict__ info) {
-  extern __shared__ double S[];  // [NB][DLD]
-  __shared__ double colbuf[NB];
-  const int tid = threadIdx.x;
-  for (int e = tid; e < NB * NB; e += DT) {
-    const int r = e >> 7, cc = e & 127;
-    S[r * DLD + cc] = (cc <= r) ? Akk[(long long)r * lda + cc] : 0.0;
-  }
-  __syncthreads();
-  // ---- unblocked right-looking Cholesky, lower ----
-  for (int j = 0; j < NB; ++j) {
-    const double d = S[j * DLD + j];
-    if (!(d > 0.0)) {  // also catches NaN
-      if (tid == 0 && col0 + j < n_true) atomicCAS(info, 0, col0 + j + 1);
+__global__ void __launch_bounds__(DT, 1) diag_block_kernel(const double *__restrict__ Akk, long long lda,
+                                                           double *__restrict__ Xkk, long long ldx, int col0,
+                                                           int n_true, int *__restrict__ info) {
+  extern __shared__ double Ls[];  // [NB][DLD]: the factor, for phase 2
+  __shared__ double line[2][NB];
+  __shared__ double rdiag[NB];  // 1 / L[j][j]
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+
+  double v[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, c = tx + 32 * b;
+      v[a][b] = (c <= i) ? Akk[(long long)i * lda + c] : 0.0;
     }
-    const double sj = sqrt(d);
-    __syncthreads();  // everyone has read the pivot
-    for (int i = j + tid; i < NB; i += DT) S[i * DLD + j] = (i == j) ? sj : S[i * DLD + j] / sj;
-    __syncthreads();
-    // trailing update of the lower triangle: rows i > j, cols j < cc <= i
-    const int rem = NB - 1 - j;
-    for (int e = tid; e < rem * rem; e += DT) {
-      const int ii = e / rem, cj = e - ii * rem;
-      if (cj <= ii) {
-        const int i = j + 1 + ii, cc = j + 1 + cj;
-        S[i * DLD + cc] -= S[i * DLD + j] * S[cc * DLD + j];
+
+  // ---------------- phase 1: Cholesky, lower ----------------
+  for (int j = 0; j < NB; ++j) {
+    double *col = line[j & 1];
+    if (tx == (j & 31)) {
+      const int bj = j >> 5;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const double x = (bj == 0) ? v[a][0] : (bj == 1) ? v[a][1] : (bj == 2) ? v[a][2] : v[a][3];
+        col[ty + 16 * a] = x;
       }
     }
     __syncthreads();
-  }
-  // ---- in-place inverse of the lower-triangular factor (columns right to left) ----
-  for (int j = NB - 1; j >= 0; --j) {
-    const double xjj = 1.0 / S[j * DLD + j];
-    // t_i = sum_{k=j+1..i} X[i][k] * L[k][j], i > j: 4 threads per row, strided over k
-    const int i = j + 1 + (tid >> 2), part = tid & 3;
-    double t = 0.0;
-    if (i < NB) {
-      for (int k = j + 1 + part; k <= i; k += 4) t += S[i * DLD + k] * S[k * DLD + j];
+    const double d = col[j];
+    if (!(d > 0.0)) {  // also catches NaN
+      if (tid == 0 && col0 + j < n_true) atomicCAS(info, 0, col0 + j + 1);
     }
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    __syncthreads();  // all reads of column j done
-    if (i < NB && part == 0) colbuf[i] = -t * xjj;
-    if (tid == 0) colbuf[j] = xjj;
-    __syncthreads();
-    for (int r = j + tid; r < NB; r += DT) S[r * DLD + j] = colbuf[r];
-    __syncthreads();
+    const double rinv = __drcp_rn(d);  // MUFU.RCP64H + Newton, IEEE-rounded; no slow division path
+    const double rs = rsqrt(d);
+    if (tid == 0) rdiag[j] = rs;
+    double ci[8], cc[4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) ci[a] = col[ty + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) cc[b] = col[tx + 32 * b] * rinv;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = tx + 32 * b;
+      if (c > j) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) v[a][b] = fma(-ci[a], cc[b], v[a][b]);
+      } else if (c == j) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) v[a][b] = (ty + 16 * a == j) ? d * rs : v[a][b] * rs;  // final L[:, j]
+      }
+    }
   }
-  for (int e = tid; e < NB * NB; e += DT) {
-    const int r = e >> 7, cc = e & 127;
-    Xkk[(long long)r * ldx + cc] = (cc <= r) ? S[r * DLD + cc] : 0.0;
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, c = tx + 32 * b;
+      Ls[i * DLD + c] = (c <= i) ? v[a][b] : 0.0;
+    }
+  __syncthreads();
+
+  // ---------------- phase 2: X = L^-1 by forward substitution on all 128 right-hand sides ----------------
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) v[a][b] = (ty + 16 * a == tx + 32 * b) ? 1.0 : 0.0;
+  for (int k = 0; k < NB; ++k) {
+    double *row = line[k & 1];
+    {
+      const double dk = rdiag[k];
+      const bool own = (ty == (k & 15));
+      const int ak = k >> 4;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const bool mine = own && (a == ak);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double nv = v[a][b] * dk;  // X[k, c] final
+          v[a][b] = mine ? nv : v[a][b];
+          if (mine) row[tx + 32 * b] = nv;
+        }
+      }
+    }
+    __syncthreads();
+    double li[8], xr[4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) li[a] = Ls[(ty + 16 * a) * DLD + k];  // zero for i < k
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xr[b] = row[tx + 32 * b];             // zero for c > k
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      if (ty + 16 * a > k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[a][b] = fma(-li[a], xr[b], v[a][b]);
+      }
+    }
   }
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, c = tx + 32 * b;
+      Xkk[(long long)i * ldx + c] = (c <= i) ? v[a][b] : 0.0;
+    }
 }
 
 __global__ void pad_identity_kernel(double *__restrict__ C, long long n, long long npad) {
@@ -241,12 +296,8 @@ __global__ void mirror_lower_kernel(double *__restrict__ A, long long n, long lo
 template <bool AT, bool BT>
 int32_t gemm(gdca_ctx *ctx, const GemmP &p, int batch) {
   if (p.m <= 0 || p.n <= 0 || batch <= 0) return GDCA_OK;
-  static bool configured = false;
   const size_t smem = (size_t)GSTAGES * 2 * TILE_D * sizeof(double);
-  if (!configured) {
-    GDCA_CUDA(ctx, cudaFuncSetAttribute(dgemm_kernel<AT, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(dgemm_kernel<AT, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)(p.n / NB), (unsigned)(p.m / NB), (unsigned)batch);
   dgemm_kernel<AT, BT><<<grid, GTHREADS, smem, ctx->stream>>>(p);
   GDCA_LAUNCH_CHECK(ctx);
@@ -270,33 +321,48 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
     GDCA_LAUNCH_CHECK(ctx);
   }
   const size_t dsmem = (size_t)NB * DLD * sizeof(double);
-  static bool dconf = false;
-  if (!dconf) {
-    GDCA_CUDA(ctx, cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
-    dconf = true;
-  }
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
   auto blk = [&](double *base, int I, int Jb) { return base + ((long long)I * NB) * np + (long long)Jb * NB; };
 
-  // ---------------- potrf ----------------
-  for (int k = 0; k < nb; ++k) {
-    diag_block_kernel<<<1, DT, dsmem, ctx->stream>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
-    GDCA_LAUNCH_CHECK(ctx);
-    const int rem = nb - k - 1;
-    if (rem == 0) break;
-    GemmP p{};
-    // panel: L[I,k] = A[I,k] * X[k,k]'   (in place)
-    p.A = blk(A, k + 1, k); p.lda = np;
-    p.B = blk(X, k, k);     p.ldb = np;
-    p.C = blk(A, k + 1, k); p.ldc = np;
-    p.m = rem * NB; p.n = NB; p.k = NB; p.flags = 0; p.alpha = 1.0; p.beta = 0.0;
-    GDCA_TRY((gemm<false, false>(ctx, p, 1)));
-    // trailing: A[I,J] -= L[I,k] L[J,k]'  for I >= J > k
-    GemmP t{};
-    t.A = blk(A, k + 1, k); t.lda = np;
-    t.B = blk(A, k + 1, k); t.ldb = np;
-    t.C = blk(A, k + 1, k + 1); t.ldc = np;
-    t.m = rem * NB; t.n = rem * NB; t.k = NB; t.flags = G_LOWER_OUT; t.alpha = -1.0; t.beta = 1.0;
-    GDCA_TRY((gemm<false, false>(ctx, t, 1)));
+  // ---------------- potrf: two-level right-looking ----------------
+  // inner step (128 columns): diagonal block, panel, update of the remaining columns of the OUTER block only;
+  // after OB inner steps one trailing update with K = OB*128 (C tiles read/written n/512 times, not n/128).
+  constexpr int OB = 4;
+  for (int K0 = 0; K0 < nb; K0 += OB) {
+    const int Kend = (K0 + OB < nb) ? K0 + OB : nb;
+    for (int k = K0; k < Kend; ++k) {
+      diag_block_kernel<<<1, DT, dsmem, ctx->stream>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
+      GDCA_LAUNCH_CHECK(ctx);
+      const int rem = nb - k - 1;
+      if (rem == 0) break;
+      GemmP p{};
+      // panel: L[I,k] = A[I,k] * X[k,k]'   (in place)
+      p.A = blk(A, k + 1, k); p.lda = np;
+      p.B = blk(X, k, k);     p.ldb = np;
+      p.C = blk(A, k + 1, k); p.ldc = np;
+      p.m = rem * NB; p.n = NB; p.k = NB; p.flags = 0; p.alpha = 1.0; p.beta = 0.0;
+      GDCA_TRY((gemm<false, false>(ctx, p, 1)));
+      const int inner_cols = Kend - k - 1;
+      if (inner_cols > 0) {
+        // A[I,J] -= L[I,k] L[J,k]'  for k < J < Kend, I >= J
+        GemmP t{};
+        t.A = blk(A, k + 1, k); t.lda = np;
+        t.B = blk(A, k + 1, k); t.ldb = np;
+        t.C = blk(A, k + 1, k + 1); t.ldc = np;
+        t.m = rem * NB; t.n = inner_cols * NB; t.k = NB; t.flags = G_LOWER_OUT; t.alpha = -1.0; t.beta = 1.0;
+        GDCA_TRY((gemm<false, false>(ctx, t, 1)));
+      }
+    }
+    const int rem = nb - Kend;
+    if (rem > 0) {
+      // A[I,J] -= L[I,K0:Kend] L[J,K0:Kend]'  for I >= J >= Kend
+      GemmP t{};
+      t.A = blk(A, Kend, K0); t.lda = np;
+      t.B = blk(A, Kend, K0); t.ldb = np;
+      t.C = blk(A, Kend, Kend); t.ldc = np;
+      t.m = rem * NB; t.n = rem * NB; t.k = (Kend - K0) * NB; t.flags = G_LOWER_OUT; t.alpha = -1.0; t.beta = 1.0;
+      GDCA_TRY((gemm<false, false>(ctx, t, 1)));
+    }
   }
 
   // ---------------- trtri by recursive doubling ----------------
