@@ -279,7 +279,26 @@ def main():
         R = np.frombuffer(Rh.numpy(), dtype=glib.RANK_DTYPE)
         top = [int(R["i"][0]), int(R["j"][0]), float(R["score"][0])]
     else:
-        top = None
+        # N > 1: the public sharded API with HOST input on every rank (H2D inside), ranking copied to the host on rank 0
+        Zh = torch.empty((M, L), dtype=torch.int8).pin_memory()
+        Zh.copy_(Zd)
+        Zn = Zh.numpy()
+        e_ms = []
+        for it in range(2 + K):
+            l2_flush()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            R, _ = gdist.gdca_sharded(Zn, pc, "auto", score, 5, ctx=ctx, resident=False)
+            b.record(stream)
+            barrier()
+            tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if it >= 2:
+                e_ms.append(float(tt.item()))
+        e2e = {"value": sum(e_ms) / len(e_ms) / 1e3, "unit": "s", "h2d_bytes_per_step": L * M * world,
+               "d2h_bytes_per_step": n_out * 24}
+        top = [int(R["i"][0]), int(R["j"][0]), float(R["score"][0])] if rank == 0 else None
 
     if rank != 0:
         if dist is not None:
@@ -289,13 +308,14 @@ def main():
     # ---- roofline of the dominant kernel (pair sweep), measured live
     roof, stages = None, None
     pk = peaks()
-    if world == 1:
+    if True:
         lop3, popc, dmma, dfma = (ctypes.c_double() for _ in range(4))
         ctx.check(lib.gdca_probe_peaks(ctx.h, ctypes.byref(lop3), ctypes.byref(popc), ctypes.byref(dmma), ctypes.byref(dfma)))
         # time the sweep kernel alone: mode-2 launch (hamming sum + counts for 3 thresholds)
         ctx.check(lib.gdca_dev_load_resident(ctx.h, ctypes.c_void_p(Zd.data_ptr()), L, M))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        thr = int(stats["thresh"])
+        thr = int(stats["thresh"]) if world == 1 else L // 2
+        ctx.check(lib.gdca_set_shard(ctx.h, rank, world))
         tk = []
         for it in range(4):
             l2_flush()
@@ -306,12 +326,12 @@ def main():
             if it:
                 tk.append(a.elapsed_time(b))
         t_pair = sum(tk) / len(tk) / 1e3
-        npairs = M * (M - 1) // 2
+        npairs = M * (M - 1) // 2 // world   # this rank's shard of the sweep
         nwords = (L + 31) // 32
         alu_ops = npairs * nwords * 5                 # algorithmic ALU-pipe ops: 5 LOP3 per 32-site word per pair
         hbm_bytes = 4 * nwords * 5 * ((M + 127) // 128 * 128) + 3 * 4 * M   # packed planes once + counts
         roof = {
-            "kernel": "pair_sweep_kernel<5,2> (theta:auto + neighbour counts, one sweep)",
+            "kernel": "pair_sweep_kernel<5,2> (theta:auto + neighbour counts, one sweep)" + ("" if world == 1 else f", shard 0 of {world}"),
             "bound": "int32_alu",
             "achieved": alu_ops / t_pair / 1e12, "peak": lop3.value, "unit": "Tlop3/s",
             "frac": (alu_ops / t_pair / 1e12) / lop3.value,
@@ -323,12 +343,13 @@ def main():
                     "note": "compulsory bytes only; the sweep is ALU-bound, operands live in L2"},
             "survey_floor_ops_per_pair": 5 * ((L + 5) // 6),
         }
+        ctx.check(lib.gdca_set_shard(ctx.h, 0, 1))
         n = 20 * L
         t_cov, t_chol = stage_acc.get("ms_cov", 0) / 1e3, stage_acc.get("ms_chol", 0) / 1e3
-        stages = {
+        stages = None if world > 1 else {
             "ms": {k: round(v, 4) for k, v in stage_acc.items()},
             "theta_passes": stats["theta_passes"],
-            "weights_pairs_per_s": npairs / ((stage_acc.get("ms_theta", 0) + stage_acc.get("ms_weights", 0)) / 1e3),
+            "weights_pairs_per_s": npairs / ((stage_acc.get("ms_theta", 0) + stage_acc.get("ms_weights", 0)) / 1e3 + 1e-30),
             "cov_fp64_equiv_tflops": M * n * (n + 1) / t_cov / 1e12 if t_cov else None,
             "chol_inv_tflops": n ** 3 / t_chol / 1e12 if t_chol else None,
             "cov_plus_inv_fp64_equiv_tflops": (M * n * (n + 1) + n ** 3) / (t_cov + t_chol) / 1e12 if t_cov else None,

@@ -157,118 +157,170 @@ __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(GemmP p) {
 }
 
 // ---- diagonal block: A[k,k] (lower) -> inv(chol(A[k,k])) written to X[k,k] (lower, zeros above) ----
-// One CTA, 512 threads as 16 (ty) x 32 (tx).  Thread (ty,tx) keeps the 32 elements
-// (i = ty + 16a, c = tx + 32b), a < 8, b < 4, in REGISTERS.  Both phases are right-looking rank-1
-// sweeps with one barrier per column: the owners publish column j (raw, un-scaled) / row k through a
-// double-buffered shared line, everybody updates its registers from it.
+// One CTA of 16 warps, the 128 x 128 block lives in REGISTERS (32 doubles per thread), both phases are
+// right-looking rank-1 sweeps with ONE barrier per step and a one-step look-ahead:
+//   phase 1 (Cholesky): warp w owns the 8 columns c = w + 16b, lane l the 4 rows i = l + 32a.  In step j1
+//     everybody applies column j1-1; the warp that owns column j1 updates that column FIRST, finalises it
+//     (pivot by shuffle, one rsqrt) and publishes it through a double-buffered shared line while the
+//     other warps are still busy with their updates -- the serial chain hides behind the rank-1 update.
+//   phase 2 (X = L^-1, forward substitution on all 128 right-hand sides): transposed ownership (warp w
+//     owns rows i = w + 16a, lane l columns c = l + 32b), same look-ahead on rows.
+// The step loops are written as (slot, 16 steps) nests so that the owner's register slot is a
+// compile-time index (no dynamic register indexing, no select chains).
 constexpr int DT = 512;
 constexpr int DLD = NB + 1;
+#ifdef DIAG_DBG
+__device__ long long g_diag_clk[8];
+#define DIAG_STAMP(i) do { if (threadIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define DIAG_STAMP(i)
+#endif
 
 __global__ void __launch_bounds__(DT, 1) diag_block_kernel(const double *__restrict__ Akk, long long lda,
                                                            double *__restrict__ Xkk, long long ldx, int col0,
                                                            int n_true, int *__restrict__ info) {
-  extern __shared__ double Ls[];  // [NB][DLD]: the factor, for phase 2
+  extern __shared__ double Ls[];  // [NB][DLD]: staging, then the factor for phase 2
   __shared__ double line[2][NB];
-  __shared__ double rdiag[NB];  // 1 / L[j][j]
-  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  __shared__ double rdiag[NB];    // 1 / L[j][j]
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  DIAG_STAMP(0);
 
-  double v[8][4];
+  // coalesced load through shared memory (rows contiguous), then pick own elements
+  for (int e = tid; e < NB * NB; e += DT) {
+    const int r = e >> 7, c = e & 127;
+    Ls[r * DLD + c] = (c <= r) ? Akk[(long long)r * lda + c] : 0.0;
+  }
+  __syncthreads();
+  double v[4][8];  // v[a][b] = element (i = l + 32a, c = w + 16b)
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = ty + 16 * a, c = tx + 32 * b;
-      v[a][b] = (c <= i) ? Akk[(long long)i * lda + c] : 0.0;
-    }
+    for (int b = 0; b < 8; ++b) v[a][b] = Ls[(l + 32 * a) * DLD + w + 16 * b];
+  DIAG_STAMP(1);
 
   // ---------------- phase 1: Cholesky, lower ----------------
-  for (int j = 0; j < NB; ++j) {
-    double *col = line[j & 1];
-    if (tx == (j & 31)) {
-      const int bj = j >> 5;
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const double x = (bj == 0) ? v[a][0] : (bj == 1) ? v[a][1] : (bj == 2) ? v[a][2] : v[a][3];
-        col[ty + 16 * a] = x;
+  for (int b1 = 0; b1 < 8; ++b1) {        // register slot of the column being finalised
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j1 = 16 * b1 + jj;        // column finalised in this step (owner: warp jj)
+      const int j = j1 - 1;               // column applied in this step (-1: none)
+      const bool owner = (w == jj);
+      const double *col = line[j & 1];
+      double li[4], lc[8];
+      if (j >= 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) li[a] = col[l + 32 * a];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) lc[b] = col[w + 16 * b];
       }
-    }
-    __syncthreads();
-    const double d = col[j];
-    if (!(d > 0.0)) {  // also catches NaN
-      if (tid == 0 && col0 + j < n_true) atomicCAS(info, 0, col0 + j + 1);
-    }
-    const double rinv = __drcp_rn(d);  // MUFU.RCP64H + Newton, IEEE-rounded; no slow division path
-    const double rs = rsqrt(d);
-    if (tid == 0) rdiag[j] = rs;
-    double ci[8], cc[4];
+      if (owner) {
+        if (j >= 0) {
 #pragma unroll
-    for (int a = 0; a < 8; ++a) ci[a] = col[ty + 16 * a];
+          for (int a = 0; a < 4; ++a) v[a][b1] = fma(-li[a], lc[b1], v[a][b1]);
+        }
+        // pivot: row j1 = lane (j1 & 31) of slot a = j1 >> 5 = b1 >> 1 (compile time)
+        const double d = __shfl_sync(0xffffffffu, v[b1 >> 1][b1], j1 & 31);
+        if (!(d > 0.0)) {  // also catches NaN
+          if (l == 0 && col0 + j1 < n_true) atomicCAS(info, 0, col0 + j1 + 1);
+        }
+        const double rs = rsqrt(d);
+        if (l == 0) rdiag[j1] = rs;
+        double *out = line[j1 & 1];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) cc[b] = col[tx + 32 * b] * rinv;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int c = tx + 32 * b;
-      if (c > j) {
-#pragma unroll
-        for (int a = 0; a < 8; ++a) v[a][b] = fma(-ci[a], cc[b], v[a][b]);
-      } else if (c == j) {
-#pragma unroll
-        for (int a = 0; a < 8; ++a) v[a][b] = (ty + 16 * a == j) ? d * rs : v[a][b] * rs;  // final L[:, j]
+        for (int a = 0; a < 4; ++a) {
+          const int i = l + 32 * a;
+          const double lij = (i == j1) ? d * rs : ((i > j1) ? v[a][b1] * rs : 0.0);  // final L[i][j1]
+          v[a][b1] = lij;
+          out[i] = lij;
+        }
       }
+      if (j >= 0) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int c = w + 16 * b;
+          // warp-uniform: columns right of j, except the one the owner has already brought up to date
+          if (c > j && !(owner && b == b1)) {
+            // rows above the diagonal (i < c) only hold don't-care values: no per-element predicate needed
+#pragma unroll
+            for (int a = 0; a < 4; ++a) v[a][b] = fma(-li[a], lc[b], v[a][b]);
+          }
+        }
+      }
+      __syncthreads();
     }
   }
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = ty + 16 * a, c = tx + 32 * b;
+    for (int b = 0; b < 8; ++b) {
+      const int i = l + 32 * a, c = w + 16 * b;
       Ls[i * DLD + c] = (c <= i) ? v[a][b] : 0.0;
     }
   __syncthreads();
+  DIAG_STAMP(2);
 
-  // ---------------- phase 2: X = L^-1 by forward substitution on all 128 right-hand sides ----------------
+  // ---------------- phase 2: X = L^-1 ----------------
+  double t[8][4];  // t[a][b] = element (i = w + 16a, c = l + 32b)
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) v[a][b] = (ty + 16 * a == tx + 32 * b) ? 1.0 : 0.0;
-  for (int k = 0; k < NB; ++k) {
-    double *row = line[k & 1];
-    {
-      const double dk = rdiag[k];
-      const bool own = (ty == (k & 15));
-      const int ak = k >> 4;
+    for (int b = 0; b < 4; ++b) t[a][b] = (w + 16 * a == l + 32 * b) ? 1.0 : 0.0;
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const bool mine = own && (a == ak);
+  for (int a1 = 0; a1 < 8; ++a1) {        // register slot of the row being finalised
+#pragma unroll 1
+    for (int kk = 0; kk < 16; ++kk) {
+      const int k1 = 16 * a1 + kk;        // row finalised in this step (owner: warp kk)
+      const int k = k1 - 1;               // row applied in this step (-1: none)
+      const bool owner = (w == kk);
+      const double *row = line[k & 1];
+      double li[8], xr[4];
+      if (k >= 0) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) li[a] = Ls[(w + 16 * a) * DLD + k];  // warp-uniform; zero for i < k
+#pragma unroll
+        for (int b = 0; b < 4; ++b) xr[b] = row[l + 32 * b];             // zero for c > k
+      }
+      if (owner) {
+        const double dk = rdiag[k1];
+        double *out = line[k1 & 1];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const double nv = v[a][b] * dk;  // X[k, c] final
-          v[a][b] = mine ? nv : v[a][b];
-          if (mine) row[tx + 32 * b] = nv;
+          double x = t[a1][b];
+          if (k >= 0) x = fma(-li[a1], xr[b], x);
+          x *= dk;  // X[k1, c] final (zero for c > k1)
+          t[a1][b] = x;
+          out[l + 32 * b] = x;
         }
       }
-    }
-    __syncthreads();
-    double li[8], xr[4];
+      if (k >= 0) {
 #pragma unroll
-    for (int a = 0; a < 8; ++a) li[a] = Ls[(ty + 16 * a) * DLD + k];  // zero for i < k
+        for (int a = 0; a < 8; ++a) {
+          if (w + 16 * a > k && !(owner && a == a1)) {  // warp-uniform
+            // xr is zero for columns > k, so the update is exact without a per-element predicate
 #pragma unroll
-    for (int b = 0; b < 4; ++b) xr[b] = row[tx + 32 * b];             // zero for c > k
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      if (ty + 16 * a > k) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) v[a][b] = fma(-li[a], xr[b], v[a][b]);
+            for (int b = 0; b < 4; ++b) t[a][b] = fma(-li[a], xr[b], t[a][b]);
+          }
+        }
       }
+      __syncthreads();
     }
   }
+  DIAG_STAMP(3);
+  // stage through shared memory for coalesced row writes
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int i = ty + 16 * a, c = tx + 32 * b;
-      Xkk[(long long)i * ldx + c] = (c <= i) ? v[a][b] : 0.0;
+      const int i = w + 16 * a, c = l + 32 * b;
+      Ls[i * DLD + c] = (c <= i) ? t[a][b] : 0.0;
     }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += DT) {
+    const int r = e >> 7, c = e & 127;
+    Xkk[(long long)r * ldx + c] = Ls[r * DLD + c];
+  }
+  DIAG_STAMP(4);
 }
 
 __global__ void pad_identity_kernel(double *__restrict__ C, long long n, long long npad) {
