@@ -242,7 +242,7 @@ void gdca_destroy(gdca_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (!ctx->dZ_borrowed) cudaFree(ctx->dZ);
-  void *bufs[] = {ctx->dZt,  ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
+  void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR};
   for (void *b : bufs)

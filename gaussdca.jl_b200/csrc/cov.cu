@@ -10,8 +10,9 @@
 // 1/400 of the products are non-zero.  This kernel does the M*L^2/2 = 2.5e10 useful additions directly:
 //
 //   1. per site i, sequence ids are grouped by the state at i (stable counting sort -> list(i,a));
-//   2. one CTA owns output row (i,a) x a chunk of 128 sites j; thread t owns site j.  For every k in
-//      list(i,a) it adds W[k] to a PRIVATE shared-memory accumulator acc[Z[j,k]][t].  No atomics, no
+//   2. one CTA owns output row (i,a) x a chunk of 256 sites j; thread t owns sites t and t+128.  For every k in
+//      list(i,a) it adds W[k] to a PRIVATE shared-memory accumulator acc[Z[j,k]][t] (list entries are staged
+//      128 at a time in shared memory; the two states come from one 16-bit load of a recoded copy of Z).  No atomics, no
 //      bank conflicts (thread t always hits bank pair t mod 16), every element is summed in ascending
 //      sequence order, so the result is deterministic and bit-identical for (r,c) and (c,r);
 //   3. the epilogue applies 1/Meff, the pseudocount mix and "- Pi Pi'" and writes the row chunk.
@@ -107,50 +108,94 @@ __global__ void __launch_bounds__(256) pi_kernel(const int32_t *__restrict__ lis
   }
 }
 
+// ---- Zq: recoded + permuted copy of the alignment for the covariance kernel --------------------------
+// Row k holds, for every chunk of 256 sites, the accumulator SLOT (state-1, or s for the gap state /
+// padding) of site  j = chunk*256 + u*128 + t  at byte position  chunk*256 + 2t + u:  thread t of a covariance
+// CTA reads its two sites (t and t+128) with one 16-bit load, and the slot needs no decoding.
+constexpr int CS = 256;  // sites per covariance CTA (2 per thread)
+
+__global__ void build_zq_kernel(const int8_t *__restrict__ Z, long long L, long long M, long long Lq, int s,
+                                uint8_t *__restrict__ Zq) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * Lq) return;
+  const long long k = e / Lq;
+  const int p = (int)(e - k * Lq);
+  const int c = p / CS, q2 = p - c * CS;
+  const int t = q2 >> 1, u = q2 & 1;
+  const long long j = (long long)c * CS + u * JT + t;
+  int slot = s;
+  if (j < L) {
+    const int st = (int)Z[k * L + j];
+    if (st >= 1 && st <= s) slot = st - 1;
+  }
+  Zq[e] = (uint8_t)slot;
+}
+
 struct CovParams {
-  const int8_t *Z;  // [M][L]
+  const uint8_t *Zq;  // [M][Lq]
   const int32_t *list, *listoff;
   const double *W, *meff, *Pi;
   double *C;  // [npad][npad], leading dimension ld
-  long long L, M, n, ld;
+  long long L, M, n, ld, Lq;
   int q, s, nchunks;
   int rank, world;
   double pc;
 };
 
 constexpr int UNR = 8;
+constexpr int STG = 128;  // list entries staged per round (one per thread)
 
 __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
-  extern __shared__ double acc[];  // [q][JT]; row s is the dump slot for state q / padding
+  extern __shared__ double acc[];  // [q][2][JT]; slot s is the dump for the gap state / padding
+  __shared__ __align__(16) double2 stage[STG];  // {bit pattern of the row offset k*Lq, W[k]}
   const int r = blockIdx.y;        // output row (i, a)
   const int i = r / P.s, a = r - i * P.s + 1;
   const int jc = blockIdx.x;
-  if ((jc + 1) * JT <= i) return;                 // chunk entirely left of the diagonal block
+  if ((jc + 1) * CS <= i) return;                      // chunk entirely left of the diagonal block
   if (P.world > 1 && (i % P.world) != P.rank) return;  // rows are dealt to ranks by site
   const int t = threadIdx.x;
-  const long long j = (long long)jc * JT + t;
-  const bool jvalid = j < P.L;
-  for (int b = 0; b < P.q; ++b) acc[b * JT + t] = 0.0;
+  for (int b = 0; b < 2 * P.q; ++b) acc[b * JT + t] = 0.0;
   // (private columns: no barrier needed before the accumulation loop)
 
   const int beg = P.listoff[(long long)i * (NSTATE + 1) + a], end = P.listoff[(long long)i * (NSTATE + 1) + a + 1];
   const int32_t *l = P.list + (long long)i * P.M;
-  const int8_t *Zj = P.Z + (jvalid ? j : 0);
-  for (int base = beg; base < end; base += UNR) {
-    int k[UNR];
-    double w[UNR];
-    int st[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) k[u] = (base + u < end) ? l[base + u] : -1;
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      w[u] = (k[u] >= 0) ? P.W[k[u]] : 0.0;
-      st[u] = (k[u] >= 0 && jvalid) ? (int)Zj[(long long)k[u] * P.L] : P.q;
+  const uint8_t *Zt = P.Zq + (long long)jc * CS + 2 * t;
+  const unsigned Lq = (unsigned)P.Lq;
+  double *acc0 = acc + t, *acc1 = acc + JT + t;
+  const int slot_stride = 2 * JT;
+
+  for (int base = beg; base < end; base += STG) {
+    const int nst = min(STG, end - base);
+    __syncthreads();  // previous round fully consumed
+    if (t < nst) {
+      const int k = l[base + t];
+      double2 e;
+      e.x = __longlong_as_double((long long)((unsigned)k * Lq));  // < 2^32 (checked on the host)
+      e.y = P.W[k];
+      stage[t] = e;
     }
+    __syncthreads();
+    int u0 = 0;
+    for (; u0 + UNR <= nst; u0 += UNR) {
+      unsigned short zz[UNR];
+      double w[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int slot = (st[u] >= 1 && st[u] <= P.s) ? st[u] - 1 : P.s;
-      acc[slot * JT + t] += w[u];
+      for (int u = 0; u < UNR; ++u) {
+        const double2 e = stage[u0 + u];  // broadcast
+        w[u] = e.y;
+        zz[u] = *reinterpret_cast<const unsigned short *>(Zt + (unsigned)__double_as_longlong(e.x));
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        acc0[(zz[u] & 0xff) * slot_stride] += w[u];
+        acc1[(zz[u] >> 8) * slot_stride] += w[u];
+      }
+    }
+    for (; u0 < nst; ++u0) {
+      const double2 e = stage[u0];
+      const unsigned short zz = *reinterpret_cast<const unsigned short *>(Zt + (unsigned)__double_as_longlong(e.x));
+      acc0[(zz & 0xff) * slot_stride] += e.y;
+      acc1[(zz >> 8) * slot_stride] += e.y;
     }
   }
   __syncthreads();
@@ -160,12 +205,12 @@ __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
   const double pir = P.Pi[r];
   const double pcq = P.pc / P.q, pcqq = pcq / P.q, omp = 1.0 - P.pc;
   double *Crow = P.C + (long long)r * P.ld;
-  for (int e = t; e < JT * P.s; e += JT) {
-    const int jl = e / P.s, b = e - jl * P.s;
-    const long long jj = (long long)jc * JT + jl;
+  for (int e = t; e < CS * P.s; e += JT) {
+    const int jl = e / P.s, b = e - jl * P.s;       // site within the chunk, state
+    const long long jj = (long long)jc * CS + jl;
     if (jj >= P.L || jj < i) continue;
     const long long c = jj * P.s + b;
-    const double ptrue = acc[b * JT + jl] / Meff;
+    const double ptrue = acc[b * slot_stride + (jl >> 7) * JT + (jl & (JT - 1))] / Meff;
     double pij;
     if (jj == i)
       pij = omp * ptrue + ((b == a - 1) ? pcq : 0.0);
@@ -229,6 +274,12 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)npad * npad));
   GDCA_TRY(gdca_reserve(ctx, ctx->dZt, ctx->capZt, (size_t)L * M));
   int8_t *Zt = ctx->dZt;
+  const long long Lq = (L + CS - 1) / CS * CS;
+  if ((unsigned long long)M * (unsigned long long)Lq >= (1ull << 32))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "covariance: M * roundup(L,256) must be < 2^32");
+  GDCA_TRY(gdca_reserve(ctx, ctx->dZq, ctx->capZq, (size_t)M * Lq));
+  build_zq_kernel<<<(unsigned)(((size_t)M * Lq + 255) / 256), 256, 0, ctx->stream>>>(ctx->dZ, L, M, Lq, ctx->s, ctx->dZq);
+  GDCA_LAUNCH_CHECK(ctx);
 
   transpose_Z_kernel<<<dim3((unsigned)((M + 63) / 64), (unsigned)((L + 63) / 64)), 256, 0, ctx->stream>>>(ctx->dZ, L, M, Zt);
   GDCA_LAUNCH_CHECK(ctx);
@@ -240,7 +291,8 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dC, 0, (size_t)npad * npad * sizeof(double), ctx->stream));
 
   CovParams P;
-  P.Z = ctx->dZ;
+  P.Zq = ctx->dZq;
+  P.Lq = Lq;
   P.list = ctx->dList;
   P.listoff = ctx->dListOff;
   P.W = ctx->dW;
@@ -253,11 +305,12 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   P.ld = npad;
   P.q = ctx->q;
   P.s = ctx->s;
-  P.nchunks = (int)((L + JT - 1) / JT);
+  P.nchunks = (int)((L + CS - 1) / CS);
   P.rank = ctx->shard_rank;
   P.world = ctx->shard_world;
   P.pc = pc;
-  const size_t smem = (size_t)ctx->q * JT * sizeof(double);
+  const size_t smem = (size_t)ctx->q * 2 * JT * sizeof(double);
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cov_rows_kernel<<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
   GDCA_LAUNCH_CHECK(ctx);
   ctx->pseudocount = pc;
