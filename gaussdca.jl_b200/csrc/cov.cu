@@ -10,9 +10,10 @@
 // 1/400 of the products are non-zero.  This kernel does the M*L^2/2 = 2.5e10 useful additions directly:
 //
 //   1. per site i, sequence ids are grouped by the state at i (stable counting sort -> list(i,a));
-//   2. one CTA owns output row (i,a) x a chunk of 256 sites j; thread t owns sites t and t+128.  For every k in
-//      list(i,a) it adds W[k] to a PRIVATE shared-memory accumulator acc[Z[j,k]][t] (list entries are staged
-//      128 at a time in shared memory; the two states come from one 16-bit load of a recoded copy of Z).  No atomics, no
+//   2. one CTA owns output row (i,a) x a chunk of 512 sites starting at the diagonal block; thread t owns 4
+//      adjacent sites.  For every k in list(i,a) it adds W[k] to PRIVATE shared-memory accumulators
+//      acc[Z[j,k]][u][t] (list entries are staged 128 at a time in shared memory; the four states come from
+//      one 32-bit load of a recoded copy of Z).  No atomics, no
 //      bank conflicts (thread t always hits bank pair t mod 16), every element is summed in ascending
 //      sequence order, so the result is deterministic and bit-identical for (r,c) and (c,r);
 //   3. the epilogue applies 1/Meff, the pseudocount mix and "- Pi Pi'" and writes the row chunk.
@@ -108,21 +109,16 @@ __global__ void __launch_bounds__(256) pi_kernel(const int32_t *__restrict__ lis
   }
 }
 
-// ---- Zq: recoded + permuted copy of the alignment for the covariance kernel --------------------------
-// Row k holds, for every chunk of 256 sites, the accumulator SLOT (state-1, or s for the gap state /
-// padding) of site  j = chunk*256 + u*128 + t  at byte position  chunk*256 + 2t + u:  thread t of a covariance
-// CTA reads its two sites (t and t+128) with one 16-bit load, and the slot needs no decoding.
-constexpr int CS = 256;  // sites per covariance CTA (2 per thread)
-
+// ---- Zq: recoded copy of the alignment for the covariance kernel --------------------------------------
+// Zq[k][j] = accumulator SLOT of sequence k at site j: state-1, or s (the dump slot) for the gap state and for
+// the padding sites j >= L.  Row stride Lq is a multiple of 128, so a thread reads its SPT adjacent sites with
+// one aligned load and the slot needs no decoding in the inner loop.
 __global__ void build_zq_kernel(const int8_t *__restrict__ Z, long long L, long long M, long long Lq, int s,
                                 uint8_t *__restrict__ Zq) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= M * Lq) return;
   const long long k = e / Lq;
-  const int p = (int)(e - k * Lq);
-  const int c = p / CS, q2 = p - c * CS;
-  const int t = q2 >> 1, u = q2 & 1;
-  const long long j = (long long)c * CS + u * JT + t;
+  const long long j = e - k * Lq;
   int slot = s;
   if (j < L) {
     const int st = (int)Z[k * L + j];
@@ -145,57 +141,66 @@ struct CovParams {
 constexpr int UNR = 8;
 constexpr int STG = 128;  // list entries staged per round (one per thread)
 
+template <int SPT> struct ZLoad;
+template <> struct ZLoad<2> { typedef unsigned short type; };
+template <> struct ZLoad<4> { typedef unsigned int type; };
+
+// CTA (row r = (i,a), chunk c): sites [start + c*CH, start + (c+1)*CH), CH = JT*SPT, start = i rounded down to a
+// warp's worth of sites (32*SPT).  Thread t owns the SPT adjacent sites start + c*CH + SPT*t + u.
+template <int SPT>
 __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
-  extern __shared__ double acc[];  // [q][2][JT]; slot s is the dump for the gap state / padding
-  __shared__ __align__(16) double2 stage[STG];  // {bit pattern of the row offset k*Lq, W[k]}
-  const int r = blockIdx.y;        // output row (i, a)
+  constexpr int CH = JT * SPT;
+  extern __shared__ double acc[];      // [q][SPT][JT]; slot s is the dump for the gap state / padding
+  __shared__ unsigned stage_off[STG];  // row offset k*Lq of the staged sequences
+  __shared__ double stage_w[STG];      // W[k]
+  const int r = blockIdx.y;            // output row (i, a)
   const int i = r / P.s, a = r - i * P.s + 1;
-  const int jc = blockIdx.x;
-  if ((jc + 1) * CS <= i) return;                      // chunk entirely left of the diagonal block
   if (P.world > 1 && (i % P.world) != P.rank) return;  // rows are dealt to ranks by site
+  const int start = (i / (32 * SPT)) * (32 * SPT) + blockIdx.x * CH;
+  if (start >= P.L) return;
   const int t = threadIdx.x;
-  for (int b = 0; b < 2 * P.q; ++b) acc[b * JT + t] = 0.0;
+  const int j0 = start + SPT * t;                 // first site of this thread
+  const bool active = ((t >> 5) * 32 * SPT + start) < (int)P.Lq;   // warp-uniform: warp has sites inside the row
+  for (int b = 0; b < SPT * P.q; ++b) acc[b * JT + t] = 0.0;
   // (private columns: no barrier needed before the accumulation loop)
 
   const int beg = P.listoff[(long long)i * (NSTATE + 1) + a], end = P.listoff[(long long)i * (NSTATE + 1) + a + 1];
   const int32_t *l = P.list + (long long)i * P.M;
-  const uint8_t *Zt = P.Zq + (long long)jc * CS + 2 * t;
+  const uint8_t *Zt = P.Zq + j0;
   const unsigned Lq = (unsigned)P.Lq;
-  double *acc0 = acc + t, *acc1 = acc + JT + t;
-  const int slot_stride = 2 * JT;
+  double *acct = acc + t;
+  constexpr int slot_stride = SPT * JT;
+  typedef typename ZLoad<SPT>::type zword;
 
   for (int base = beg; base < end; base += STG) {
     const int nst = min(STG, end - base);
     __syncthreads();  // previous round fully consumed
-    if (t < nst) {
-      const int k = l[base + t];
-      double2 e;
-      e.x = __longlong_as_double((long long)((unsigned)k * Lq));  // < 2^32 (checked on the host)
-      e.y = P.W[k];
-      stage[t] = e;
+    {
+      // pad the round with no-op entries (weight 0, row 0) so the inner loop has no tail
+      const bool real = t < nst;
+      const int k = real ? l[base + t] : 0;
+      stage_off[t] = (unsigned)k * Lq;  // < 2^32 (checked on the host)
+      stage_w[t] = real ? P.W[k] : 0.0;
     }
     __syncthreads();
-    int u0 = 0;
-    for (; u0 + UNR <= nst; u0 += UNR) {
-      unsigned short zz[UNR];
-      double w[UNR];
+    if (!active) continue;
+    // software pipeline: the Zq words of group g+1 are in flight while group g is accumulated
+    zword cur[UNR], nxt[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const double2 e = stage[u0 + u];  // broadcast
-        w[u] = e.y;
-        zz[u] = *reinterpret_cast<const unsigned short *>(Zt + (unsigned)__double_as_longlong(e.x));
+    for (int u = 0; u < UNR; ++u) cur[u] = *reinterpret_cast<const zword *>(Zt + stage_off[u]);
+    for (int u0 = 0; u0 < nst; u0 += UNR) {
+      if (u0 + UNR < nst) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) nxt[u] = *reinterpret_cast<const zword *>(Zt + stage_off[u0 + UNR + u]);
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
-        acc0[(zz[u] & 0xff) * slot_stride] += w[u];
-        acc1[(zz[u] >> 8) * slot_stride] += w[u];
+        const double wv = stage_w[u0 + u];  // broadcast
+#pragma unroll
+        for (int sidx = 0; sidx < SPT; ++sidx) acct[((cur[u] >> (8 * sidx)) & 0xff) * slot_stride + sidx * JT] += wv;
       }
-    }
-    for (; u0 < nst; ++u0) {
-      const double2 e = stage[u0];
-      const unsigned short zz = *reinterpret_cast<const unsigned short *>(Zt + (unsigned)__double_as_longlong(e.x));
-      acc0[(zz & 0xff) * slot_stride] += e.y;
-      acc1[(zz >> 8) * slot_stride] += e.y;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) cur[u] = nxt[u];
     }
   }
   __syncthreads();
@@ -205,12 +210,12 @@ __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
   const double pir = P.Pi[r];
   const double pcq = P.pc / P.q, pcqq = pcq / P.q, omp = 1.0 - P.pc;
   double *Crow = P.C + (long long)r * P.ld;
-  for (int e = t; e < CS * P.s; e += JT) {
+  for (int e = t; e < CH * P.s; e += JT) {
     const int jl = e / P.s, b = e - jl * P.s;       // site within the chunk, state
-    const long long jj = (long long)jc * CS + jl;
+    const long long jj = (long long)start + jl;
     if (jj >= P.L || jj < i) continue;
     const long long c = jj * P.s + b;
-    const double ptrue = acc[b * slot_stride + (jl >> 7) * JT + (jl & (JT - 1))] / Meff;
+    const double ptrue = acc[b * slot_stride + (jl % SPT) * JT + jl / SPT] / Meff;
     double pij;
     if (jj == i)
       pij = omp * ptrue + ((b == a - 1) ? pcq : 0.0);
@@ -274,9 +279,9 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)npad * npad));
   GDCA_TRY(gdca_reserve(ctx, ctx->dZt, ctx->capZt, (size_t)L * M));
   int8_t *Zt = ctx->dZt;
-  const long long Lq = (L + CS - 1) / CS * CS;
+  const long long Lq = (L + 127) / 128 * 128;
   if ((unsigned long long)M * (unsigned long long)Lq >= (1ull << 32))
-    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "covariance: M * roundup(L,256) must be < 2^32");
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "covariance: M * roundup(L,128) must be < 2^32");
   GDCA_TRY(gdca_reserve(ctx, ctx->dZq, ctx->capZq, (size_t)M * Lq));
   build_zq_kernel<<<(unsigned)(((size_t)M * Lq + 255) / 256), 256, 0, ctx->stream>>>(ctx->dZ, L, M, Lq, ctx->s, ctx->dZq);
   GDCA_LAUNCH_CHECK(ctx);
@@ -305,13 +310,14 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   P.ld = npad;
   P.q = ctx->q;
   P.s = ctx->s;
-  P.nchunks = (int)((L + CS - 1) / CS);
+  constexpr int SPT = 2;
+  P.nchunks = (int)((L + JT * SPT - 1) / (JT * SPT));
   P.rank = ctx->shard_rank;
   P.world = ctx->shard_world;
   P.pc = pc;
-  const size_t smem = (size_t)ctx->q * 2 * JT * sizeof(double);
-  GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cov_rows_kernel<<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
+  const size_t smem = (size_t)ctx->q * SPT * JT * sizeof(double);
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cov_rows_kernel<SPT><<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
   GDCA_LAUNCH_CHECK(ctx);
   ctx->pseudocount = pc;
   ctx->have_cov = true;
