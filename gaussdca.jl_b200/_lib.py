@@ -77,6 +77,8 @@ SIGNATURES = {
     "gdca_dev_counts_ptr": (_p, [_p]),
     "gdca_dev_counts_stride": (_i64, [_p]),
     "gdca_theta_from_ham_sum": (_i32, [_i64, _i64, _u64, _pdbl, _pi64, _pu64]),
+    "gdca_theta_from_ident_sum": (_i32, [_i64, _i64, _u64, _pdbl, _pi64]),
+    "gdca_dev_ident_sum": (_i32, [_p, _pu64]),
     "gdca_dev_finish_weights": (_i32, [_p, _i32, _pdbl]),
     "gdca_dev_set_weights": (_i32, [_p, _p, _dbl]),
     "gdca_dev_covariance": (_i32, [_p, _dbl]),

@@ -65,7 +65,7 @@ int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
   set_shape(ctx, L, M, q);
   GDCA_TRY(gdca_k_pack(ctx));
   ctx->have_alignment = true;
-  ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
   return GDCA_OK;
 }
 
@@ -84,49 +84,20 @@ int32_t weights_stage(gdca_ctx *ctx, double theta) {
   st.theta_passes = 0;
   st.ident_sum = 0;
   if (theta < 0) {
-    // speculative single sweep: estimate thresh from a sample of the tiles (every stride-th item, at
-    // least ~2 tiles per SM, at most 1/2 and at least 1/64 of the sweep), then count for thresh-1,
-    // thresh, thresh+1 while accumulating the exact hamming sum.  Always verified against the exact value.
-    unsigned long long hs[2] = {0, 0};
-    const long long T = ctx->Mpad / GDCA_TILE;
-    int stride = (int)((T * (T + 1) / 2) / (2 * (long long)ctx->num_sms));
-    if (stride > 64) stride = 64;
-    int64_t guess = -1;
-    if (stride >= 2) {
-      GDCA_TRY(gdca_k_pair_pass(ctx, 0, 0, stride));
-      GDCA_CUDA(ctx, cudaMemcpyAsync(hs, ctx->dHam, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
-      GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      if (hs[1] > 0) {
-        const double np = (double)hs[1];
-        const double mean_ident = (np * (double)ctx->L - (double)hs[0]) / (double)ctx->L / np;
-        const double th = fmin(0.5, 0.38 * 0.32 / mean_ident);
-        guess = (int64_t)floor(th * (double)ctx->L);
-      }
-    }
-    if (guess >= 0) {
-      GDCA_TRY(gdca_k_pair_pass(ctx, 2, (int)guess, 1));
-      st.theta_passes = 1;
-    } else {
-      GDCA_TRY(gdca_k_pair_pass(ctx, 0, 0, 1));
-      st.theta_passes = 1;
-    }
-    GDCA_CUDA(ctx, cudaMemcpyAsync(hs, ctx->dHam, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
-    GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // theta = :auto without a pair sweep: sum_{k<l} ident(k,l) = sum_i sum_v n_iv (n_iv - 1)/2 from the per-site
+    // state histograms (exact integers, O(M L)); then ONE neighbour-count sweep with the exact threshold.
+    unsigned long long ident = 0;
+    GDCA_TRY(gdca_k_ident_sum(ctx, &ident));
     double th;
     int64_t thresh;
-    uint64_t ident;
-    GDCA_TRY(gdca_theta_from_ham_sum(ctx->L, ctx->M, hs[0], &th, &thresh, &ident));
+    GDCA_TRY(gdca_theta_from_ident_sum(ctx->L, ctx->M, ident, &th, &thresh));
     st.theta = th;
     st.thresh = thresh;
     st.ident_sum = ident;
     GDCA_TRY(rec(ctx, EV_THETA));
-    if (guess >= 0 && thresh >= guess - 1 && thresh <= guess + 1) {
-      GDCA_TRY(gdca_k_finish_weights(ctx, (int)(thresh - (guess - 1))));
-    } else {
-      GDCA_TRY(gdca_k_pair_pass(ctx, 1, (int)thresh, 1));
-      st.theta_passes += 1;
-      GDCA_TRY(gdca_k_finish_weights(ctx, 0));
-    }
+    GDCA_TRY(gdca_k_pair_pass(ctx, 1, (int)thresh, 1));
+    st.theta_passes = 1;
+    GDCA_TRY(gdca_k_finish_weights(ctx, 0));
   } else {
     st.theta = theta;
     GDCA_TRY(rec(ctx, EV_THETA));
@@ -136,6 +107,7 @@ int32_t weights_stage(gdca_ctx *ctx, double theta) {
     } else {
       st.thresh = (int64_t)floor(theta * (double)ctx->L);
       GDCA_TRY(gdca_k_pair_pass(ctx, 1, (int)st.thresh, 1));
+      st.theta_passes = 1;
       GDCA_TRY(gdca_k_finish_weights(ctx, 0));
     }
   }
@@ -266,17 +238,31 @@ int64_t gdca_ranking_length(int64_t L, int64_t min_separation) {
   return d > 0 ? d * (d + 1) / 2 : 0;
 }
 
-int32_t gdca_theta_from_ham_sum(int64_t L, int64_t M, uint64_t ham_sum, double *theta, int64_t *thresh,
-                                uint64_t *ident_sum) {
+int32_t gdca_theta_from_ident_sum(int64_t L, int64_t M, uint64_t ident, double *theta, int64_t *thresh) {
   if (L < 1 || M < 2) return GDCA_ERR_INVALID_ARG;
-  const uint64_t npairs = (uint64_t)M * (uint64_t)(M - 1) / 2;
-  const uint64_t ident = npairs * (uint64_t)L - ham_sum;
   // same IEEE operations, same order, as oracle theta_from_ident_sum
   const double meanfracid = ((double)ident / (double)L) / (0.5 * (double)M * (double)(M - 1));
   const double th = fmin(0.5, 0.38 * 0.32 / meanfracid);
   if (theta) *theta = th;
   if (thresh) *thresh = (int64_t)floor(th * (double)L);
+  return GDCA_OK;
+}
+
+int32_t gdca_theta_from_ham_sum(int64_t L, int64_t M, uint64_t ham_sum, double *theta, int64_t *thresh,
+                                uint64_t *ident_sum) {
+  if (L < 1 || M < 2) return GDCA_ERR_INVALID_ARG;
+  const uint64_t npairs = (uint64_t)M * (uint64_t)(M - 1) / 2;
+  const uint64_t ident = npairs * (uint64_t)L - ham_sum;
   if (ident_sum) *ident_sum = ident;
+  return gdca_theta_from_ident_sum(L, M, ident, theta, thresh);
+}
+
+int32_t gdca_dev_ident_sum(gdca_ctx *ctx, uint64_t *ident_sum) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  unsigned long long v = 0;
+  GDCA_TRY(gdca_k_ident_sum(ctx, &v));
+  if (ident_sum) *ident_sum = v;
   return GDCA_OK;
 }
 

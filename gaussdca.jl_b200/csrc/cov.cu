@@ -92,6 +92,23 @@ __global__ void __launch_bounds__(LB) build_lists_kernel(const int8_t *__restric
   }
 }
 
+// ---- sum over pairs k<l of #identical positions, WITHOUT visiting any pair ---------------------------------
+// A position i contributes one identity for every pair of sequences that carry the same state there:
+//     sum_{k<l} ident(k,l) = sum_i sum_v n_iv (n_iv - 1) / 2,     n_iv = #{k : Z[i,k] = v}  (gap state included).
+// The n_iv are the bucket sizes of the per-site lists, so theta = :auto costs O(M L), not O(M^2 L).
+__global__ void __launch_bounds__(256) ident_sum_kernel(const int32_t *__restrict__ listoff, long long L,
+                                                        unsigned long long *__restrict__ out) {
+  unsigned long long acc = 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < L * NSTATE; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / NSTATE;
+    const int v = (int)(e - i * NSTATE);
+    const unsigned long long nv = (unsigned long long)(listoff[i * (NSTATE + 1) + v + 1] - listoff[i * (NSTATE + 1) + v]);
+    acc += nv * (nv - 1) / 2;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 // ---- Pi[(i,a)] = (1-pc) * sum_{k in list(i,a)} W[k] / Meff + pc/q  (deterministic tree) ----
 __global__ void __launch_bounds__(256) pi_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ listoff,
                                                  const double *__restrict__ W, const double *__restrict__ meff,
@@ -268,17 +285,43 @@ int32_t gdca_k_extract_diag(gdca_ctx *ctx) {
   return GDCA_OK;
 }
 
+// per-site lists of sequence ids grouped by state (once per loaded alignment; used by theta and the covariance)
+int32_t gdca_k_build_lists(gdca_ctx *ctx) {
+  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "build_lists: no alignment loaded");
+  if (ctx->have_lists) return GDCA_OK;
+  const long long L = ctx->L, M = ctx->M;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dList, ctx->capList, (size_t)L * M));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dListOff, ctx->capListOff, (size_t)L * (NSTATE + 1)));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dZt, ctx->capZt, (size_t)L * M));
+  transpose_Z_kernel<<<dim3((unsigned)((M + 63) / 64), (unsigned)((L + 63) / 64)), 256, 0, ctx->stream>>>(ctx->dZ, L, M, ctx->dZt);
+  GDCA_LAUNCH_CHECK(ctx);
+  build_lists_kernel<<<(unsigned)L, LB, 0, ctx->stream>>>(ctx->dZt, M, ctx->dList, ctx->dListOff);
+  GDCA_LAUNCH_CHECK(ctx);
+  ctx->have_lists = true;
+  return GDCA_OK;
+}
+
+// dHam[0] <- sum over pairs k<l of the number of identical positions (exact)
+int32_t gdca_k_ident_sum(gdca_ctx *ctx, unsigned long long *ident_out) {
+  GDCA_TRY(gdca_k_build_lists(ctx));
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dHam, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  ident_sum_kernel<<<64, 256, 0, ctx->stream>>>(ctx->dListOff, ctx->L, ctx->dHam);
+  GDCA_LAUNCH_CHECK(ctx);
+  unsigned long long ident = 0;
+  GDCA_CUDA(ctx, cudaMemcpyAsync(&ident, ctx->dHam, sizeof ident, cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ident_out) *ident_out = ident;
+  return GDCA_OK;
+}
+
 int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "covariance: no alignment loaded");
   if (!ctx->have_weights) return gdca_fail(ctx, GDCA_ERR_STATE, "covariance: weights not computed");
   const long long L = ctx->L, M = ctx->M, n = ctx->n;
-  GDCA_TRY(gdca_reserve(ctx, ctx->dList, ctx->capList, (size_t)L * M));
-  GDCA_TRY(gdca_reserve(ctx, ctx->dListOff, ctx->capListOff, (size_t)L * (NSTATE + 1)));
+  GDCA_TRY(gdca_k_build_lists(ctx));
   GDCA_TRY(gdca_reserve(ctx, ctx->dPi, ctx->capPi, (size_t)n));
   const long long npad = ctx->npad;
   GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)npad * npad));
-  GDCA_TRY(gdca_reserve(ctx, ctx->dZt, ctx->capZt, (size_t)L * M));
-  int8_t *Zt = ctx->dZt;
   const long long Lq = (L + 127) / 128 * 128;
   if ((unsigned long long)M * (unsigned long long)Lq >= (1ull << 32))
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "covariance: M * roundup(L,128) must be < 2^32");
@@ -286,10 +329,6 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   build_zq_kernel<<<(unsigned)(((size_t)M * Lq + 255) / 256), 256, 0, ctx->stream>>>(ctx->dZ, L, M, Lq, ctx->s, ctx->dZq);
   GDCA_LAUNCH_CHECK(ctx);
 
-  transpose_Z_kernel<<<dim3((unsigned)((M + 63) / 64), (unsigned)((L + 63) / 64)), 256, 0, ctx->stream>>>(ctx->dZ, L, M, Zt);
-  GDCA_LAUNCH_CHECK(ctx);
-  build_lists_kernel<<<(unsigned)L, LB, 0, ctx->stream>>>(Zt, M, ctx->dList, ctx->dListOff);
-  GDCA_LAUNCH_CHECK(ctx);
   pi_kernel<<<(unsigned)L, 256, 0, ctx->stream>>>(ctx->dList, ctx->dListOff, ctx->dW, ctx->dMeff, M, ctx->q, pc, ctx->dPi);
   GDCA_LAUNCH_CHECK(ctx);
   // zero everything: padding rows/cols, the not-yet-mirrored lower part, and other shards' rows

@@ -53,7 +53,7 @@ struct gdca_ctx {
   gdca_rank_t *dR = nullptr; size_t capR = 0;
 
   // ---- state flags ----
-  bool have_alignment = false, have_weights = false, have_cov = false, have_inv = false;
+  bool have_alignment = false, have_lists = false, have_weights = false, have_cov = false, have_inv = false;
   double meff = 0.0, pseudocount = 0.0;
   int counts_row = -1;  // row of dCounts the weights came from (-1: theta == 0)
   gdca_stats_t stats{};
@@ -107,6 +107,8 @@ int32_t gdca_k_maxq(gdca_ctx *ctx);                       // pack.cu: dQ <- max(
 int32_t gdca_k_pack(gdca_ctx *ctx);                       // pack.cu: dZ -> dPlanes
 int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride);   // pairs.cu
 int32_t gdca_k_finish_weights(gdca_ctx *ctx, int which);  // weights.cu
+int32_t gdca_k_build_lists(gdca_ctx *ctx);                // cov.cu: per-site lists of sequence ids grouped by state
+int32_t gdca_k_ident_sum(gdca_ctx *ctx, unsigned long long *ident_out);  // cov.cu: sum_{k<l} ident from site histograms
 int32_t gdca_k_covariance(gdca_ctx *ctx, double pc);      // cov.cu
 int32_t gdca_k_symmetrize_C(gdca_ctx *ctx);               // cov.cu: mirror upper site blocks, save diag blocks
 int32_t gdca_k_extract_diag(gdca_ctx *ctx);               // cov.cu: save the s x s diagonal blocks of dC

@@ -4,9 +4,10 @@ The reference has no multi-device path (one Julia process, shared-memory threads
 this is new.  Work partition, chosen so that every exchanged quantity is an exact integer or a
 sum with zeros (results are bit-identical for any number of ranks):
 
+  theta :auto  no exchange: every rank holds the alignment and computes the exact identity sum from per-site
+               state histograms (O(M L)).
   pair sweep   tiles (bi <= bj) of the M x M pair matrix dealt round-robin to ranks; every rank holds the
-               whole packed alignment.  Exchange: all-reduce(sum) of int32 counts[3][Mpad] and of the
-               u64 {hamming sum, pairs visited}  -- 2.4 MB at M = 200k.
+               whole packed alignment.  Exchange: all-reduce(sum) of the int32 neighbour counts -- 2.4 MB at M = 200k.
   covariance   output rows dealt to ranks by site (i mod world); each rank writes its rows of C into a
                zeroed n x n buffer.  Exchange: reduce(sum) to rank 0 -- adding zeros is exact.
   inverse, scores, APC, ranking: rank 0 (n^3 flop on one GPU; the block scores are HBM-bound
@@ -26,20 +27,17 @@ import math
 import numpy as np
 
 
-def theta_from_ham(L: int, M: int, ham_sum: int):
-    """Host arithmetic of gdca_theta_from_ham_sum (same IEEE operations in the same order)."""
-    npairs = M * (M - 1) // 2
-    ident = npairs * L - ham_sum
+def theta_from_ident(L: int, M: int, ident: int):
+    """Host arithmetic of gdca_theta_from_ident_sum (same IEEE operations in the same order)."""
     meanfracid = (ident / L) / (0.5 * M * (M - 1))
     theta = 0.5 if meanfracid == 0.0 else min(0.5, 0.38 * 0.32 / meanfracid)
-    return theta, int(math.floor(theta * L)), ident
+    return theta, int(math.floor(theta * L))
 
 
-def sample_stride(M: int, n_units: int, tile: int = 128) -> int:
-    """Every stride-th tile of a shard is visited by the sampling sweep (0: problem too small to sample)."""
-    T = (M + tile - 1) // tile
-    stride = (T * (T + 1) // 2) // (2 * n_units)
-    return min(stride, 64) if stride >= 2 else 0
+def theta_from_ham(L: int, M: int, ham_sum: int):
+    """Same, from the hamming sum of a mode-0/2 sweep."""
+    ident = M * (M - 1) // 2 * L - ham_sum
+    return theta_from_ident(L, M, ident) + (ident,)
 
 
 def run_sharded(be, dist, L: int, M: int, theta, pseudocount: float, score: str, min_separation: int):
@@ -48,47 +46,23 @@ def run_sharded(be, dist, L: int, M: int, theta, pseudocount: float, score: str,
     rank, world = dist.get_rank(), dist.get_world_size()
     be.set_shard(rank, world)
     info = {"passes": 0}
-    auto = isinstance(theta, str)
-    if auto:
-        guess = -1
-        stride = sample_stride(M, be.n_units() * world)
-        if stride:
-            be.pair_sample(stride)
-            ham = be.ham_tensor()
-            dist.all_reduce(ham)
-            h, npairs = (int(v) for v in be.to_host(ham))
-            if npairs > 0:
-                mean_ident = (npairs * float(L) - float(h)) / float(L) / float(npairs)
-                th = 0.5 if mean_ident == 0.0 else min(0.5, 0.38 * 0.32 / mean_ident)
-                guess = int(math.floor(th * L))
-        be.pair_pass(2 if guess >= 0 else 0, max(guess, 0))
-        info["passes"] = 1
-        ham = be.ham_tensor()
-        dist.all_reduce(ham)
-        if guess >= 0:
-            dist.all_reduce(be.counts_tensor())
-        h, npairs = (int(v) for v in be.to_host(ham))
-        assert npairs == M * (M - 1) // 2, (npairs, M)
-        th, thresh, ident = theta_from_ham(L, M, h)
-        info.update(theta=th, thresh=thresh, ident_sum=ident)
-        if guess >= 0 and guess - 1 <= thresh <= guess + 1:
-            which = thresh - (guess - 1)
-        else:
-            be.pair_pass(1, thresh)
-            dist.all_reduce(be.counts_tensor())
-            info["passes"] += 1
-            which = 0
+    if isinstance(theta, str):
+        # theta = :auto needs no exchange: every rank holds the alignment and gets the exact identity sum
+        # from the per-site state histograms (O(M L)).
+        ident = be.ident_sum()
+        th, thresh = theta_from_ident(L, M, ident)
+        info["ident_sum"] = ident
     else:
         th = float(theta)
         thresh = int(math.floor(th * L))
-        info.update(theta=th, thresh=thresh)
-        if th == 0.0:
-            which = -1
-        else:
-            be.pair_pass(1, thresh)
-            dist.all_reduce(be.counts_tensor())
-            info["passes"] = 1
-            which = 0
+    info.update(theta=th, thresh=thresh)
+    if th == 0.0:
+        which = -1                                # W == 1, Meff == M: no sweep at all
+    else:
+        be.pair_pass(1, thresh)                   # this rank's tiles of the M x M pair matrix
+        dist.all_reduce(be.counts_tensor())       # exact integers: the sum is independent of the rank count
+        info["passes"] = 1
+        which = 0
     info["meff"] = be.finish_weights(which)      # every rank: W = 1/count, Meff (identical everywhere)
     be.covariance(pseudocount)                   # this rank's rows of C, zeros elsewhere
     if world > 1:
@@ -135,8 +109,10 @@ class GpuBackend:
     def set_shard(self, rank, world):
         self.ctx.check(self.lib.gdca_set_shard(self.ctx.h, rank, world))
 
-    def pair_sample(self, stride):
-        self.ctx.check(self.lib.gdca_dev_pair_sample(self.ctx.h, stride))
+    def ident_sum(self):
+        v = ctypes.c_uint64()
+        self.ctx.check(self.lib.gdca_dev_ident_sum(self.ctx.h, ctypes.byref(v)))
+        return int(v.value)
 
     def pair_pass(self, mode, thresh):
         self.ctx.check(self.lib.gdca_dev_pair_pass(self.ctx.h, mode, thresh))

@@ -59,7 +59,7 @@ typedef struct {
   int64_t thresh;       /* floor(theta*L); neighbours have hamming < thresh                          */
   double meff;          /* sum_k 1/count[k], correctly rounded from the count histogram              */
   uint64_t ident_sum;   /* sum_{k<l} #identical positions (only when theta == :auto)                 */
-  int32_t theta_passes; /* pair sweeps executed (1 when the speculative threshold held, else 2)      */
+  int32_t theta_passes; /* M x M pair sweeps executed (1, or 0 when theta == 0)                     */
   int32_t reserved;
   /* device milliseconds per stage, CUDA events on the library's stream */
   float ms_h2d, ms_pack, ms_theta, ms_weights, ms_cov, ms_chol, ms_inv, ms_score, ms_apc, ms_rank, ms_d2h, ms_total;
@@ -129,7 +129,11 @@ int32_t gdca_dev_pair_sample(gdca_ctx *ctx, int32_t stride);
 void *gdca_dev_ham_sum_ptr(gdca_ctx *ctx);
 void *gdca_dev_counts_ptr(gdca_ctx *ctx);
 int64_t gdca_dev_counts_stride(gdca_ctx *ctx);
-/* theta from the (all-reduced) hamming sum -- host arithmetic identical to the oracle's. */
+/* sum_{k<l} #identical positions of the loaded alignment from per-site state histograms: O(M L), no pair
+ * sweep (replaces the O(M^2 L) loop of DCAUtils compute_theta, call site src/GaussDCA.jl:28); exact. */
+int32_t gdca_dev_ident_sum(gdca_ctx *ctx, uint64_t *ident_sum);
+int32_t gdca_theta_from_ident_sum(int64_t L, int64_t M, uint64_t ident_sum, double *theta, int64_t *thresh);
+/* theta from the (all-reduced) hamming sum of a mode-0/2 sweep -- host arithmetic identical to the oracle's. */
 int32_t gdca_theta_from_ham_sum(int64_t L, int64_t M, uint64_t ham_sum, double *theta, int64_t *thresh,
                                 uint64_t *ident_sum);
 /* counts (all-reduced, row `which` of the counts buffer) -> W = 1/(1+count), Meff.  theta == 0 path: which = -1. */

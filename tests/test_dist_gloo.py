@@ -59,9 +59,10 @@ class FakeBackend:
         if mode != 0:
             self.counts = self.torch.from_numpy(cnt.reshape(-1).copy())
 
-    def pair_sample(self, stride):
-        self.calls.append(("sample", stride))
-        self._sweep(0, 0, stride)
+    def ident_sum(self):
+        self.calls.append(("ident",))
+        iu = np.triu_indices(self.M, 1)
+        return int((self.L - self.H[iu]).sum())
 
     def pair_pass(self, mode, thresh):
         self.calls.append(("pass", mode, thresh))
@@ -128,7 +129,7 @@ def _worker(rank, world, port, case, out):
 
 
 @pytest.mark.parametrize("case", [(24, 1400, "auto", "frob"), (24, 300, "auto", "frob"), (16, 300, 0.3, "DI"),
-                                  (16, 200, 0.0, "frob")], ids=["auto-speculative", "auto-small", "fixed", "theta0"])
+                                  (16, 200, 0.0, "frob")], ids=["auto", "auto-small", "fixed", "theta0"])
 def test_sharded_driver_world2_gloo(orc, case):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -163,8 +164,6 @@ def test_sharded_driver_world2_gloo(orc, case):
     assert max(abs(x - y) for (_, _, x), (_, _, y) in zip(R0, Ro)) < 1e-10
     if case[2] == "auto":
         assert i0["ident_sum"] == orc.ident_sum(Z)
-        assert i0["passes"] == (1 if M >= 1000 else 2)        # big enough to sample -> one speculative sweep
-        if M >= 1000:
-            assert i0["calls"][0][0] == "sample" and i0["calls"][1][:2] == ("pass", 2)
+        assert i0["passes"] == 1 and i0["calls"] == [("ident",), ("pass", 1, st["thresh"])]   # one sweep, exact threshold
     elif theta == 0.0:
         assert i0["passes"] == 0 and i0["calls"] == []

@@ -135,8 +135,8 @@ def test_weights_duplicates_and_small_q(pkg, orc, ctx):
     assert counts[:100].min() >= 2
 
 
-def test_speculative_theta_pass_is_exact_and_single(pkg, orc, ctx):
-    """Large enough for the sampled estimate to engage: one sweep, still bit-exact."""
+def test_theta_auto_needs_one_sweep_and_is_exact(pkg, orc, ctx):
+    """theta=:auto comes from per-site state histograms (no sweep); the count sweep exits early -- still bit-exact."""
     Z = orc.synth_alignment(100, 20000, seed=11)
     tho = orc.compute_theta(Z)
     counts, W, Meff, thresh = orc.compute_weights(Z, tho)
@@ -183,6 +183,34 @@ def test_sharded_pair_sweep_sums_to_unsharded(pkg, orc, ctx):
     c1, _ = grab()
     assert np.array_equal(c1 + 1, counts)
     assert orc.ident_sum(Z) == M * (M - 1) // 2 * L - int(h_full[0])
+    # the O(M L) histogram route gives the same exact integer as the O(M^2 L) sweep
+    import ctypes
+    v = ctypes.c_uint64()
+    ctx.check(lib.gdca_dev_ident_sum(ctx.h, ctypes.byref(v)))
+    assert v.value == orc.ident_sum(Z)
+
+
+def test_early_exit_is_exact_on_adversarial_layouts(pkg, orc, ctx):
+    """Neighbours that only differ in the LAST sites, far pairs that only differ in the FIRST sites, thresholds at
+    word boundaries: the per-warp early exit must never change a count."""
+    rng = np.random.default_rng(3)
+    L, M = 96, 700
+    base = rng.integers(1, 22, size=(1, L), dtype=np.int8)
+    Z = np.repeat(base, M, axis=0)
+    for k in range(M):
+        if k % 3 == 0:      # differ only at the end
+            nd = rng.integers(0, 40)
+            Z[k, L - nd:] = rng.integers(1, 22, size=nd)
+        elif k % 3 == 1:    # differ only at the beginning
+            nd = rng.integers(0, 70)
+            Z[k, :nd] = rng.integers(1, 22, size=nd)
+        else:
+            Z[k] = rng.integers(1, 22, size=L)
+    Z[0, 0] = 21
+    for theta in (1 / 96 + 1e-9, 0.25, 32 / 96 + 1e-9, 33 / 96 + 1e-9, 0.5, 64 / 96 + 1e-9, 1.0):
+        counts, W, Meff, thresh = orc.compute_weights(Z, theta)
+        w = pkg.compute_weights(Z, theta, ctx=ctx, full=True)
+        assert w["thresh"] == thresh and np.array_equal(w["counts"], counts), theta
 
 
 # ----------------------------------------------------------------------------- covariance / inverse / scores

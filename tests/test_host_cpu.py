@@ -51,7 +51,7 @@ def test_struct_layouts_match_the_header(pkg, tmp_path):
 
 def test_theta_host_arithmetic_matches_oracle(pkg, orc):
     """gdca_theta_from_ham_sum is host code in the library: same IEEE operations as the oracle."""
-    from gaussdca_jl_b200.dist import theta_from_ham
+    from gaussdca_jl_b200.dist import theta_from_ham, theta_from_ident
     lib = pkg.load()
     rng = np.random.default_rng(0)
     for L, M in [(53, 106), (400, 94), (500, 200000), (1500, 1000000), (1, 2)]:
@@ -64,6 +64,10 @@ def test_theta_host_arithmetic_matches_oracle(pkg, orc):
             want = orc.theta_from_ident_sum(ident, L, M)
             assert th.value == want and ids.value == ident and thr.value == int(np.floor(want * L))
             assert theta_from_ham(L, M, ham) == (want, thr.value, ident)
+            assert theta_from_ident(L, M, ident) == (want, thr.value)
+            th2, thr2 = ctypes.c_double(), ctypes.c_int64()
+            assert lib.gdca_theta_from_ident_sum(L, M, ident, ctypes.byref(th2), ctypes.byref(thr2)) == 0
+            assert (th2.value, thr2.value) == (want, thr.value)
 
 
 def test_no_cpu_fallback(pkg):
