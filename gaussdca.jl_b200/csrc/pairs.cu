@@ -71,7 +71,7 @@ struct PairParams {
   int rank, world;
   int thresh;
   int32_t *counts;     // [3][Mpad]
-  unsigned long long *ham_sum;  // [0] sum of hamming distances, [1] pairs visited
+  unsigned long long *ham_sum;  // [0] sum of hamming distances, [1] pairs visited (mode 1: pair-words executed)
 };
 
 // acc += pc on the FMA pipe: a 3-register IMAD (multiplier held in a register so ptxas cannot
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
   int cur_c = 0;
   long long cur_it = 0;
   bool warp_done = false;  // MODE 1: this warp's sub-tile can no longer contain a neighbour pair
+  unsigned long long words_done = 0;  // MODE 1: 32-site words this warp really processed (x 1024 pairs each)
   for (long long f = 0; f < n_flat; ++f) {
     cp_async_wait<0>();
     __syncthreads();  // stage f landed for everyone; everyone is done with stage f-1
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
       for (int w0 = 0; w0 < wcount && !warp_done; w0 += 2) {
         process_word(w0);
         if (w0 + 1 < wcount) process_word(w0 + 1);
+        words_done += (w0 + 1 < wcount) ? 2 : 1;
         unsigned dmin = acc[0][0];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -326,6 +328,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
   }
   cp_async_wait<0>();
 
+  if (MODE == 1) {
+    if (lane == 0 && words_done) atomicAdd(P.ham_sum + 1, words_done * 1024ull);  // executed pair-words (roofline evidence)
+  }
   if (MODE == 0 || MODE == 2) {
     for (int o = 16; o; o >>= 1) {
       ham_local += __shfl_xor_sync(0xffffffffu, ham_local, o);
@@ -366,7 +371,7 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
   if (mode < 0 || mode > 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "pair_pass: mode must be 0, 1 or 2");
   GDCA_TRY(gdca_reserve(ctx, ctx->dCounts, ctx->capCounts, (size_t)3 * ctx->Mpad));
   if (mode != 0) GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dCounts, 0, (size_t)3 * ctx->Mpad * sizeof(int32_t), ctx->stream));
-  if (mode != 1) GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dHam, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dHam, 0, 2 * sizeof(unsigned long long), ctx->stream));
   if (sample_stride < 1) sample_stride = 1;
 
   PairParams P;

@@ -124,7 +124,8 @@ int32_t gdca_dev_load_resident(gdca_ctx *ctx, const int8_t *Z_dev, int64_t L, in
 int32_t gdca_dev_pair_pass(gdca_ctx *ctx, int32_t mode, int64_t thresh);
 /* mode-0 sweep over every stride-th tile of this shard (cheap estimate of the mean identity). */
 int32_t gdca_dev_pair_sample(gdca_ctx *ctx, int32_t stride);
-/* partial results of this shard, device pointers: u64[2] {hamming sum, pairs visited}; int32[3*Mpad] counts (row t = thresh-1+t
+/* partial results of this shard, device pointers: u64[2] {hamming sum, pairs visited} (after a mode-1 sweep
+ * slot [1] holds the number of (pair, 32-site word) units really executed, i.e. not skipped by the early exit); int32[3*Mpad] counts (row t = thresh-1+t
  * in mode 2, row 0 only in mode 1), NOT including the self count. */
 void *gdca_dev_ham_sum_ptr(gdca_ctx *ctx);
 void *gdca_dev_counts_ptr(gdca_ctx *ctx);
