@@ -198,7 +198,12 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
     return GDCA_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e);
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail(e);
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fact, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dHam, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dQ, sizeof(int))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dMeff, 2 * sizeof(double))) != cudaSuccess) return fail(e);
@@ -221,6 +226,9 @@ void gdca_destroy(gdca_ctx *ctx) {
     if (b) cudaFree(b);
   for (int i = 0; i < EV_COUNT; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->ev_fact) cudaEventDestroy(ctx->ev_fact);
+  if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -346,12 +346,13 @@ __global__ void mirror_lower_kernel(double *__restrict__ A, long long n, long lo
 }
 
 template <bool AT, bool BT>
-int32_t gemm(gdca_ctx *ctx, const GemmP &p, int batch) {
+int32_t gemm(gdca_ctx *ctx, const GemmP &p, int batch, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->stream;
   if (p.m <= 0 || p.n <= 0 || batch <= 0) return GDCA_OK;
   const size_t smem = (size_t)GSTAGES * 2 * TILE_D * sizeof(double);
   GDCA_CUDA(ctx, cudaFuncSetAttribute(dgemm_kernel<AT, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)(p.n / NB), (unsigned)(p.m / NB), (unsigned)batch);
-  dgemm_kernel<AT, BT><<<grid, GTHREADS, smem, ctx->stream>>>(p);
+  dgemm_kernel<AT, BT><<<grid, GTHREADS, smem, stream>>>(p);
   GDCA_LAUNCH_CHECK(ctx);
   return GDCA_OK;
 }
@@ -380,6 +381,8 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   // inner step (128 columns): diagonal block, panel, update of the remaining columns of the OUTER block only;
   // after OB inner steps one trailing update with K = OB*128 (C tiles read/written n/512 times, not n/128).
   constexpr int OB = 4;
+  cudaStream_t sA = ctx->stream, sB = ctx->stream2;
+  bool pending_trail = false;
   for (int K0 = 0; K0 < nb; K0 += OB) {
     const int Kend = (K0 + OB < nb) ? K0 + OB : nb;
     for (int k = K0; k < Kend; ++k) {
@@ -407,15 +410,33 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
     }
     const int rem = nb - Kend;
     if (rem > 0) {
-      // A[I,J] -= L[I,K0:Kend] L[J,K0:Kend]'  for I >= J >= Kend
+      // Trailing update A[I,J] -= L[I,K0:Kend] L[J,K0:Kend]' (I >= J >= Kend), split for a one-panel look-ahead:
+      //   part 1 (main stream): only the columns of the NEXT outer panel [Kend, Kn) -- the factorisation goes on;
+      //   part 2 (helper stream, low priority): all columns >= Kn, overlapping the next panel's serial chain.
+      const int Kn = (Kend + OB < nb) ? Kend + OB : nb;
+      GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_fact, sA));          // panel [K0,Kend) is final
+      if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));  // columns >= Kend carry update K0-OB
       GemmP t{};
       t.A = blk(A, Kend, K0); t.lda = np;
       t.B = blk(A, Kend, K0); t.ldb = np;
       t.C = blk(A, Kend, Kend); t.ldc = np;
-      t.m = rem * NB; t.n = rem * NB; t.k = (Kend - K0) * NB; t.flags = G_LOWER_OUT; t.alpha = -1.0; t.beta = 1.0;
-      GDCA_TRY((gemm<false, false>(ctx, t, 1)));
+      t.m = rem * NB; t.n = (Kn - Kend) * NB; t.k = (Kend - K0) * NB; t.flags = G_LOWER_OUT; t.alpha = -1.0; t.beta = 1.0;
+      GDCA_TRY((gemm<false, false>(ctx, t, 1, sA)));
+      const int rem2 = nb - Kn;
+      if (rem2 > 0) {
+        GDCA_CUDA(ctx, cudaStreamWaitEvent(sB, ctx->ev_fact, 0));
+        GemmP u{};
+        u.A = blk(A, Kn, K0); u.lda = np;
+        u.B = blk(A, Kn, K0); u.ldb = np;
+        u.C = blk(A, Kn, Kn); u.ldc = np;
+        u.m = rem2 * NB; u.n = rem2 * NB; u.k = (Kend - K0) * NB; u.flags = G_LOWER_OUT; u.alpha = -1.0; u.beta = 1.0;
+        GDCA_TRY((gemm<false, false>(ctx, u, 1, sB)));
+        GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_trail, sB));
+        pending_trail = true;
+      }
     }
   }
+  if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));
 
   // ---------------- trtri by recursive doubling ----------------
   for (int h = 1; h < nb; h *= 2) {

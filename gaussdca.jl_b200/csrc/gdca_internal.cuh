@@ -15,7 +15,9 @@
 struct gdca_ctx {
   int device = 0;
   int num_sms = GDCA_NUM_SMS_DEFAULT;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // main stream (created with the highest priority: it carries every critical path)
+  cudaStream_t stream2 = nullptr;  // helper stream: bulk trailing updates of the Cholesky (look-ahead)
+  cudaEvent_t ev_fact = nullptr, ev_trail = nullptr;  // look-ahead hand-shakes
   std::string err;
   int32_t shard_rank = 0, shard_world = 1;
   int64_t launches = 0;

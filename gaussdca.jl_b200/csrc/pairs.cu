@@ -201,16 +201,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
       // Early exit (exact): hamming only grows with more sites, so once every pair of this WARP's 16 x 64
       // sub-tile has reached thresh none of them can be a neighbour and the remaining words are skipped.
       // Each warp decides alone (no CTA barrier); the vote costs ~20 instructions per two words.
-      for (int w0 = 0; w0 < wcount && !warp_done; w0 += 2) {
-        process_word(w0);
-        if (w0 + 1 < wcount) process_word(w0 + 1);
-        words_done += (w0 + 1 < wcount) ? 2 : 1;
+      // no pair can reach thresh before ceil(thresh/32) words: run those without votes, fully pipelined,
+      // vote once right after them, then every two words
+      auto vote = [&]() {
         unsigned dmin = acc[0][0];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j) dmin = min(dmin, acc[i][j]);
         warp_done = __all_sync(0xffffffffu, (int)dmin >= P.thresh) != 0;
+      };
+      int n_free = (P.thresh + 31) / 32 - cur_c * WC;
+      n_free = max(0, min(n_free, wcount));
+      if (!warp_done && n_free > 0) {
+#pragma unroll 4
+        for (int w = 0; w < n_free; ++w) process_word(w);
+        words_done += n_free;
+        vote();
+      }
+      for (int w0 = n_free; w0 < wcount && !warp_done; w0 += 2) {
+        process_word(w0);
+        if (w0 + 1 < wcount) process_word(w0 + 1);
+        words_done += (w0 + 1 < wcount) ? 2 : 1;
+        vote();
       }
     } else {
 #pragma unroll 4
