@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
     if (MODE == 1) {
       // Early exit (exact): hamming only grows with more sites, so once every pair of this WARP's 16 x 64
       // sub-tile has reached thresh none of them can be a neighbour and the remaining words are skipped.
-      // Each warp decides alone (no CTA barrier); the vote costs ~20 instructions per two words.
+      // Each warp decides alone (no CTA barrier); the vote costs ~20 instructions per word (224 instructions).
       // no pair can reach thresh before ceil(thresh/32) words: run those without votes, fully pipelined,
-      // vote once right after them, then every two words
+      // vote once right after them, then after every word
       auto vote = [&]() {
         unsigned dmin = acc[0][0];
 #pragma unroll
@@ -219,10 +219,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
         words_done += n_free;
         vote();
       }
-      for (int w0 = n_free; w0 < wcount && !warp_done; w0 += 2) {
+      for (int w0 = n_free; w0 < wcount && !warp_done; ++w0) {
         process_word(w0);
-        if (w0 + 1 < wcount) process_word(w0 + 1);
-        words_done += (w0 + 1 < wcount) ? 2 : 1;
+        words_done += 1;
         vote();
       }
     } else {
