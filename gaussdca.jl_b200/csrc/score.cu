@@ -17,21 +17,50 @@ namespace {
 
 constexpr int SW = 4;  // warps (blocks j) per CTA
 
+// One warp per (i<j) block.  The block is read ONCE from HBM with 16-byte loads issued back to back (all of a
+// lane's loads are in flight before the first use), parked in shared memory, and the gauge is applied in a
+// second pass over shared memory (two-pass for accuracy: ||K|| can be far below ||B||).
 __global__ void __launch_bounds__(SW * 32) fn_kernel(const double *__restrict__ mJ, long long ld, int L, int s,
                                                      double *__restrict__ S) {
   extern __shared__ double sm[];  // [SW][s*s + 2*s]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.y, j = blockIdx.x * SW + warp;
   if (j <= i || j >= L) return;
-  double *Bk = sm + (size_t)warp * (s * s + 2 * s);
+  double *Bk = sm + (size_t)warp * (s * s + 2 * s + 2);
   double *rs = Bk + s * s, *cs = rs + s;
   const int ss = s * s;
   double tot = 0.0;
-  for (int e = lane; e < ss; e += 32) {
-    const int a = e / s, b = e - a * s;
-    const double v = mJ[((long long)i * s + a) * ld + (long long)j * s + b];
-    Bk[e] = v;
-    tot += v;
+  const double *base = mJ + ((long long)i * s) * ld + (long long)j * s;
+  if ((s & 1) == 0) {
+    // rows of s doubles are 16-byte aligned (ld and j*s are even): s/2 double2 per row
+    const int hs = s >> 1, nv = s * hs;
+    constexpr int MAXV = 8;  // up to 8 x 32 double2 = 512 doubles >= 30*30/2
+    double2 v[MAXV];
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+      const int e = lane + 32 * u;
+      if (e < nv) {
+        const int a = e / hs, b2 = e - a * hs;
+        v[u] = *reinterpret_cast<const double2 *>(base + (long long)a * ld + 2 * b2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+      const int e = lane + 32 * u;
+      if (e < nv) {
+        const int a = e / hs, b2 = e - a * hs;
+        Bk[a * s + 2 * b2] = v[u].x;
+        Bk[a * s + 2 * b2 + 1] = v[u].y;
+        tot += v[u].x + v[u].y;
+      }
+    }
+  } else {
+    for (int e = lane; e < ss; e += 32) {
+      const int a = e / s, b = e - a * s;
+      const double x = base[(long long)a * ld + b];
+      Bk[e] = x;
+      tot += x;
+    }
   }
   for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
   __syncwarp();
@@ -189,7 +218,7 @@ int32_t gdca_k_score(gdca_ctx *ctx, int score) {
   GDCA_TRY(gdca_reserve(ctx, ctx->dS, ctx->capS, (size_t)L * L));
   dim3 grid((unsigned)((L + SW - 1) / SW), (unsigned)L);
   if (score == GDCA_SCORE_FROB) {
-    const size_t smem = (size_t)SW * (s * s + 2 * s) * sizeof(double);
+    const size_t smem = (size_t)SW * (s * s + 2 * s + 2) * sizeof(double);
     fn_kernel<<<grid, SW * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, L, s, ctx->dS);
     GDCA_LAUNCH_CHECK(ctx);
   } else if (score == GDCA_SCORE_DI) {
