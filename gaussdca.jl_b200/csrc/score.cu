@@ -7,7 +7,7 @@
 //        V = (sqrt(C_ii) mJ_ij sqrt(C_jj)) (.)';  DI = s/2 log(1/2) + 1/2 sum_k log(1 + sqrt(1 + 4 lambda_k(V)))
 //      evaluated through the equivalent form lambda_k = sigma_k(Lc_i' mJ_ij Lc_j)^2 with C_ii = Lc_i Lc_i'
 //      (similarity transform; removes the per-site matrix square root).  Singular values come from a
-//      one-sided Jacobi iteration held entirely in shared memory, one warp per (i,j) block.
+//      one-sided Jacobi iteration held entirely in shared memory, three (i,j) blocks per warp.
 //
 // One warp per (i<j) block; a CTA is 4 warps sharing site i.  FN is HBM-bound (3200 B read per
 // block at s = 20); DI adds ~3e5 FP64 flop per block on the plain FP64 pipe.
@@ -118,56 +118,74 @@ __global__ void site_chol_kernel(const double *__restrict__ Cdiag, int s, double
   }
 }
 
+// One warp handles NSUB = min(3, 32 / ceil(s/2)) consecutive blocks (i, j0..j0+NSUB-1): the two 20x20x20
+// products use all 32 lanes per block, and the Jacobi rounds -- s/2 disjoint column pairs each -- run for
+// all NSUB blocks at once (30 of 32 lanes busy at s = 20 instead of 10).
 __global__ void __launch_bounds__(SW * 32) di_kernel(const double *__restrict__ mJ, long long ld,
-                                                     const double *__restrict__ Lc, int L, int s,
+                                                     const double *__restrict__ Lc, int L, int s, int nsub,
                                                      double *__restrict__ S) {
-  extern __shared__ double sm[];  // Li[s*s] + SW * (G[s*(s+1)] + Lj[s*s] + T1[s*s])
+  extern __shared__ double sm[];  // Li[s*s] + SW * (nsub * G[s*(s+1)] + Lj[s*s] + T1[s*s])
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.y, j = blockIdx.x * SW + warp;
+  const int i = blockIdx.y;
+  const int j0 = (blockIdx.x * SW + warp) * nsub;
   const int ss = s * s, gs = s + 1;
   double *Li = sm;
   for (int e = threadIdx.x; e < ss; e += SW * 32) Li[e] = Lc[(long long)i * ss + e];
   __syncthreads();
-  if (j <= i || j >= L) return;
-  double *G = sm + ss + (size_t)warp * (s * gs + 2 * ss);
-  double *Lj = G + s * gs, *T1 = Lj + ss;
-  // B (row-major, temporarily in G) and Lj
-  for (int e = lane; e < ss; e += 32) {
-    const int a = e / s, b = e - a * s;
-    G[e] = mJ[((long long)i * s + a) * ld + (long long)j * s + b];
-    Lj[e] = Lc[(long long)j * ss + e];
+  if (j0 + nsub - 1 <= i || j0 >= L) return;  // no block of this warp lies in the upper triangle
+  double *Gall = sm + ss + (size_t)warp * (nsub * s * gs + 2 * ss);
+  double *Lj = Gall + nsub * s * gs, *T1 = Lj + ss;
+
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int j = j0 + sub;
+    double *G = Gall + sub * s * gs;
+    if (j <= i || j >= L) {  // inactive slot: zero columns never rotate
+      for (int e = lane; e < s * gs; e += 32) G[e] = 0.0;
+      __syncwarp();
+      continue;
+    }
+    // B (row-major, temporarily in G) and Lj
+    for (int e = lane; e < ss; e += 32) {
+      const int a = e / s, b = e - a * s;
+      G[e] = mJ[((long long)i * s + a) * ld + (long long)j * s + b];
+      Lj[e] = Lc[(long long)j * ss + e];
+    }
+    __syncwarp();
+    // T1 = B * Lj      (Lj lower: k >= b)
+    for (int e = lane; e < ss; e += 32) {
+      const int a = e / s, b = e - a * s;
+      double t = 0.0;
+      for (int k = b; k < s; ++k) t += G[a * s + k] * Lj[k * s + b];
+      T1[e] = t;
+    }
+    __syncwarp();
+    // A = Li' * T1     (Li lower: k >= a);  stored column-major in G with stride gs
+    for (int e = lane; e < ss; e += 32) {
+      const int a = e / s, b = e - a * s;
+      double t = 0.0;
+      for (int k = a; k < s; ++k) t += Li[k * s + a] * T1[k * s + b];
+      G[b * gs + a] = t;  // column b, row a
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  // T1 = B * Lj      (Lj lower: k >= b)
-  for (int e = lane; e < ss; e += 32) {
-    const int a = e / s, b = e - a * s;
-    double t = 0.0;
-    for (int k = b; k < s; ++k) t += G[a * s + k] * Lj[k * s + b];
-    T1[e] = t;
-  }
-  __syncwarp();
-  // A = Li' * T1     (Li lower: k >= a);  stored column-major in G with stride gs
-  for (int e = lane; e < ss; e += 32) {
-    const int a = e / s, b = e - a * s;
-    double t = 0.0;
-    for (int k = a; k < s; ++k) t += Li[k * s + a] * T1[k * s + b];
-    G[b * gs + a] = t;  // column b, row a
-  }
-  __syncwarp();
-  // ---- one-sided Jacobi: orthogonalise the columns of G; sigma_k^2 = ||g_k||^2 ----
+
+  // ---- one-sided Jacobi: orthogonalise the columns of every G; sigma_k^2 = ||g_k||^2 ----
   const int nc = (s + 1) & ~1;  // even number of players (last one is a bye when s is odd)
   const int half = nc >> 1;
+  const int mysub = lane / half, mypair = lane - mysub * half;
+  const bool jlane = mysub < nsub;
+  double *G = Gall + (jlane ? mysub : 0) * s * gs;
   for (int sweep = 0; sweep < 40; ++sweep) {
     bool rotated = false;
     for (int r = 0; r < nc - 1; ++r) {
       int p = -1, q2 = -1;
-      if (lane < half) {
-        if (lane == 0) {
+      if (jlane) {
+        if (mypair == 0) {
           p = nc - 1;
           q2 = r;
         } else {
-          p = (r + lane) % (nc - 1);
-          q2 = (r - lane + (nc - 1)) % (nc - 1);
+          p = (r + mypair) % (nc - 1);
+          q2 = (r - mypair + (nc - 1)) % (nc - 1);
         }
       }
       if (p >= 0 && p < s && q2 < s) {
@@ -179,7 +197,7 @@ __global__ void __launch_bounds__(SW * 32) di_kernel(const double *__restrict__ 
           be += y * y;
           ga += x * y;
         }
-        if (fabs(ga) > 1e-16 * sqrt(al * be) && ga != 0.0) {
+        if (fabs(ga) > 1e-15 * sqrt(al * be) && ga != 0.0) {
           const double zeta = (be - al) / (2.0 * ga);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double cth = 1.0 / sqrt(1.0 + t * t), sth = cth * t;
@@ -195,18 +213,23 @@ __global__ void __launch_bounds__(SW * 32) di_kernel(const double *__restrict__ 
     }
     if (!__any_sync(0xffffffffu, rotated)) break;
   }
-  double part = 0.0;
-  if (lane < s) {
-    const double *gk = G + lane * gs;
-    double lam = 0.0;
-    for (int k = 0; k < s; ++k) lam += gk[k] * gk[k];
-    part = log(1.0 + sqrt(1.0 + 4.0 * lam));
-  }
-  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if (lane == 0) {
-    const double di = 0.5 * s * log(0.5) + 0.5 * part;
-    S[(long long)i * L + j] = di;
-    S[(long long)j * L + i] = di;
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int j = j0 + sub;
+    if (j <= i || j >= L) continue;  // warp-uniform
+    const double *Gs = Gall + sub * s * gs;
+    double part = 0.0;
+    if (lane < s) {
+      const double *gk = Gs + lane * gs;
+      double lam = 0.0;
+      for (int k = 0; k < s; ++k) lam += gk[k] * gk[k];
+      part = log(1.0 + sqrt(1.0 + 4.0 * lam));
+    }
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) {
+      const double di = 0.5 * s * log(0.5) + 0.5 * part;
+      S[(long long)i * L + j] = di;
+      S[(long long)j * L + i] = di;
+    }
   }
 }
 
@@ -227,9 +250,12 @@ int32_t gdca_k_score(gdca_ctx *ctx, int score) {
     double *Lc = ctx->dRed;
     site_chol_kernel<<<(unsigned)L, 32, (size_t)s * s * sizeof(double), ctx->stream>>>(ctx->dCdiag, s, Lc);
     GDCA_LAUNCH_CHECK(ctx);
-    const size_t smem = ((size_t)s * s + (size_t)SW * (s * (s + 1) + 2 * s * s)) * sizeof(double);
+    const int half = (s + 1) / 2;
+    const int nsub = (32 / half) < 3 ? (32 / half) : 3;
+    const size_t smem = ((size_t)s * s + (size_t)SW * ((size_t)nsub * s * (s + 1) + 2 * s * s)) * sizeof(double);
     GDCA_CUDA(ctx, cudaFuncSetAttribute(di_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    di_kernel<<<grid, SW * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, Lc, L, s, ctx->dS);
+    dim3 dgrid((unsigned)((L + SW * nsub - 1) / (SW * nsub)), (unsigned)L);
+    di_kernel<<<dgrid, SW * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, Lc, L, s, nsub, ctx->dS);
     GDCA_LAUNCH_CHECK(ctx);
   } else {
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "score: must be 0 (frob) or 1 (DI)");
