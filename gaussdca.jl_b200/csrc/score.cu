@@ -34,24 +34,26 @@ __global__ void __launch_bounds__(SW * 32) fn_kernel(const double *__restrict__ 
   if ((s & 1) == 0) {
     // rows of s doubles are 16-byte aligned (ld and j*s are even): s/2 double2 per row
     const int hs = s >> 1, nv = s * hs;
-    constexpr int MAXV = 8;  // up to 8 x 32 double2 = 512 doubles >= 30*30/2
-    double2 v[MAXV];
+    constexpr int MAXV = 8;  // 8 x 32 double2 in flight per round (one round at s = 20, two at s = 30)
+    for (int e0 = 0; e0 < nv; e0 += MAXV * 32) {
+      double2 v[MAXV];
 #pragma unroll
-    for (int u = 0; u < MAXV; ++u) {
-      const int e = lane + 32 * u;
-      if (e < nv) {
-        const int a = e / hs, b2 = e - a * hs;
-        v[u] = *reinterpret_cast<const double2 *>(base + (long long)a * ld + 2 * b2);
+      for (int u = 0; u < MAXV; ++u) {
+        const int e = e0 + lane + 32 * u;
+        if (e < nv) {
+          const int a = e / hs, b2 = e - a * hs;
+          v[u] = *reinterpret_cast<const double2 *>(base + (long long)a * ld + 2 * b2);
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < MAXV; ++u) {
-      const int e = lane + 32 * u;
-      if (e < nv) {
-        const int a = e / hs, b2 = e - a * hs;
-        Bk[a * s + 2 * b2] = v[u].x;
-        Bk[a * s + 2 * b2 + 1] = v[u].y;
-        tot += v[u].x + v[u].y;
+      for (int u = 0; u < MAXV; ++u) {
+        const int e = e0 + lane + 32 * u;
+        if (e < nv) {
+          const int a = e / hs, b2 = e - a * hs;
+          Bk[a * s + 2 * b2] = v[u].x;
+          Bk[a * s + 2 * b2 + 1] = v[u].y;
+          tot += v[u].x + v[u].y;
+        }
       }
     }
   } else {

@@ -270,7 +270,7 @@ def test_inverse_not_spd_raises_posdef(pkg, orc, ctx):
     assert ei.value.info == eo.value.info == 151
 
 
-@pytest.mark.parametrize("q", [21, 20, 5])
+@pytest.mark.parametrize("q", [21, 20, 5, 25, 31, 3])
 def test_scores_vs_oracle_random_spd(pkg, orc, ctx, q):
     s, L = q - 1, 12
     n = s * L
@@ -385,3 +385,63 @@ def test_properties_at_full_config_B(pkg, ctx):
     C, Pi, q = pkg.compute_covariance(Z, w["W"], w["Meff"], 0.8, ctx=ctx)
     mJ = pkg.inverse(C, ctx=ctx)
     assert np.max(np.abs(mJ @ C - np.eye(C.shape[0]))) < 1e-9
+
+
+# ----------------------------------------------------------------------------- more edges
+def test_synthetic_generator_bytes_match_oracle(pkg, orc, ctx):
+    from gaussdca_jl_b200._lib import ptr
+    for L, M in [(37, 230), (200, 1000), (5, 49)]:
+        Z = np.empty((M, L), dtype=np.int8)
+        ctx.check(ctx.lib.gdca_synth_alignment(ctx.h, ptr(Z), L, M, 20140321))
+        assert np.array_equal(Z, orc.synth_alignment(L, M, 20140321))
+
+
+def test_q31_thirty_states(pkg, orc, ctx):
+    """Largest alphabet the reference allows (q = 31, src/GaussDCA.jl:26): 5 planes, s = 30 blocks."""
+    rng = np.random.default_rng(31)
+    Z = rng.integers(1, 32, size=(600, 9), dtype=np.int8)
+    Z[0, 0] = 31
+    for score in ("frob", "DI"):
+        st = {}
+        Ro = orc.gdca_from_Z(Z, 0.5, "auto", score, 2, stages=st)
+        R, s = pkg.gdca_from_alignment(Z, 0.5, "auto", score, 2, ctx=ctx, return_stats=True)
+        assert s["q"] == 31 and s["n"] == 270 and s["thresh"] == st["thresh"] and s["meff"] == st["Meff"]
+        assert_rank_equal_tie_aware(R, Ro)
+
+
+def test_degenerate_shapes(pkg, orc, ctx):
+    # L <= min_separation: empty ranking, like the reference's zero-length Vector (src/GaussDCA.jl:90)
+    Z = orc.synth_alignment(5, 300, seed=1)
+    assert pkg.gdca_from_alignment(Z, ctx=ctx) == []
+    assert pkg.gdca_from_alignment(Z, min_separation=4, ctx=ctx)[0][:2] == (1, 5)
+    # a single sequence: theta must be given, W = 1, C comes from the pseudocount alone
+    Z1 = orc.synth_alignment(12, 1, seed=2)
+    Z1[0, 0] = 21
+    Ro = orc.gdca_from_Z(Z1, 0.8, 0.2, "frob", 3)
+    R = pkg.gdca_from_alignment(Z1, 0.8, 0.2, "frob", 3, ctx=ctx)
+    assert_rank_equal_tie_aware(R, Ro)
+    with pytest.raises(ValueError, match="at least 2 sequences"):
+        pkg.gdca_from_alignment(Z1, ctx=ctx)
+    # all sequences identical: every pair is a neighbour, Meff = 1
+    Zs = np.repeat(orc.synth_alignment(20, 1, seed=3), 500, axis=0)
+    Zs[:, 0] = 21
+    w = pkg.compute_weights(Zs, "auto", ctx=ctx, full=True)
+    assert w["theta"] == orc.compute_theta(Zs) and np.all(w["counts"] == 500) and w["Meff"] == 1.0
+
+
+def test_resident_run_equals_host_run_and_context_reuse(pkg, orc, ctx):
+    """gdca_run_resident (Z already in HBM) == gdca_run (host Z); one context across shapes and scores."""
+    import ctypes
+    import torch
+    from gaussdca_jl_b200 import _lib as glib
+    for (L, M, score) in [(64, 5000, "frob"), (33, 700, "DI"), (128, 2000, "frob")]:
+        Z = orc.synth_alignment(L, M, seed=L)
+        R_host = pkg.gdca_from_alignment(Z, score=score, ctx=ctx, as_array=True)
+        Zd = torch.from_numpy(Z).cuda()
+        n_out = int(ctx.lib.gdca_ranking_length(L, 5))
+        R = np.empty(n_out, dtype=glib.RANK_DTYPE)
+        st = glib.Stats()
+        ctx.check(ctx.lib.gdca_run_resident(ctx.h, ctypes.c_void_p(Zd.data_ptr()), L, M, -1.0, 0.8,
+                                            glib.SCORE_CODES[score], 5, glib.ptr(R), n_out, ctypes.byref(st)))
+        assert np.array_equal(R, R_host)          # same kernels, same order: bit-identical
+        assert st.theta_passes == 1 and st.ms_total > 0
