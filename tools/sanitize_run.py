@@ -1,0 +1,17 @@
+"""Small end-to-end runs for compute-sanitizer (memcheck / racecheck): fixtures + ragged synthetic shapes."""
+import sys
+sys.path.insert(0, ".")
+import numpy as np
+import __graft_entry__ as g
+pkg = g.load_package()
+orc = g.load_oracle()
+ctx = pkg.Context(0)
+R = pkg.gDCA("tests/golden/small.fasta.gz", ctx=ctx)
+print("small frob", R[0])
+R = pkg.gDCA("tests/golden/small.fasta.gz", pseudocount=0.2, score="DI", remove_dups=True, ctx=ctx)
+print("small DI", R[0])
+for L, M in [(33, 129), (70, 300), (130, 257)]:
+    Z = orc.synth_alignment(L, M, seed=L)
+    for score in ("frob", "DI"):
+        R = pkg.gdca_from_alignment(Z, score=score, ctx=ctx)
+        print(L, M, score, R[0])
