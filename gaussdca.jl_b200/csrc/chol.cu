@@ -61,7 +61,9 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 template <bool AT, bool BT>
 __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(GemmP p) {
   extern __shared__ __align__(16) double sm[];
-  const int m0 = blockIdx.y * NB, n0 = blockIdx.x * NB;
+  // longest-K tiles first: with G_KEND_M the K range grows with m0, so walk the block rows from the bottom
+  const int by = (p.flags & G_KEND_M) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int m0 = by * NB, n0 = blockIdx.x * NB;
   if ((p.flags & G_LOWER_OUT) && n0 > m0) return;
   int kbeg = 0, kend = p.k;
   if (p.flags & G_KBEG_N) kbeg = max(kbeg, n0);
