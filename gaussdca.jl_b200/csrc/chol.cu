@@ -19,7 +19,7 @@ namespace {
 
 constexpr int NB = GDCA_NB;  // 128
 constexpr int BK = 16;
-constexpr int GSTAGES = 3;
+constexpr int GSTAGES = 4;      // 4-slot ring: stage kt+1 is already visible while kt is computed (fragment prefetch)
 constexpr int LDS_N = BK + 4;    // [row][k] tile stride (doubles): conflict-free 64-bit fragment loads
 constexpr int LDS_T = NB + 8;    // [k][row] tile stride
 constexpr int TILE_D = NB * LDS_N;  // 2560 doubles >= BK*LDS_T = 2176
@@ -112,27 +112,43 @@ __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(GemmP p) {
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
+  auto load_frags = [&](const double *As, const double *Bs, int kk, double (&a)[8], double (&b)[4]) {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+      a[mi] = AT ? As[(kk * 4 + c) * LDS_T + wm * 64 + mi * 8 + g] : As[(wm * 64 + mi * 8 + g) * LDS_N + kk * 4 + c];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+      b[ni] = BT ? Bs[(kk * 4 + c) * LDS_T + wn * 32 + ni * 8 + g] : Bs[(wn * 32 + ni * 8 + g) * LDS_N + kk * 4 + c];
+  };
+
+  // Ring invariant at the top of iteration kt: stages <= kt+1 have landed and are visible to every thread, so the
+  // first fragments of stage kt+1 can be fetched while the last DMMAs of stage kt issue -- the barrier and the
+  // shared-memory latency no longer sit in front of the tensor pipe.
   load_stage(0);
   load_stage(1);
+  load_stage(2);
+  double fa[2][8], fb[2][4];  // ping-pong fragment registers (BK/4 is even: every stage starts on buffer 0)
+  cp_wait<2>();  // stage 0
+  __syncthreads();
+  if (nk > 0) load_frags(sm, sm + TILE_D, 0, fa[0], fb[0]);
   for (int kt = 0; kt < nk; ++kt) {
-    cp_wait<GSTAGES - 2>();
+    cp_wait<1>();  // stages <= kt+1 (only kt+2 may still be in flight)
     __syncthreads();
-    load_stage(kt + GSTAGES - 1);
+    load_stage(kt + GSTAGES - 1);  // slot of stage kt-1: everyone finished reading it before this barrier
     const double *As = sm + (size_t)(kt % GSTAGES) * 2 * TILE_D;
     const double *Bs = As + TILE_D;
+    const double *An = sm + (size_t)((kt + 1) % GSTAGES) * 2 * TILE_D;
+    const double *Bn = An + TILE_D;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[8], b[4];
-#pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
-        a[mi] = AT ? As[(kk * 4 + c) * LDS_T + wm * 64 + mi * 8 + g] : As[(wm * 64 + mi * 8 + g) * LDS_N + kk * 4 + c];
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
-        b[ni] = BT ? Bs[(kk * 4 + c) * LDS_T + wn * 32 + ni * 8 + g] : Bs[(wn * 32 + ni * 8 + g) * LDS_N + kk * 4 + c];
+      if (kk + 1 < BK / 4)
+        load_frags(As, Bs, kk + 1, fa[(kk + 1) & 1], fb[(kk + 1) & 1]);
+      else if (kt + 1 < nk)
+        load_frags(An, Bn, 0, fa[0], fb[0]);
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], fa[kk & 1][mi], fb[kk & 1][ni]);
     }
   }
   cp_wait<0>();
