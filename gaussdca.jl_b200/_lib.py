@@ -97,6 +97,12 @@ SIGNATURES = {
     "gdca_synth_alignment_dev": (_i32, [_p, _p, _i64, _i64, _u64]),
     "gdca_synth_alignment": (_i32, [_p, _p, _i64, _i64, _u64]),
     "gdca_probe_peaks": (_i32, [_p, _pdbl, _pdbl, _pdbl, _pdbl]),
+    "gdca_read_fasta_alignment": (_i32, [ctypes.c_char_p, _dbl, ctypes.POINTER(_p), _pi64, _pi64]),
+    "gdca_remove_duplicate_sequences": (_i32, [_p, _i64, _i64, _p, _pi64, _p]),
+    "gdca_write_rank": (_i32, [ctypes.c_char_p, _p, _i64]),
+    "gdca_format_rank": (_i32, [_p, _i64, _p, _i64, _pi64]),
+    "gdca_free_host": (None, [_p]),
+    "gdca_host_last_error": (ctypes.c_char_p, []),
 }
 
 _lib = None

@@ -100,11 +100,18 @@ def printrank(*args):
         io, R = args
     else:
         raise TypeError("printrank([io|outfile,] R)")
+    arr = R if isinstance(R, np.ndarray) else np.array(R, dtype=RANK_DTYPE).reshape(-1)
+    arr = np.ascontiguousarray(arr, dtype=RANK_DTYPE)
+    lib = _lib.load()
     if isinstance(io, (str, os.PathLike)):
-        with open(io, "w") as fh:
-            return printrank(fh, R)
-    rows = R.tolist() if isinstance(R, np.ndarray) else R
-    io.write("".join("%i %i %e\n" % (i, j, x) for i, j, x in rows))
+        if lib.gdca_write_rank(os.fsencode(io), ptr(arr), arr.size) != _lib.GDCA_OK:
+            raise OSError(lib.gdca_host_last_error().decode())
+        return
+    buf = ctypes.create_string_buffer(64 * arr.size + 1)
+    used = ctypes.c_int64()
+    if lib.gdca_format_rank(ptr(arr), arr.size, buf, len(buf), ctypes.byref(used)) != _lib.GDCA_OK:
+        raise RuntimeError(lib.gdca_host_last_error().decode())
+    io.write(buf.raw[:used.value].decode("ascii"))
 
 
 # ------------------------------------------------------------------ staged, DCAUtils-shaped pieces

@@ -1,0 +1,281 @@
+// host_io.cpp -- host front-end of the gDCA path: the I/O that stays on the CPU.
+//
+//   gdca_read_fasta_alignment        DCAUtils read_fasta_alignment        (reference call site src/GaussDCA.jl:20)
+//   gdca_remove_duplicate_sequences  DCAUtils remove_duplicate_sequences  (reference call site src/GaussDCA.jl:21-23)
+//   gdca_write_rank / gdca_format_rank   printrank, "%i %i %e\n"          (reference src/GaussDCA.jl:67-74)
+//
+// Once the GPU path takes 0.14 s for a 200k-sequence alignment, parsing its 100 MB FASTA file dominates the wall
+// clock of gDCA(filename): this reader does it in one pass over the (transparently gunzipped) bytes, encoding
+// sequences in parallel.  No CUDA here; these entry points work without a GPU.
+//
+// Semantics (identical to the oracle's reader, tests/test_host_cpu.py):
+//   * a record starts at a line that begins with '>'; its sequence is the concatenation of the following lines
+//     with white space removed;
+//   * match columns = positions of the FIRST record whose character is not '.' and not a lowercase letter;
+//     every other record must have the same length ("inputs are not aligned") and the same match columns
+//     ("inconsistent inputs");
+//   * a sequence is kept when (#'-' in match columns) / L <= max_gap_fraction;
+//   * A C D E F G H I K L M N P Q R S T V W Y -> 1..20, everything else (B J O U X Z '-' ...) -> 21.
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gdca_b200.h"
+
+namespace {
+
+thread_local std::string g_host_error;
+
+int32_t host_fail(const char *msg) {
+  g_host_error = msg;
+  return GDCA_ERR_INVALID_ARG;
+}
+
+struct Tables {
+  int8_t code[256];
+  bool match[256];
+  Tables() {
+    for (int c = 0; c < 256; ++c) {
+      code[c] = 21;
+      match[c] = !(c == '.' || (c >= 'a' && c <= 'z'));
+    }
+    const char *aa = "ACDEFGHIKLMNPQRSTVWY";
+    for (int k = 0; aa[k]; ++k) code[(unsigned char)aa[k]] = (int8_t)(k + 1);
+  }
+};
+const Tables T;
+
+bool read_all(const char *path, std::vector<char> &buf) {
+  // plain files: one fread; gzip (magic 1f 8b): zlib
+  FILE *pf = fopen(path, "rb");
+  if (!pf) return false;
+  unsigned char magic[2] = {0, 0};
+  const size_t got2 = fread(magic, 1, 2, pf);
+  if (!(got2 == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
+    fseek(pf, 0, SEEK_END);
+    const long sz = ftell(pf);
+    fseek(pf, 0, SEEK_SET);
+    buf.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t rd = sz > 0 ? fread(buf.data(), 1, (size_t)sz, pf) : 0;
+    fclose(pf);
+    buf.resize(rd);
+    return true;
+  }
+  fclose(pf);
+  gzFile f = gzopen(path, "rb");
+  if (!f) return false;
+  gzbuffer(f, 1 << 20);
+  size_t used = 0;
+  buf.resize(1 << 22);
+  for (;;) {
+    if (used == buf.size()) buf.resize(buf.size() * 2);
+    const size_t want = buf.size() - used;
+    const int got = gzread(f, buf.data() + used, (unsigned)(want > (1u << 30) ? (1u << 30) : want));
+    if (got < 0) {
+      gzclose(f);
+      return false;
+    }
+    if (got == 0) break;
+    used += (size_t)got;
+  }
+  gzclose(f);
+  buf.resize(used);
+  return true;
+}
+
+struct Rec {
+  size_t beg, end;  // sequence bytes (may contain line breaks / blanks) in the file buffer
+};
+
+inline bool is_ws(char c) { return c == '\n' || c == '\r' || c == ' ' || c == '\t'; }
+
+// 64-bit FNV-1a over a row; good enough for a verified (memcmp) hash set
+inline uint64_t row_hash(const int8_t *p, int64_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (int64_t i = 0; i < n; ++i) {
+    h ^= (uint8_t)p[i];
+    h *= 1099511628211ull;
+  }
+  return h ^ (h >> 29);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gdca_host_last_error(void) { return g_host_error.c_str(); }
+
+void gdca_free_host(void *p) { free(p); }
+
+int32_t gdca_read_fasta_alignment(const char *path, double max_gap_fraction, int8_t **Z_out, int64_t *L_out,
+                                  int64_t *M_out) {
+  if (!path || !Z_out || !L_out || !M_out) return host_fail("read_fasta_alignment: NULL argument");
+  *Z_out = nullptr;
+  *L_out = *M_out = 0;
+  std::vector<char> buf;
+  if (!read_all(path, buf)) {
+    g_host_error = std::string("cannot open file ") + path;
+    return GDCA_ERR_INVALID_ARG;
+  }
+  // ---- index the records (a header is a line starting with '>')
+  std::vector<Rec> recs;
+  const size_t n = buf.size();
+  size_t pos = 0;
+  bool in_record = false;
+  while (pos < n) {
+    const char *nl = (const char *)memchr(buf.data() + pos, '\n', n - pos);
+    const size_t eol = nl ? (size_t)(nl - buf.data()) : n;
+    if (buf[pos] == '>') {
+      if (in_record) recs.back().end = pos;
+      recs.push_back(Rec{eol < n ? eol + 1 : n, n});
+      in_record = true;
+    }
+    pos = eol + 1;
+  }
+  if (recs.empty()) return host_fail("no sequences found in the FASTA file");
+
+  // ---- first record: length and match columns
+  auto seq_len = [&](const Rec &r) {
+    size_t len = 0;
+    for (size_t p = r.beg; p < r.end; ++p) len += !is_ws(buf[p]);
+    return len;
+  };
+  const size_t len0 = seq_len(recs[0]);
+  std::vector<uint8_t> is_match(len0);
+  int64_t L = 0;
+  {
+    size_t c = 0;
+    for (size_t p = recs[0].beg; p < recs[0].end; ++p) {
+      if (is_ws(buf[p])) continue;
+      is_match[c] = T.match[(unsigned char)buf[p]];
+      L += is_match[c];
+      ++c;
+    }
+  }
+  if (L == 0) return host_fail("alignment has no match columns");
+
+  // ---- every record: validate, count gaps, encode (parallel over records)
+  const int64_t R = (int64_t)recs.size();
+  int8_t *all = (int8_t *)malloc((size_t)R * (size_t)L);
+  if (!all) return host_fail("out of host memory");
+  std::vector<uint8_t> keep((size_t)R, 0);
+  int bad = 0;  // 1: not aligned, 2: inconsistent
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t r = 0; r < R; ++r) {
+    int8_t *row = all + (size_t)r * (size_t)L;
+    size_t c = 0;
+    int64_t m = 0, gaps = 0;
+    int err = 0;
+    for (size_t p = recs[r].beg; p < recs[r].end; ++p) {
+      const char ch = buf[p];
+      if (is_ws(ch)) continue;
+      if (c >= len0) {
+        err = 1;
+        break;
+      }
+      const bool mt = T.match[(unsigned char)ch];
+      if (mt != (bool)is_match[c]) {
+        err = 2;
+        // keep scanning to tell "not aligned" (length) from "inconsistent" (columns) like the reference does
+      } else if (mt) {
+        row[m++] = T.code[(unsigned char)ch];
+        gaps += (ch == '-');
+      }
+      ++c;
+    }
+    if (!err && c != len0) err = 1;
+    if (err == 2 && c != len0) err = 1;
+    if (err) {
+#pragma omp critical
+      if (!bad || err < bad) bad = err;
+      continue;
+    }
+    keep[(size_t)r] = ((double)gaps / (double)L <= max_gap_fraction);
+  }
+  if (bad) {
+    free(all);
+    return host_fail(bad == 1 ? "inputs are not aligned" : "inconsistent inputs");
+  }
+  // ---- compact the kept sequences, order preserved
+  int64_t M = 0;
+  for (int64_t r = 0; r < R; ++r) {
+    if (!keep[(size_t)r]) continue;
+    if (M != r) memmove(all + (size_t)M * (size_t)L, all + (size_t)r * (size_t)L, (size_t)L);
+    ++M;
+  }
+  if (M == 0) {
+    free(all);
+    char b[160];
+    snprintf(b, sizeof b, "Out of %lld sequences, none passed the filter (max_gap_fraction=%g)", (long long)R, max_gap_fraction);
+    return host_fail(b);
+  }
+  *Z_out = all;
+  *L_out = L;
+  *M_out = M;
+  return GDCA_OK;
+}
+
+int32_t gdca_remove_duplicate_sequences(const int8_t *Z, int64_t L, int64_t M, int8_t *Z_out, int64_t *M_out,
+                                        int64_t *kept) {
+  if (!Z || !Z_out || !M_out || L < 1 || M < 1) return host_fail("remove_duplicate_sequences: bad argument");
+  size_t cap = 16;
+  while (cap < (size_t)M * 2) cap <<= 1;
+  std::vector<int64_t> table(cap, -1);
+  int64_t out = 0;
+  for (int64_t k = 0; k < M; ++k) {
+    const int8_t *row = Z + (size_t)k * (size_t)L;
+    size_t h = (size_t)row_hash(row, L) & (cap - 1);
+    bool dup = false;
+    while (table[h] >= 0) {
+      if (memcmp(Z_out + (size_t)table[h] * (size_t)L, row, (size_t)L) == 0) {
+        dup = true;
+        break;
+      }
+      h = (h + 1) & (cap - 1);
+    }
+    if (dup) continue;
+    table[h] = out;
+    if (Z_out + (size_t)out * (size_t)L != row) memmove(Z_out + (size_t)out * (size_t)L, row, (size_t)L);
+    if (kept) kept[out] = k;
+    ++out;
+  }
+  *M_out = out;
+  return GDCA_OK;
+}
+
+// printrank(outfile, R): one "%i %i %e\n" line per row (src/GaussDCA.jl:67-74)
+int32_t gdca_write_rank(const char *path, const gdca_rank_t *R, int64_t n) {
+  if (!path || (!R && n > 0) || n < 0) return host_fail("write_rank: bad argument");
+  FILE *f = fopen(path, "w");
+  if (!f) {
+    g_host_error = std::string("cannot open file ") + path;
+    return GDCA_ERR_INVALID_ARG;
+  }
+  std::vector<char> line(1 << 16);
+  setvbuf(f, nullptr, _IOFBF, 1 << 20);
+  for (int64_t k = 0; k < n; ++k) fprintf(f, "%lld %lld %e\n", (long long)R[k].i, (long long)R[k].j, R[k].score);
+  const bool ok = (fclose(f) == 0);
+  return ok ? GDCA_OK : host_fail("write_rank: write failed");
+}
+
+// printrank(io, R) for hosts that own the stream: formats into buf; returns the bytes needed in *used
+// (call with cap = 0 to size the buffer: at most 64 bytes per row).
+int32_t gdca_format_rank(const gdca_rank_t *R, int64_t n, char *buf, int64_t cap, int64_t *used) {
+  if ((!R && n > 0) || n < 0 || !used) return host_fail("format_rank: bad argument");
+  int64_t off = 0;
+  char tmp[96];
+  for (int64_t k = 0; k < n; ++k) {
+    const int len = snprintf(tmp, sizeof tmp, "%lld %lld %e\n", (long long)R[k].i, (long long)R[k].j, R[k].score);
+    if (buf && off + len <= cap) memcpy(buf + off, tmp, (size_t)len);
+    off += len;
+  }
+  *used = off;
+  return (buf && off > cap) ? host_fail("format_rank: buffer too small") : GDCA_OK;
+}
+
+}  // extern "C"

@@ -160,6 +160,23 @@ int64_t gdca_dev_kernel_launches(gdca_ctx *ctx); /* kernels launched by this con
 int32_t gdca_synth_alignment_dev(gdca_ctx *ctx, int8_t *Z_dev, int64_t L, int64_t M, uint64_t seed);
 int32_t gdca_synth_alignment(gdca_ctx *ctx, int8_t *Z_host, int64_t L, int64_t M, uint64_t seed);
 
+/* ---- host front-end (no GPU needed): the I/O of src/GaussDCA.jl:20-23 and printrank (:67-74) ----------------
+ * Errors of these four are reported through gdca_host_last_error(). */
+/* DCAUtils read_fasta_alignment (call site src/GaussDCA.jl:20): plain or gzipped FASTA -> Z (L x M Int8, one sequence
+ * per column).  The buffer is malloc'ed by the library; release it with gdca_free_host. */
+int32_t gdca_read_fasta_alignment(const char *path, double max_gap_fraction, int8_t **Z_out, int64_t *L_out,
+                                  int64_t *M_out);
+/* DCAUtils remove_duplicate_sequences (call site src/GaussDCA.jl:21-23): first occurrence of every distinct sequence,
+ * order kept.  Z_out needs room for L*M bytes and may alias Z; kept (optional, int64[M]) receives the kept indices. */
+int32_t gdca_remove_duplicate_sequences(const int8_t *Z, int64_t L, int64_t M, int8_t *Z_out, int64_t *M_out,
+                                        int64_t *kept);
+/* printrank(outfile, R) / printrank(io, R): "%i %i %e\n" per row (src/GaussDCA.jl:67-74).  gdca_format_rank writes
+ * into buf (<= 64 bytes per row) and reports the bytes used. */
+int32_t gdca_write_rank(const char *path, const gdca_rank_t *R, int64_t n);
+int32_t gdca_format_rank(const gdca_rank_t *R, int64_t n, char *buf, int64_t cap, int64_t *used);
+void gdca_free_host(void *p);
+const char *gdca_host_last_error(void);
+
 /* ---- measured-peak helpers (bench only): raw pipe throughput probes --------------------------- */
 int32_t gdca_probe_peaks(gdca_ctx *ctx, double *lop3_tops, double *popc_tops, double *dmma_tflops, double *dfma_tflops);
 

@@ -125,6 +125,44 @@ def test_fasta_reader_and_dedup_match_oracle(pkg, orc, tmp_path):
     p.write_text(">a\nACD\n>b\nAC\n")
     with pytest.raises(ValueError, match="not aligned"):
         pkg.read_fasta_alignment(str(p), 0.9)
+    p.write_text(">a\nAcD\n>b\nACd\n")
+    with pytest.raises(ValueError, match="inconsistent inputs"):
+        pkg.read_fasta_alignment(str(p), 0.9)
+    with pytest.raises(ValueError, match="cannot open file"):
+        pkg.read_fasta_alignment(str(tmp_path / "missing.fasta"), 0.9)
+    p.write_text(">a\n---\n>b\n---\n")
+    with pytest.raises(ValueError, match="none passed the filter"):
+        pkg.read_fasta_alignment(str(p), 0.5)
+    # header lines may contain '>', lines may be wrapped, CRLF line ends, blank lines, text before the first record
+    p.write_bytes(b"; comment\r\n>s1 desc >still header\r\nAC\r\nDE\r\n\r\n>s2\r\nWY-K\r\n")
+    Z = pkg.read_fasta_alignment(str(p), 0.9)
+    assert Z.tolist() == [[1, 2, 3, 4], [19, 20, 21, 9]] and np.array_equal(Z, orc.read_fasta_alignment(str(p), 0.9))
+
+
+def test_fasta_reader_large_synthetic_and_gzip(pkg, orc, tmp_path):
+    """Round trip of a 3000 x 300 synthetic alignment through FASTA text (plain, wrapped at 60, and gzipped)."""
+    import gzip
+    L, M = 300, 3000
+    Z = orc.synth_alignment(L, M, seed=4)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY-", dtype=np.uint8)
+    rows = [letters[Z[k] - 1].tobytes() for k in range(M)]
+    plain = tmp_path / "a.fasta"
+    with open(plain, "wb") as f:
+        for k, r in enumerate(rows):
+            f.write(b">seq%d\n" % k)
+            for o in range(0, L, 60):
+                f.write(r[o:o + 60] + b"\n")
+    gz = tmp_path / "a.fasta.gz"
+    with open(plain, "rb") as f, gzip.open(gz, "wb") as o:
+        o.write(f.read())
+    for path in (plain, gz):
+        Zr = pkg.read_fasta_alignment(str(path), 1.0)
+        assert np.array_equal(Zr, Z)
+    # duplicates: append copies in scrambled positions, keep-first semantics and the kept indices
+    Zd = np.concatenate([Z[:50], Z[10:30], Z[:5], Z[50:60]])
+    out, kept = pkg.remove_duplicate_sequences(Zd)
+    assert np.array_equal(out, orc.remove_duplicate_sequences(Zd)) and np.array_equal(out, Zd[kept])
+    assert out.shape[0] == 60 and kept.tolist() == list(range(50)) + list(range(75, 85))
 
 
 def test_printrank_format(pkg, orc, tmp_path):
@@ -135,6 +173,10 @@ def test_printrank_format(pkg, orc, tmp_path):
     out = tmp_path / "r.txt"
     pkg.printrank(str(out), R)
     assert out.read_text() == buf.getvalue()
+    big = [(i, i + 7, (-1) ** i * 1.2345678e-3 * 10.0 ** (i % 40 - 20)) for i in range(1, 3000)]
+    b2 = io.StringIO()
+    pkg.printrank(b2, big)
+    assert b2.getvalue() == orc.format_rank(big)
     from gaussdca_jl_b200._lib import RANK_DTYPE
     arr = np.array(R, dtype=RANK_DTYPE)
     buf2 = io.StringIO()
