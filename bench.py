@@ -46,6 +46,16 @@ def peaks():
         return {}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
+    of the same workload (profiles/r1_traffic.json, made by tools/summarise_profiles.py)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]
+        return (t["dram_bytes_read"] or 0) + (t["dram_bytes_write"] or 0)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -343,7 +353,7 @@ def main():
             "ms_per_launch": t_pair * 1e3, "pairs_per_s": npairs / t_pair,
             "executed_fraction_of_full_sweep": alu_ops / full_ops,
             "effective_tlop3_per_s_full_sweep_equivalent": full_ops / t_pair / 1e12,
-            "traffic": None,
+            "traffic": ncu_traffic("pair_sweep_kernel<5, 1>") if world == 1 and args.workload == "C" else None,
             "hbm": {"achieved": hbm_bytes / t_pair / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
                     "frac": hbm_bytes / t_pair / 1e9 / pk["hbm_gbs"] if pk.get("hbm_gbs") else None,
                     "note": "compulsory bytes only; the sweep is ALU-bound, operands live in L2"},

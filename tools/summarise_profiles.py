@@ -30,6 +30,7 @@ KEYS = [
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__warps_eligible.avg.per_cycle_active",
 ]
 seen = set()
+traffic = {}
 with open(f"{OUT}/{ROUND}_top_kernels.md", "w") as f:
     f.write(f"# {ROUND}: `ncu --set full --clock-control none --import-source on` of the top kernels (config C: L=500, M=200k)\n\n"
             "One launch each, captured with tools/make_profiles.sh; read here with `ncu -i ... --page raw --csv`.\n")
@@ -54,6 +55,13 @@ with open(f"{OUT}/{ROUND}_top_kernels.md", "w") as f:
         for k in KEYS:
             if k in hdr and r[hdr.index(k)] not in ("", "n/a"):
                 f.write(f"| `{k}` | {r[hdr.index(k)]} | {units[hdr.index(k)]} |\n")
+        def _bytes(key):
+            if key not in hdr or not r[hdr.index(key)]:
+                return None
+            v = float(r[hdr.index(key)].replace(",", ""))
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(units[hdr.index(key)], 1)
+        traffic[short] = {"dram_bytes_read": _bytes("dram__bytes_read.sum"), "dram_bytes_write": _bytes("dram__bytes_write.sum"),
+                          "gpu_time_ms_under_ncu": t if units[hdr.index("gpu__time_duration.sum")].startswith("ms") else t / 1e3}
         st = []
         for i, h in enumerate(hdr):
             m = re.match(r"smsp__average_warps_issue_stalled_(.*)_per_issue_active.ratio", h)
@@ -64,6 +72,8 @@ with open(f"{OUT}/{ROUND}_top_kernels.md", "w") as f:
                     pass
         st.sort(reverse=True)
         f.write("\nstall reasons (warps per issue-active cycle): " + ", ".join(f"{n} {v:.2f}" for v, n in st[:8]) + "\n")
+
+json.dump(traffic, open(f"{OUT}/{ROUND}_traffic.json", "w"), indent=1)
 
 # ---- 3. the bench line of the same build
 if os.path.exists("gpurun_out/bench_r1.json"):
