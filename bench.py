@@ -207,6 +207,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = os.environ.get("GDCA_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = pkg.Context(local)   # raises loudly without the CUDA library / a B200
     lib = ctx.lib
