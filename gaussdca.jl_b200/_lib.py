@@ -89,6 +89,12 @@ SIGNATURES = {
     "gdca_dev_mJ_ptr": (_p, [_p]),
     "gdca_dev_score_rank": (_i32, [_p, _i32, _i64, _p, _i64]),
     "gdca_dev_S_ptr": (_p, [_p]),
+    "gdca_dev_peer_export": (_i32, [_p, _p]),
+    "gdca_dev_peer_import": (_i32, [_p, _i32, _p]),
+    "gdca_dev_peer_valid": (_i32, [_p]),
+    "gdca_dev_peer_close": (_i32, [_p]),
+    "gdca_dev_zero_counts": (_i32, [_p]),
+    "gdca_dev_zero_C": (_i32, [_p]),
     "gdca_dev_sync": (_i32, [_p]),
     "gdca_dev_copy_to_host": (_i32, [_p, _p, _p, _i64]),
     "gdca_dev_get_stats": (_i32, [_p, ctypes.POINTER(Stats)]),

@@ -10,6 +10,8 @@
 
 static thread_local std::string g_create_error;
 
+static int32_t peer_close_all(gdca_ctx *ctx);
+
 namespace {
 
 enum { EV_BEGIN = 0, EV_H2D, EV_PACK, EV_THETA, EV_WEIGHTS, EV_COV, EV_CHOL, EV_SCORE, EV_APC, EV_RANK, EV_D2H, EV_COUNT };
@@ -63,6 +65,8 @@ int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
   }
   if (q < 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "alignment has q = max(Z) < 2: nothing to couple");
   set_shape(ctx, L, M, q);
+  // buffers that peers have mapped are about to move: drop the mappings (the host re-exchanges handles)
+  if (ctx->peers_ready && ((size_t)3 * ctx->Mpad > ctx->capCounts || (size_t)ctx->npad * ctx->npad > ctx->capC)) peer_close_all(ctx);
   GDCA_TRY(gdca_k_pack(ctx));
   ctx->have_alignment = true;
   ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
@@ -217,6 +221,8 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
 void gdca_destroy(gdca_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (void *m : ctx->peer_opened)
+    if (m) cudaIpcCloseMemHandle(m);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (!ctx->dZ_borrowed) cudaFree(ctx->dZ);
   void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
@@ -384,6 +390,93 @@ int32_t gdca_dev_score_rank(gdca_ctx *ctx, int32_t score, int64_t min_separation
     GDCA_CUDA(ctx, cudaMemcpyAsync(R_host, ctx->dR, (size_t)R_len * sizeof(gdca_rank_t), cudaMemcpyDeviceToHost, ctx->stream));
     GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  return GDCA_OK;
+}
+
+// ------------------------------------------------------------------ peer memory (one process per GPU)
+static int32_t peer_close_all(gdca_ctx *ctx) {
+  for (void *&m : ctx->peer_opened) {
+    if (m) cudaIpcCloseMemHandle(m);
+    m = nullptr;
+  }
+  for (int r = 0; r < GDCA_MAX_PEERS; ++r) ctx->peer_counts[r] = nullptr, ctx->peer_C[r] = nullptr;
+  ctx->peers_ready = false;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_peer_export(gdca_ctx *ctx, uint8_t *handles128) {
+  if (!ctx || !handles128) return GDCA_ERR_INVALID_ARG;
+  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "peer_export: no alignment loaded");
+  GDCA_TRY(set_device(ctx));
+  // the buffers the peers will write into must exist (and keep their address) before the handles are taken
+  GDCA_TRY(gdca_reserve(ctx, ctx->dCounts, ctx->capCounts, (size_t)3 * ctx->Mpad));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)ctx->npad * ctx->npad));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  GDCA_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->dCounts));
+  memcpy(handles128, &h, 64);
+  GDCA_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->dC));
+  memcpy(handles128 + 64, &h, 64);
+  ctx->exported_counts = ctx->dCounts;
+  ctx->exported_C = ctx->dC;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_peer_import(gdca_ctx *ctx, int32_t world, const uint8_t *handles /* world x 128 bytes */) {
+  if (!ctx || !handles) return GDCA_ERR_INVALID_ARG;
+  if (world < 2 || world > GDCA_MAX_PEERS || world != ctx->shard_world)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "peer_import: world must equal the shard world (2..16)");
+  GDCA_TRY(set_device(ctx));
+  peer_close_all(ctx);
+  for (int r = 0; r < world; ++r) {
+    if (r == ctx->shard_rank) {
+      ctx->peer_counts[r] = ctx->dCounts;
+      ctx->peer_C[r] = ctx->dC;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    void *p = nullptr;
+    memcpy(&h, handles + (size_t)r * 128, 64);
+    GDCA_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_opened[2 * r] = p;
+    ctx->peer_counts[r] = (int32_t *)p;
+    memcpy(&h, handles + (size_t)r * 128 + 64, 64);
+    GDCA_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_opened[2 * r + 1] = p;
+    ctx->peer_C[r] = (double *)p;
+  }
+  ctx->peers_ready = true;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_peer_close(gdca_ctx *ctx) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  return peer_close_all(ctx);
+}
+
+// 1 when the exported buffers are still the live ones (no re-export / re-import needed for this alignment)
+int32_t gdca_dev_peer_valid(gdca_ctx *ctx) {
+  if (!ctx) return 0;
+  return (ctx->peers_ready && ctx->exported_counts == ctx->dCounts && ctx->exported_C == ctx->dC &&
+          ctx->capCounts >= (size_t)3 * ctx->Mpad && ctx->capC >= (size_t)ctx->npad * ctx->npad) ? 1 : 0;
+}
+
+int32_t gdca_dev_zero_counts(gdca_ctx *ctx) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dCounts, ctx->capCounts, (size_t)3 * ctx->Mpad));
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dCounts, 0, (size_t)3 * ctx->Mpad * sizeof(int32_t), ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_zero_C(gdca_ctx *ctx) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)ctx->npad * ctx->npad));
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dC, 0, (size_t)ctx->npad * ctx->npad * sizeof(double), ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return GDCA_OK;
 }
 

@@ -331,8 +331,10 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
 
   pi_kernel<<<(unsigned)L, 256, 0, ctx->stream>>>(ctx->dList, ctx->dListOff, ctx->dW, ctx->dMeff, M, ctx->q, pc, ctx->dPi);
   GDCA_LAUNCH_CHECK(ctx);
-  // zero everything: padding rows/cols, the not-yet-mirrored lower part, and other shards' rows
-  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dC, 0, (size_t)npad * npad * sizeof(double), ctx->stream));
+  // zero everything: padding rows/cols, the not-yet-mirrored lower part, and other shards' rows.  In peer mode the
+  // host zeroes rank 0's buffer (gdca_dev_zero_C) and barriers BEFORE any rank launches this stage.
+  if (!(ctx->peers_ready && ctx->shard_world > 1))
+    GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dC, 0, (size_t)npad * npad * sizeof(double), ctx->stream));
 
   CovParams P;
   P.Zq = ctx->dZq;
@@ -342,7 +344,10 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   P.W = ctx->dW;
   P.meff = ctx->dMeff;
   P.Pi = ctx->dPi;
-  P.C = ctx->dC;
+  // one process per GPU with peer buffers imported: every rank stores its rows straight into rank 0's C over
+  // NVLink (rows are dealt by site, so the writes are disjoint: the reduce is fused into the kernel's epilogue)
+  const bool peer_out = ctx->peers_ready && ctx->shard_world > 1;
+  P.C = peer_out ? ctx->peer_C[0] : ctx->dC;
   P.L = L;
   P.M = M;
   P.n = n;

@@ -11,6 +11,7 @@
 #define GDCA_TILE 128          // sequences per pair-sweep tile edge
 #define GDCA_MAX_PLANES 5      // q <= 31  ->  5 bit planes
 #define GDCA_NB 128            // Cholesky / GEMM block
+#define GDCA_MAX_PEERS 16
 
 struct gdca_ctx {
   int device = 0;
@@ -53,6 +54,14 @@ struct gdca_ctx {
   unsigned long long *dKeys = nullptr; size_t capKeys = 0;
   uint32_t *dVals = nullptr; size_t capVals = 0;
   gdca_rank_t *dR = nullptr; size_t capR = 0;
+
+  // ---- peer memory (one process per GPU): IPC-mapped counts / C buffers of the other ranks ----
+  bool peers_ready = false;
+  int32_t *peer_counts[GDCA_MAX_PEERS] = {};   // [r] -> rank r's dCounts (own rank: dCounts)
+  double *peer_C[GDCA_MAX_PEERS] = {};         // [r] -> rank r's dC
+  void *peer_opened[2 * GDCA_MAX_PEERS] = {};  // mappings to close
+  int32_t *exported_counts = nullptr;          // buffers the exported handles refer to (re-export if they moved)
+  double *exported_C = nullptr;
 
   // ---- state flags ----
   bool have_alignment = false, have_lists = false, have_weights = false, have_cov = false, have_inv = false;

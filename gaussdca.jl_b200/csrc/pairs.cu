@@ -14,7 +14,9 @@
 //     tile for L <= 512 -> one barrier per tile); the ring runs across tile boundaries, so the next
 //     tile is in flight while this one is computed.
 //   * only tiles bi <= bj of the symmetric pair matrix are visited; a hit credits both sequences.
-//   * persistent grid (one CTA per SM), items strided over (rank, world) for multi-GPU sharding.
+//   * persistent grid (one CTA per SM), items strided over (rank, world) for multi-GPU sharding; with peer
+//     buffers imported (gdca_dev_peer_import) the epilogue adds the (rare) hits into EVERY rank's counters with
+//     peer atomics over NVLink -- the all-reduce of the counts is fused into the sweep, no collective follows.
 //   * mode 1 (neighbour counts, the production path) exits a warp's 16 x 64 sub-tile as soon as all of its
 //     partial hamming distances have reached thresh -- exact, and ~40 % fewer words on typical alignments.
 //     theta = :auto no longer needs a sweep at all (cov.cu:ident_sum_kernel); modes 0 and 2 (hamming sum,
@@ -70,7 +72,8 @@ struct PairParams {
   long long n_items;   // T(T+1)/2
   int rank, world;
   int thresh;
-  int32_t *counts;     // [3][Mpad]
+  int32_t *counts[GDCA_MAX_PEERS];  // [3][Mpad] of every rank that must see the hits (fused all-reduce over peer memory)
+  int npeers;
   unsigned long long *ham_sum;  // [0] sum of hamming distances, [1] pairs visited (mode 1: pair-words executed)
 };
 
@@ -317,13 +320,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
             if (r < TILE) {
               const int v = s_row[k][r];
               if (v) {
-                atomicAdd(P.counts + (long long)k * P.Mpad + (long long)bi * TILE + r, v);
+                for (int pr = 0; pr < P.npeers; ++pr)  // own buffer and, over NVLink, every peer's
+                  atomicAdd(P.counts[pr] + (long long)k * P.Mpad + (long long)bi * TILE + r, v);
                 s_row[k][r] = 0;
               }
             } else {
               const int v = s_col[k][r - TILE];
               if (v) {
-                atomicAdd(P.counts + (long long)k * P.Mpad + (long long)bj * TILE + (r - TILE), v);
+                for (int pr = 0; pr < P.npeers; ++pr)
+                  atomicAdd(P.counts[pr] + (long long)k * P.Mpad + (long long)bj * TILE + (r - TILE), v);
                 s_col[k][r - TILE] = 0;
               }
             }
@@ -382,7 +387,9 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
   if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "pair_pass: no alignment loaded");
   if (mode < 0 || mode > 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "pair_pass: mode must be 0, 1 or 2");
   GDCA_TRY(gdca_reserve(ctx, ctx->dCounts, ctx->capCounts, (size_t)3 * ctx->Mpad));
-  if (mode != 0) GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dCounts, 0, (size_t)3 * ctx->Mpad * sizeof(int32_t), ctx->stream));
+  // in peer mode the host zeroes every rank's counters (gdca_dev_zero_counts) and barriers before the sweep
+  if (mode != 0 && !(ctx->peers_ready && ctx->shard_world > 1))
+    GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dCounts, 0, (size_t)3 * ctx->Mpad * sizeof(int32_t), ctx->stream));
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dHam, 0, 2 * sizeof(unsigned long long), ctx->stream));
   if (sample_stride < 1) sample_stride = 1;
 
@@ -398,7 +405,13 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
   P.rank = ctx->shard_rank;
   P.world = ctx->shard_world * sample_stride;
   P.thresh = thresh;
-  P.counts = ctx->dCounts;
+  if (ctx->peers_ready && ctx->shard_world > 1) {
+    P.npeers = ctx->shard_world;
+    for (int r = 0; r < P.npeers; ++r) P.counts[r] = ctx->peer_counts[r];
+  } else {
+    P.npeers = 1;
+    P.counts[0] = ctx->dCounts;
+  }
   P.ham_sum = ctx->dHam;
   switch (ctx->nplanes) {
     case 1: return launch_pairs<1>(ctx, mode, P);

@@ -7,14 +7,15 @@ sum with zeros (results are bit-identical for any number of ranks):
   theta :auto  no exchange: every rank holds the alignment and computes the exact identity sum from per-site
                state histograms (O(M L)).
   pair sweep   tiles (bi <= bj) of the M x M pair matrix dealt round-robin to ranks; every rank holds the
-               whole packed alignment.  Exchange: all-reduce(sum) of the int32 neighbour counts -- 2.4 MB at M = 200k.
-  covariance   output rows dealt to ranks by site (i mod world); each rank writes its rows of C into a
-               zeroed n x n buffer.  Exchange: reduce(sum) to rank 0 -- adding zeros is exact.
+               whole packed alignment.  Exchange FUSED into the kernel: the (rare) neighbour hits are added into
+               every rank's int32 counters with peer atomics over NVLink (CUDA-IPC mapped buffers).
+  covariance   output rows dealt to ranks by site (i mod world).  Exchange FUSED into the kernel: every rank
+               stores its rows straight into rank 0's C over NVLink (disjoint rows, no reduction needed).
   inverse, scores, APC, ranking: rank 0 (n^3 flop on one GPU; the block scores are HBM-bound
                microseconds).  Other ranks wait at the closing barrier.
 
-`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing only: the collectives run on
-buffers owned by libgdca_b200.so, enqueued on the library's own CUDA stream.
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing only: it carries the 128-byte IPC
+handles once per context and the barriers; no collective touches the data path.
 
 The control flow lives in `run_sharded`, written against a small backend interface so that the
 host logic (speculative threshold, row selection, who does what) is testable on CPU with gloo.
@@ -59,14 +60,13 @@ def run_sharded(be, dist, L: int, M: int, theta, pseudocount: float, score: str,
     if th == 0.0:
         which = -1                                # W == 1, Meff == M: no sweep at all
     else:
-        be.pair_pass(1, thresh)                   # this rank's tiles of the M x M pair matrix
-        dist.all_reduce(be.counts_tensor())       # exact integers: the sum is independent of the rank count
+        # this rank's tiles of the M x M pair matrix; afterwards EVERY rank holds the complete integer counts
+        # (GPU: peer atomics inside the sweep kernel; exact, independent of the rank count)
+        be.sweep_counts(thresh, dist)
         info["passes"] = 1
         which = 0
     info["meff"] = be.finish_weights(which)      # every rank: W = 1/count, Meff (identical everywhere)
-    be.covariance(pseudocount)                   # this rank's rows of C, zeros elsewhere
-    if world > 1:
-        dist.reduce(be.C_tensor(), dst=0)
+    be.covariance_to_root(pseudocount, dist)     # this rank's rows of C end up in rank 0's buffer
     R = None
     if rank == 0:
         be.inverse()
@@ -117,6 +117,47 @@ class GpuBackend:
     def pair_pass(self, mode, thresh):
         self.ctx.check(self.lib.gdca_dev_pair_pass(self.ctx.h, mode, thresh))
 
+    # -- exchange steps fused into the kernels over peer memory (CUDA IPC + NVLink); the host only barriers
+    def _ensure_peers(self, dist):
+        torch = self.torch
+        world = dist.get_world_size()
+        if world == 1:
+            return
+        dev = f"cuda:{self.ctx.device}"
+        ok = torch.tensor([self.lib.gdca_dev_peer_valid(self.ctx.h)], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op="min")
+        if int(ok.item()) == 1:
+            return
+        self.ctx.check(self.lib.gdca_dev_peer_close(self.ctx.h))
+        dist.barrier()                                   # nobody still maps a buffer that is about to move
+        mine = np.zeros(128, dtype=np.uint8)
+        self.ctx.check(self.lib.gdca_dev_peer_export(self.ctx.h, mine.ctypes.data_as(ctypes.c_void_p)))
+        table = dist.all_gather_bytes(mine)              # (world, 128) uint8
+        table = np.ascontiguousarray(table)
+        self.ctx.check(self.lib.gdca_dev_peer_import(self.ctx.h, world, table.ctypes.data_as(ctypes.c_void_p)))
+        dist.barrier()
+
+    def sweep_counts(self, thresh, dist):
+        self._ensure_peers(dist)
+        if dist.get_world_size() > 1:
+            self.ctx.check(self.lib.gdca_dev_zero_counts(self.ctx.h))
+            dist.barrier()                               # every rank's counters are zero before anyone adds
+        self.pair_pass(1, thresh)
+        if dist.get_world_size() > 1:
+            self.ctx.check(self.lib.gdca_dev_sync(self.ctx.h))
+            dist.barrier()                               # all peer atomics have landed
+
+    def covariance_to_root(self, pc, dist):
+        self._ensure_peers(dist)
+        if dist.get_world_size() > 1:
+            if dist.get_rank() == 0:
+                self.ctx.check(self.lib.gdca_dev_zero_C(self.ctx.h))
+            dist.barrier()
+        self.covariance(pc)
+        if dist.get_world_size() > 1:
+            self.ctx.check(self.lib.gdca_dev_sync(self.ctx.h))
+            dist.barrier()                               # all rows have landed in rank 0's C
+
     def ham_tensor(self):
         return self._view(self.lib.gdca_dev_ham_sum_ptr(self.ctx.h), (2,), "<i8")
 
@@ -163,13 +204,18 @@ class _StreamDist:
     def get_world_size(self):
         return self.d.get_world_size()
 
-    def all_reduce(self, t):
+    def all_reduce(self, t, op="sum"):
         with self.torch.cuda.stream(self.stream):
-            self.d.all_reduce(t)
+            self.d.all_reduce(t, op=self.d.ReduceOp.MIN if op == "min" else self.d.ReduceOp.SUM)
 
-    def reduce(self, t, dst=0):
-        with self.torch.cuda.stream(self.stream):
-            self.d.reduce(t, dst=dst)
+    def all_gather_bytes(self, arr):
+        """numpy uint8[k] on every rank -> numpy uint8[world, k] (control-plane data: IPC handles)."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            mine = torch.from_numpy(arr).to(f"cuda:{torch.cuda.current_device()}")
+            out = torch.empty((self.d.get_world_size(), arr.size), dtype=torch.uint8, device=mine.device)
+            self.d.all_gather_into_tensor(out, mine)
+            return out.cpu().numpy()
 
     def barrier(self):
         self.stream.synchronize()

@@ -149,6 +149,18 @@ int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info); /* C -> mJ on this devic
 void *gdca_dev_mJ_ptr(gdca_ctx *ctx);
 int32_t gdca_dev_score_rank(gdca_ctx *ctx, int32_t score, int64_t min_separation, gdca_rank_t *R_host, int64_t R_len);
 void *gdca_dev_S_ptr(gdca_ctx *ctx); /* L x L APC-corrected scores after gdca_dev_score_rank */
+/* Peer memory for one-process-per-GPU hosts: the exchange steps fused into the kernels, no collective library on
+ * the data path.  Every rank exports CUDA-IPC handles of its counts and C buffers (128 bytes: counts | C); the host
+ * all-gathers them (any transport) and imports the table.  From then on (a) the pair sweep adds its neighbour hits
+ * into EVERY rank's counters with peer atomics over NVLink (fused all-reduce) and (b) the covariance kernel stores
+ * its rows straight into rank 0's C (fused reduce; rows are dealt by site, writes are disjoint).  The host only
+ * barriers: zero_counts -> barrier -> pair_pass -> sync -> barrier; rank 0 zero_C -> barrier -> covariance -> sync -> barrier. */
+int32_t gdca_dev_peer_export(gdca_ctx *ctx, uint8_t *handles128);
+int32_t gdca_dev_peer_import(gdca_ctx *ctx, int32_t world, const uint8_t *handles /* world x 128 bytes */);
+int32_t gdca_dev_peer_valid(gdca_ctx *ctx); /* 1: imported mappings still match the live buffers */
+int32_t gdca_dev_peer_close(gdca_ctx *ctx);
+int32_t gdca_dev_zero_counts(gdca_ctx *ctx);
+int32_t gdca_dev_zero_C(gdca_ctx *ctx);
 int32_t gdca_dev_sync(gdca_ctx *ctx);
 /* stream-ordered D2H copy of any exposed device buffer, then sync (hosts without a CUDA binding) */
 int32_t gdca_dev_copy_to_host(gdca_ctx *ctx, void *dst_host, const void *src_dev, int64_t nbytes);

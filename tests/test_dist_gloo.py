@@ -77,6 +77,14 @@ class FakeBackend:
     def to_host(self, t):
         return t.tolist()
 
+    def sweep_counts(self, thresh, dist):
+        self.pair_pass(1, thresh)
+        dist.all_reduce(self.counts)          # CPU stand-in for the peer atomics of the GPU backend
+
+    def covariance_to_root(self, pc, dist):
+        self.covariance(pc)
+        dist.reduce(self.C, dst=0)            # CPU stand-in for the peer stores into rank 0's buffer
+
     def finish_weights(self, which):
         if which < 0:
             self.cnt = np.ones(self.M, dtype=np.int32)
