@@ -362,7 +362,7 @@ def main():
         }
         ctx.check(lib.gdca_set_shard(ctx.h, 0, 1))
         n = 20 * L
-        t_cov, t_chol = stage_acc.get("ms_cov", 0) / 1e3, stage_acc.get("ms_chol", 0) / 1e3
+        t_cov, t_chol = stage_acc.get("ms_cov", 0) / 1e3, (stage_acc.get("ms_chol", 0) + stage_acc.get("ms_inv", 0)) / 1e3
         stages = None if world > 1 else {
             "ms": {k: round(v, 4) for k, v in stage_acc.items()},
             "theta_passes": stats["theta_passes"],

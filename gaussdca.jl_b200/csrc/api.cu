@@ -10,9 +10,17 @@
 
 static thread_local std::string g_create_error;
 
-static int32_t peer_close_all(gdca_ctx *ctx);
-
 namespace {
+
+int32_t peer_close_all(gdca_ctx *ctx) {
+  for (void *&m : ctx->peer_opened) {
+    if (m) cudaIpcCloseMemHandle(m);
+    m = nullptr;
+  }
+  for (int r = 0; r < GDCA_MAX_PEERS; ++r) ctx->peer_counts[r] = nullptr, ctx->peer_C[r] = nullptr;
+  ctx->peers_ready = false;
+  return GDCA_OK;
+}
 
 enum { EV_BEGIN = 0, EV_H2D, EV_PACK, EV_THETA, EV_WEIGHTS, EV_COV, EV_CHOL, EV_SCORE, EV_APC, EV_RANK, EV_D2H, EV_COUNT };
 
@@ -214,6 +222,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaMalloc((void **)&ctx->dInfo, sizeof(int))) != cudaSuccess) return fail(e);
   for (int i = 0; i < EV_COUNT; ++i)
     if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreate(&ctx->ev[GDCA_EV_POTRF])) != cudaSuccess) return fail(e);
   *out = ctx;
   return GDCA_OK;
 }
@@ -230,7 +239,7 @@ void gdca_destroy(gdca_ctx *ctx) {
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR};
   for (void *b : bufs)
     if (b) cudaFree(b);
-  for (int i = 0; i < EV_COUNT; ++i)
+  for (int i = 0; i < 16; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->ev_fact) cudaEventDestroy(ctx->ev_fact);
   if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
@@ -394,16 +403,6 @@ int32_t gdca_dev_score_rank(gdca_ctx *ctx, int32_t score, int64_t min_separation
 }
 
 // ------------------------------------------------------------------ peer memory (one process per GPU)
-static int32_t peer_close_all(gdca_ctx *ctx) {
-  for (void *&m : ctx->peer_opened) {
-    if (m) cudaIpcCloseMemHandle(m);
-    m = nullptr;
-  }
-  for (int r = 0; r < GDCA_MAX_PEERS; ++r) ctx->peer_counts[r] = nullptr, ctx->peer_C[r] = nullptr;
-  ctx->peers_ready = false;
-  return GDCA_OK;
-}
-
 int32_t gdca_dev_peer_export(gdca_ctx *ctx, uint8_t *handles128) {
   if (!ctx || !handles128) return GDCA_ERR_INVALID_ARG;
   if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "peer_export: no alignment loaded");
@@ -555,8 +554,8 @@ static int32_t run_impl(gdca_ctx *ctx, const int8_t *Z, bool resident, int64_t L
     st.ms_theta = ev_ms(ctx, EV_PACK, EV_THETA);
     st.ms_weights = ev_ms(ctx, EV_THETA, EV_WEIGHTS);
     st.ms_cov = ev_ms(ctx, EV_WEIGHTS, EV_COV);
-    st.ms_chol = ev_ms(ctx, EV_COV, EV_CHOL);
-    st.ms_inv = 0.f;
+    st.ms_chol = ev_ms(ctx, EV_COV, GDCA_EV_POTRF);   // blocked Cholesky factorisation
+    st.ms_inv = ev_ms(ctx, GDCA_EV_POTRF, EV_CHOL);   // trtri + lauum + mirror
     st.ms_score = ev_ms(ctx, EV_CHOL, EV_SCORE);
     st.ms_apc = ev_ms(ctx, EV_SCORE, EV_APC);
     st.ms_rank = ev_ms(ctx, EV_APC, EV_RANK);

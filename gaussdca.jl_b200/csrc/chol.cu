@@ -455,6 +455,7 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
     }
   }
   if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));
+  if (ctx->ev[GDCA_EV_POTRF]) GDCA_CUDA(ctx, cudaEventRecord(ctx->ev[GDCA_EV_POTRF], sA));
 
   // ---------------- trtri by recursive doubling ----------------
   for (int h = 1; h < nb; h *= 2) {

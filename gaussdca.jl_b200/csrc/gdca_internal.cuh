@@ -12,6 +12,7 @@
 #define GDCA_MAX_PLANES 5      // q <= 31  ->  5 bit planes
 #define GDCA_NB 128            // Cholesky / GEMM block
 #define GDCA_MAX_PEERS 16
+#define GDCA_EV_POTRF 15        // ctx->ev[15]: recorded by chol.cu between the factorisation and the inversion
 
 struct gdca_ctx {
   int device = 0;

@@ -61,7 +61,7 @@ typedef struct {
   uint64_t ident_sum;   /* sum_{k<l} #identical positions (only when theta == :auto)                 */
   int32_t theta_passes; /* M x M pair sweeps executed (1, or 0 when theta == 0)                     */
   int32_t reserved;
-  /* device milliseconds per stage, CUDA events on the library's stream */
+  /* device milliseconds per stage, CUDA events on the library's stream (ms_chol: factorisation, ms_inv: inversion) */
   float ms_h2d, ms_pack, ms_theta, ms_weights, ms_cov, ms_chol, ms_inv, ms_score, ms_apc, ms_rank, ms_d2h, ms_total;
 } gdca_stats_t;
 
