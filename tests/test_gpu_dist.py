@@ -21,19 +21,20 @@ rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = pkg.Context(local)
-L, M = 64, 30000
-Z = np.empty((M, L), dtype=np.int8)
-ctx.check(ctx.lib.gdca_synth_alignment(ctx.h, ptr(Z), L, M, 77))
 out = {}
-for theta, score in (("auto", "frob"), (0.25, "DI")):
+# second shape is larger: the library's buffers move, the peer mappings must be re-exchanged transparently
+for (L, M, theta, score) in ((64, 30000, "auto", "frob"), (64, 30000, 0.25, "DI"), (96, 41000, "auto", "frob")):
+    Z = np.empty((M, L), dtype=np.int8)
+    ctx.check(ctx.lib.gdca_synth_alignment(ctx.h, ptr(Z), L, M, 77))
     R, info = gd.gdca_sharded(Z, 0.8, theta, score, 5, ctx=ctx)
     if rank == 0:
-        ctx.check(ctx.lib.gdca_set_shard(ctx.h, 0, 1))
-        R1, st = pkg.gdca_from_alignment(Z, 0.8, theta, score, 5, ctx=ctx, return_stats=True, as_array=True)
+        # single-GPU fused run on a SEPARATE context (rank 0's sharded context keeps its peer mappings)
+        ctx1 = globals().setdefault("_ctx1", pkg.Context(local))
+        R1, st = pkg.gdca_from_alignment(Z, 0.8, theta, score, 5, ctx=ctx1, return_stats=True, as_array=True)
         same_keys = bool(np.array_equal(R["i"], R1["i"]) and np.array_equal(R["j"], R1["j"]))
-        out[f"{theta}-{score}"] = dict(same_keys=same_keys, max_abs=float(np.max(np.abs(R["score"] - R1["score"]))),
-                                       thresh=(info["thresh"], st["thresh"]), meff=(info["meff"], st["meff"]),
-                                       passes=info["passes"])
+        out[f"{L}x{M}-{theta}-{score}"] = dict(same_keys=same_keys, max_abs=float(np.max(np.abs(R["score"] - R1["score"]))),
+                                               thresh=(info["thresh"], st["thresh"]), meff=(info["meff"], st["meff"]),
+                                               passes=info["passes"])
     dist.barrier()
 if rank == 0:
     print("RESULT " + json.dumps(out))
@@ -60,4 +61,4 @@ def test_nccl_sharded_equals_single_gpu(tmp_path):
         assert v["same_keys"], (k, v)            # identical ranking order
         assert v["max_abs"] == 0.0, (k, v)       # bit-identical scores: integer exchange + sums with zeros
         assert v["thresh"][0] == v["thresh"][1] and v["meff"][0] == v["meff"][1]
-    assert out["auto-frob"]["passes"] == 1
+    assert len(out) == 3 and out["64x30000-auto-frob"]["passes"] == 1
