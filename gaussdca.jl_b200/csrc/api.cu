@@ -75,9 +75,9 @@ int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
   set_shape(ctx, L, M, q);
   // buffers that peers have mapped are about to move: drop the mappings (the host re-exchanges handles)
   if (ctx->peers_ready && ((size_t)3 * ctx->Mpad > ctx->capCounts || (size_t)ctx->npad * ctx->npad > ctx->capC)) peer_close_all(ctx);
-  GDCA_TRY(gdca_k_pack(ctx));
   ctx->have_alignment = true;
   ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  GDCA_TRY(gdca_k_pack(ctx));  // builds the per-site lists first (site order), then the bit planes
   return GDCA_OK;
 }
 
@@ -234,7 +234,7 @@ void gdca_destroy(gdca_ctx *ctx) {
     if (m) cudaIpcCloseMemHandle(m);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (!ctx->dZ_borrowed) cudaFree(ctx->dZ);
-  void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
+  void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPerm, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR};
   for (void *b : bufs)

@@ -35,6 +35,7 @@ struct gdca_ctx {
   int8_t *dZt = nullptr; size_t capZt = 0;     // [L][M] site-major copy (list building)
   uint8_t *dZq = nullptr; size_t capZq = 0;    // [M][roundup(L,256)] recoded + permuted copy (covariance)
   uint32_t *dPlanes = nullptr; size_t capPlanes = 0;  // [nwords][nplanes][Mpad]
+  int32_t *dPerm = nullptr; size_t capPerm = 0;       // [L] packed position -> site (most variable sites first)
   int32_t *dCounts = nullptr; size_t capCounts = 0;   // [3][Mpad]
   unsigned long long *dHam = nullptr;          // [2] sum of hamming distances, pairs visited
   int *dQ = nullptr;                           // [1] max(Z)

@@ -445,3 +445,22 @@ def test_resident_run_equals_host_run_and_context_reuse(pkg, orc, ctx):
                                             glib.SCORE_CODES[score], 5, glib.ptr(R), n_out, ctypes.byref(st)))
         assert np.array_equal(R, R_host)          # same kernels, same order: bit-identical
         assert st.theta_passes == 1 and st.ms_total > 0
+
+
+def test_site_reordering_keeps_counts_exact_on_pfam_like_columns(pkg, orc, ctx):
+    """Conserved and gap-heavy columns are packed last (earlier early exit); counts must not change."""
+    rng = np.random.default_rng(9)
+    L, M = 150, 4000
+    Z = orc.synth_alignment(L, M, seed=12)
+    cons = rng.choice(L, size=60, replace=False)          # 40 % of the columns conserved / gappy
+    for c in cons[:30]:
+        Z[:, c] = np.where(rng.random(M) < 0.97, Z[0, c], Z[:, c])
+    for c in cons[30:]:
+        Z[:, c] = np.where(rng.random(M) < 0.9, 21, Z[:, c])
+    Z[0, 0] = 21
+    for theta in ("auto", 0.2, 0.45):
+        tho = orc.compute_theta(Z) if theta == "auto" else theta
+        counts, W, Meff, thresh = orc.compute_weights(Z, tho)
+        w = pkg.compute_weights(Z, theta, ctx=ctx, full=True)
+        assert w["theta"] == tho and w["thresh"] == thresh
+        assert np.array_equal(w["counts"], counts) and w["Meff"] == Meff
