@@ -15,7 +15,7 @@ ncu --set full --clock-control none --import-source on \
 ncu --set full --clock-control none --import-source on -k regex:"diag_block_kernel" -c 1 \
     -o gpurun_out/top_b python tools/dev_gpu.py 500x200000 > gpurun_out/ncu_top_b.log 2>&1
 # the last dgemm launches of one run: trailing NT updates, the trtri levels, the lauum GEMM
-ncu --set full --clock-control none --import-source on -k regex:"dgemm_kernel" -s 170 -c 25 \
+ncu --set full --clock-control none --import-source on -k regex:"dgemm_kernel" -s 186 -c 9 \
     -o gpurun_out/top_c python tools/dev_gpu.py 500x200000 > gpurun_out/ncu_top_c.log 2>&1
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err
 ls -la gpurun_out
