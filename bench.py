@@ -50,7 +50,7 @@ def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
     of the same workload (profiles/r1_traffic.json, made by tools/summarise_profiles.py)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
         return (t["dram_bytes_read"] or 0) + (t["dram_bytes_write"] or 0)
     except Exception:
         return None
@@ -339,27 +339,55 @@ def main():
         t_pair = sum(tk) / len(tk) / 1e3
         hs = np.zeros(2, dtype=np.uint64)
         ctx.check(lib.gdca_dev_copy_to_host(ctx.h, glib.ptr(hs), lib.gdca_dev_ham_sum_ptr(ctx.h), 16))
-        pair_words = int(hs[1])                       # (pair, 32-site word) units really executed
+        filt, f_tiles, s_blocks = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
+        f_tflop, ms_f, ms_x = ctypes.c_double(), ctypes.c_float(), ctypes.c_float()
+        ctx.check(lib.gdca_dev_sweep_info(ctx.h, ctypes.byref(filt), ctypes.byref(f_tiles), ctypes.byref(f_tflop),
+                                          ctypes.byref(s_blocks), ctypes.byref(ms_f), ctypes.byref(ms_x)))
+        pair_words = int(hs[1])                       # (pair, 32-site word) units really executed by the exact sweep
         npairs = M * (M - 1) // 2 // world            # this rank's shard of the sweep
         nwords = (L + 31) // 32
         alu_ops = pair_words * 5                      # executed ALU-pipe work: 5 LOP3 per pair-word
-        full_ops = npairs * nwords * 5                # a sweep without the early exit
-        hbm_bytes = 4 * nwords * 5 * ((M + 127) // 128 * 128) + 4 * M   # packed planes once + counts
-        roof = {
-            "kernel": "pair_sweep_kernel<5,1> (neighbour counts, exact early exit)" + ("" if world == 1 else f", shard {rank} of {world}"),
-            "bound": "int32_alu",
-            "achieved": alu_ops / t_pair / 1e12, "peak": lop3.value, "unit": "Tlop3/s",
-            "frac": (alu_ops / t_pair / 1e12) / lop3.value,
+        full_ops = npairs * nwords * 5                # a sweep without filter and early exit
+        Mpad = (M + 127) // 128 * 128
+        hbm_bytes = 4 * nwords * 5 * Mpad + 4 * M     # packed planes once + counts
+        t_exact = (ms_x.value / 1e3) if filt.value else t_pair
+        exact = {
+            "kernel": "pair_sweep_kernel<5,1> (exact neighbour counts, per-warp early exit)",
+            "bound": "int32_alu", "achieved": alu_ops / t_exact / 1e12, "peak": lop3.value, "unit": "Tlop3/s",
+            "frac": (alu_ops / t_exact / 1e12) / lop3.value, "ms_per_launch": t_exact * 1e3,
+            "blocks_swept": int(s_blocks.value), "blocks_total": (Mpad // 128) * (Mpad // 128 + 1) // 2 // world,
             "peak_source": "measured live: gdca_probe_peaks LOP3 issue rate (MEASURED_PEAKS.json has no INT32 figure)",
-            "ms_per_launch": t_pair * 1e3, "pairs_per_s": npairs / t_pair,
             "executed_fraction_of_full_sweep": alu_ops / full_ops,
+        }
+        common = {
+            "sweep_ms": t_pair * 1e3, "pairs_per_s": npairs / t_pair,
             "effective_tlop3_per_s_full_sweep_equivalent": full_ops / t_pair / 1e12,
-            "traffic": ncu_traffic("pair_sweep_kernel<5, 1>") if world == 1 and args.workload == "C" else None,
             "hbm": {"achieved": hbm_bytes / t_pair / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
                     "frac": hbm_bytes / t_pair / 1e9 / pk["hbm_gbs"] if pk.get("hbm_gbs") else None,
-                    "note": "compulsory bytes only; the sweep is ALU-bound, operands live in L2"},
+                    "note": "compulsory bytes only; the sweep is compute-bound, operands live in L2"},
             "survey_floor_ops_per_pair": 5 * ((L + 5) // 6),
         }
+        if filt.value:
+            # dominant kernel: the tcgen05 prefilter.  algorithmic flop = 2 * 128 * 256 * Kpad per tile x tiles launched
+            fp8_peak = 2.0 * pk["bf16_tflops"] if pk.get("bf16_tflops") else 4500.0
+            t_f = ms_f.value / 1e3
+            Kpad = (3 * L + 127) // 128 * 128
+            roof = {
+                "kernel": "tc_filter_kernel (tcgen05 kind::f8f6f4 128x256x32, TMA ring, TMEM epilogue)"
+                          + ("" if world == 1 else f", shard {rank} of {world}"),
+                "bound": "tensor", "achieved": f_tflop.value / t_f, "peak": fp8_peak, "unit": "TFLOP/s",
+                "frac": f_tflop.value / t_f / fp8_peak,
+                "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst): FP8 tensor rate = 2 x BF16 on sm_100; "
+                                "MEASURED_PEAKS.json carries no FP8 figure" if pk.get("bf16_tflops") else
+                                "nominal dense FP8 (B200_PROFILING.md fallback)"),
+                "ms_per_launch": t_f * 1e3, "tiles": int(f_tiles.value), "flop_per_tile": 2 * 128 * 256 * Kpad,
+                "l2_operand_bytes_per_launch": int(f_tiles.value) * (128 + 256) * Kpad,
+                "traffic": ncu_traffic("tc_filter_kernel") if world == 1 and args.workload == "C" else None,
+                "exact_sweep": exact, **common,
+            }
+        else:
+            roof = {**exact, "traffic": ncu_traffic("pair_sweep_kernel<5, 1>") if world == 1 and args.workload == "C" else None,
+                    **common}
         ctx.check(lib.gdca_set_shard(ctx.h, 0, 1))
         n = 20 * L
         t_cov, t_chol = stage_acc.get("ms_cov", 0) / 1e3, (stage_acc.get("ms_chol", 0) + stage_acc.get("ms_inv", 0)) / 1e3

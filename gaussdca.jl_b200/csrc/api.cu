@@ -6,6 +6,8 @@
 
 #include <new>
 
+#include <stdlib.h>
+
 #include "gdca_internal.cuh"
 
 static thread_local std::string g_create_error;
@@ -77,6 +79,7 @@ int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
   if (ctx->peers_ready && ((size_t)3 * ctx->Mpad > ctx->capCounts || (size_t)ctx->npad * ctx->npad > ctx->capC)) peer_close_all(ctx);
   ctx->have_alignment = true;
   ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  ctx->have_V = false;
   GDCA_TRY(gdca_k_pack(ctx));  // builds the per-site lists first (site order), then the bit planes
   return GDCA_OK;
 }
@@ -223,6 +226,14 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   for (int i = 0; i < EV_COUNT; ++i)
     if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreate(&ctx->ev[GDCA_EV_POTRF])) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreate(&ctx->ev_sweep0)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreate(&ctx->ev_filter)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreate(&ctx->ev_sweep1)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dNItems, sizeof(int))) != cudaSuccess) return fail(e);
+  if (const char *env = getenv("GDCA_TC_FILTER")) {
+    const int m = atoi(env);
+    if (m >= 0 && m <= 2) ctx->tc_filter_mode = m;
+  }
   *out = ctx;
   return GDCA_OK;
 }
@@ -236,11 +247,14 @@ void gdca_destroy(gdca_ctx *ctx) {
   if (!ctx->dZ_borrowed) cudaFree(ctx->dZ);
   void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPerm, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
-                  ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR};
+                  ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
+                  ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : {ctx->ev_sweep0, ctx->ev_filter, ctx->ev_sweep1})
+    if (e) cudaEventDestroy(e);
   if (ctx->ev_fact) cudaEventDestroy(ctx->ev_fact);
   if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -328,6 +342,69 @@ int32_t gdca_dev_pair_pass(gdca_ctx *ctx, int32_t mode, int64_t thresh) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   GDCA_TRY(set_device(ctx));
   return gdca_k_pair_pass(ctx, mode, (int)thresh, 1);
+}
+
+int32_t gdca_set_tc_filter(gdca_ctx *ctx, int32_t mode) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (mode < 0 || mode > 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_tc_filter: mode must be 0, 1 or 2");
+  ctx->tc_filter_mode = mode;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_tc_filter(gdca_ctx *ctx, int64_t thresh, uint8_t *flags_host, float *S_host, int64_t ld) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!flags_host) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "tc_filter: flags_host is NULL");
+  GDCA_TRY(set_device(ctx));
+  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "tc_filter: no alignment loaded");
+  const int64_t T = ctx->Mpad / GDCA_TILE, rows = ((T + 1) / 2) * 256;
+  float *dS = nullptr;
+  if (S_host) {
+    if (ld < rows) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "tc_filter: ld must be >= ceil(T/2)*256");
+    GDCA_CUDA(ctx, cudaMalloc((void **)&dS, (size_t)rows * ld * sizeof(float)));
+    GDCA_CUDA(ctx, cudaMemsetAsync(dS, 0, (size_t)rows * ld * sizeof(float), ctx->stream));
+  }
+  int32_t st = gdca_k_tc_filter(ctx, (int)thresh, dS, ld);
+  if (st == GDCA_OK) {
+    cudaError_t e = cudaMemcpyAsync(flags_host, ctx->dFlags, (size_t)(T * T), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && dS)
+      e = cudaMemcpyAsync(S_host, dS, (size_t)rows * ld * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("tc_filter: ") + cudaGetErrorString(e);
+      st = GDCA_ERR_CUDA;
+    }
+  }
+  if (dS) cudaFree(dS);
+  return st;
+}
+
+int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
+                            int64_t *swept_blocks, float *ms_filter, float *ms_exact) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const bool f = ctx->last_sweep_filtered;
+  if (filtered) *filtered = f ? 1 : 0;
+  if (filter_tiles) *filter_tiles = f ? ctx->tc_filter_tiles : 0;
+  if (filter_tflop) *filter_tflop = f ? ctx->tc_filter_tflop : 0.0;
+  const int64_t T = ctx->Mpad / GDCA_TILE;
+  int64_t blocks = T * (T + 1) / 2 / ctx->shard_world;
+  if (f) {
+    int nit = 0;
+    GDCA_CUDA(ctx, cudaMemcpy(&nit, ctx->dNItems, sizeof(int), cudaMemcpyDeviceToHost));
+    blocks = nit;
+  }
+  if (swept_blocks) *swept_blocks = blocks;
+  float a = 0.f, b = 0.f;
+  if (f) {
+    if (cudaEventElapsedTime(&a, ctx->ev_sweep0, ctx->ev_filter) != cudaSuccess) cudaGetLastError(), a = 0.f;
+    if (cudaEventElapsedTime(&b, ctx->ev_filter, ctx->ev_sweep1) != cudaSuccess) cudaGetLastError(), b = 0.f;
+  } else {
+    if (cudaEventElapsedTime(&b, ctx->ev_sweep0, ctx->ev_sweep1) != cudaSuccess) cudaGetLastError(), b = 0.f;
+  }
+  if (ms_filter) *ms_filter = a;
+  if (ms_exact) *ms_exact = b;
+  return GDCA_OK;
 }
 
 int32_t gdca_dev_pair_sample(gdca_ctx *ctx, int32_t stride) {

@@ -57,6 +57,18 @@ struct gdca_ctx {
   uint32_t *dVals = nullptr; size_t capVals = 0;
   gdca_rank_t *dR = nullptr; size_t capR = 0;
 
+  // ---- tensor-core prefilter of the neighbour-count sweep (tcfilter.cu) ----
+  uint8_t *dV = nullptr; size_t capV = 0;          // [ceil(T/2)*256][roundup(3L,128)] e4m3 simplex code of the state classes
+  uint8_t *dFlags = nullptr; size_t capFlags = 0;  // [T][T] blocks the filter could not clear
+  int2 *dItems = nullptr; size_t capItems = 0;     // compacted (bi, bj) list of flagged blocks
+  int *dNItems = nullptr;                          // [1] its length
+  bool have_V = false;
+  int tc_filter_mode = 1;                          // 0 off, 1 auto (large M), 2 always (tests)
+  bool last_sweep_filtered = false;
+  double tc_filter_tflop = 0.0;                    // flop of the last filter launch on this rank, in 1e12
+  long long tc_filter_tiles = 0;
+  cudaEvent_t ev_sweep0 = nullptr, ev_filter = nullptr, ev_sweep1 = nullptr;  // filter / exact sweep split
+
   // ---- peer memory (one process per GPU): IPC-mapped counts / C buffers of the other ranks ----
   bool peers_ready = false;
   int32_t *peer_counts[GDCA_MAX_PEERS] = {};   // [r] -> rank r's dCounts (own rank: dCounts)
@@ -119,6 +131,11 @@ static inline int32_t gdca_fail(gdca_ctx *ctx, int32_t status, const char *msg) 
 int32_t gdca_k_maxq(gdca_ctx *ctx);                       // pack.cu: dQ <- max(Z)
 int32_t gdca_k_pack(gdca_ctx *ctx);                       // pack.cu: dZ -> dPlanes
 int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride);   // pairs.cu
+int32_t gdca_k_tc_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld);  // tcfilter.cu
+static inline bool gdca_tc_filter_wanted(const gdca_ctx *ctx) {
+  // auto: the filter pays once the sweep is more than a few tiles per SM
+  return ctx->tc_filter_mode == 2 || (ctx->tc_filter_mode == 1 && ctx->M >= 16384);
+}
 int32_t gdca_k_finish_weights(gdca_ctx *ctx, int which);  // weights.cu
 int32_t gdca_k_build_lists(gdca_ctx *ctx);                // cov.cu: per-site lists of sequence ids grouped by state
 int32_t gdca_k_ident_sum(gdca_ctx *ctx, unsigned long long *ident_out);  // cov.cu: sum_{k<l} ident from site histograms

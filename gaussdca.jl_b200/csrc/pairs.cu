@@ -70,6 +70,8 @@ struct PairParams {
   long long Mpad, M;
   int nwords, nchunks, T;
   long long n_items;   // T(T+1)/2
+  const int2 *items;      // optional: explicit list of (bi, bj) blocks (tensor-core prefilter, tcfilter.cu) ...
+  const int *n_items_dev; // ... and its length, known only on the device
   int rank, world;
   int thresh;
   int32_t *counts[GDCA_MAX_PEERS];  // [3][Mpad] of every rank that must see the hits (fused all-reduce over peer memory)
@@ -102,7 +104,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
 
   // items of this CTA: local index it -> global item (blockIdx.x + it*gridDim.x)*world + rank
   const long long my_first = (long long)blockIdx.x;
-  const long long per_rank_items = (P.n_items - P.rank + P.world - 1) / P.world;  // items t with t%world==rank
+  const long long n_items = P.items ? (long long)*P.n_items_dev : P.n_items;
+  auto tile_of = [&](long long t, int &bi, int &bj) {
+    if (P.items) {
+      const int2 v = P.items[t];
+      bi = v.x;
+      bj = v.y;
+    } else {
+      item_to_tile(t, P.T, bi, bj);
+    }
+  };
+  const long long per_rank_items = (n_items - P.rank + P.world - 1) / P.world;  // items t with t%world==rank
   long long n_my = 0;
   if (my_first < per_rank_items) n_my = (per_rank_items - my_first + gridDim.x - 1) / gridDim.x;
   const long long n_flat = n_my * P.nchunks;
@@ -126,7 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
   // flat pipeline position of the loader: tile coordinates are advanced incrementally
   long long ld_f = 0;
   int ld_c = 0, ld_bi = 0, ld_bj = 0;
-  if (n_flat > 0) item_to_tile(my_first * P.world + P.rank, P.T, ld_bi, ld_bj);
+  if (n_flat > 0) tile_of(my_first * P.world + P.rank, ld_bi, ld_bj);
   const long long item_step = (long long)gridDim.x * P.world;
 
   auto issue_load = [&]() {
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
         ld_c = 0;
         if (ld_f < n_flat) {
           const long long it = ld_f / P.nchunks;
-          item_to_tile((my_first + it * gridDim.x) * P.world + P.rank, P.T, ld_bi, ld_bj);
+          tile_of((my_first + it * gridDim.x) * P.world + P.rank, ld_bi, ld_bj);
         }
       }
     }
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
       const long long t = (my_first + cur_it * gridDim.x) * P.world + P.rank;
       ++cur_it;
       int bi, bj;
-      item_to_tile(t, P.T, bi, bj);
+      tile_of(t, bi, bj);
       const bool diag = (bi == bj);
       const int hi_thresh = (MODE == 2) ? P.thresh + 1 : P.thresh;
       unsigned tile_ham = 0, tile_pairs = 0, any = 0;
@@ -393,6 +405,14 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dHam, 0, 2 * sizeof(unsigned long long), ctx->stream));
   if (sample_stride < 1) sample_stride = 1;
 
+  // production sweep: clear whole blocks on the tensor cores first, sweep only what is left (exact, tcfilter.cu)
+  const bool filtered = mode == 1 && sample_stride == 1 && gdca_tc_filter_wanted(ctx);
+  if (mode == 1) GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_sweep0, ctx->stream));
+  if (filtered) {
+    GDCA_TRY(gdca_k_tc_filter(ctx, thresh, nullptr, 0));
+    GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_filter, ctx->stream));
+  }
+
   PairParams P;
   P.planes = ctx->dPlanes;
   P.Mpad = ctx->Mpad;
@@ -404,6 +424,15 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
   // a sampled sweep visits every sample_stride-th item of this shard: items t = rank (mod world*stride)
   P.rank = ctx->shard_rank;
   P.world = ctx->shard_world * sample_stride;
+  P.items = nullptr;
+  P.n_items_dev = nullptr;
+  if (filtered) {  // the list is already this rank's share
+    P.items = ctx->dItems;
+    P.n_items_dev = ctx->dNItems;
+    P.rank = 0;
+    P.world = 1;
+  }
+  ctx->last_sweep_filtered = filtered;
   P.thresh = thresh;
   if (ctx->peers_ready && ctx->shard_world > 1) {
     P.npeers = ctx->shard_world;
@@ -413,11 +442,14 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
     P.counts[0] = ctx->dCounts;
   }
   P.ham_sum = ctx->dHam;
+  int32_t st;
   switch (ctx->nplanes) {
-    case 1: return launch_pairs<1>(ctx, mode, P);
-    case 2: return launch_pairs<2>(ctx, mode, P);
-    case 3: return launch_pairs<3>(ctx, mode, P);
-    case 4: return launch_pairs<4>(ctx, mode, P);
-    default: return launch_pairs<5>(ctx, mode, P);
+    case 1: st = launch_pairs<1>(ctx, mode, P); break;
+    case 2: st = launch_pairs<2>(ctx, mode, P); break;
+    case 3: st = launch_pairs<3>(ctx, mode, P); break;
+    case 4: st = launch_pairs<4>(ctx, mode, P); break;
+    default: st = launch_pairs<5>(ctx, mode, P); break;
   }
+  if (st == GDCA_OK && mode == 1) GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_sweep1, ctx->stream));
+  return st;
 }

@@ -1,0 +1,407 @@
+// tcfilter.cu -- K3a: tensor-core prefilter of the neighbour-count sweep (tcgen05 / TMEM / TMA, sm_100a).
+//
+// Part of the replacement of DCAUtils compute_weights (un-vendored; reference call site src/GaussDCA.jl:28):
+//   count[k] = 1 + #{l != k : hamming(k,l) < thresh}.
+// On real and synthetic alignments almost every pair is far beyond thresh.  This kernel PROVES that for whole
+// 128 x 128 blocks of sequence pairs on the tensor cores, and only the blocks it cannot clear go to the exact
+// bit-plane sweep (pairs.cu).  The result is unchanged by construction:
+//
+//   * every residue state is mapped to one of 4 classes (state & 3) and each class to a vertex of the regular
+//     simplex in {-1,+1}^3:  c0=(+,+,+) c1=(+,-,-) c2=(-,+,-) c3=(-,-,+);  v_a . v_b = 3 if a == b else -1.
+//   * for two sequences  S = sum_i v(Z_ik) . v(Z_il) = 4 * ident_proj - L,  ident_proj = #sites with equal CLASS
+//     >= ident (equal states have equal classes), so  hamming_proj = (3L - S) / 4  <=  hamming.
+//   * a pair with hamming_proj >= thresh cannot be a neighbour.  A block is cleared iff that holds for all its
+//     pairs, i.e. iff max S <= 3L - 4 thresh.  S is an exact integer (|S| <= 3L < 2^24, FP32 accumulation of
+//     +-1 products), so the test is exact and conservative: flagged blocks are a superset of the blocks that
+//     contain a neighbour pair; the sweep counts exactly in those.
+//
+// The M x M x 3L contraction runs as  V V^T  with V = [Mpad][Kpad] e4m3 (+-1.0, 0 padding), K-major:
+//   * one persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected
+//     lane), warps 2..5 = epilogue (one TMEM lane quarter each);
+//   * CTA tile 128 x 256 (UMMA M=128, N=256, K=32 per instruction, kind::f8f6f4, FP32 accumulators in TMEM),
+//     K streamed in 128-byte blocks through a 4-stage TMA ring (SWIZZLE_128B, 48 KB per stage), full/empty
+//     mbarriers, tcgen05.commit releases the stages;
+//   * two TMEM accumulator stages (2 x 256 columns = all of TMEM): the epilogue of tile t (tcgen05.ld, max over
+//     the block, one vote, one byte store) overlaps the MMAs of tile t+1.  No C matrix is ever written.
+//   * only tiles that touch the upper triangle (column block >= row block) are visited; tiles are dealt
+//     round-robin over (CTA, rank) for the multi-GPU sweep.
+#include <cuda.h>  // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through the runtime)
+
+#include "gdca_internal.cuh"
+
+namespace {
+
+constexpr int BM = 128;              // tile rows (sequences)
+constexpr int BN = 256;              // tile columns (sequences)
+constexpr int BK = 128;              // K bytes per stage (= SWIZZLE_128B atom width)
+constexpr int UK = 32;               // K per tcgen05.mma for 8-bit operands
+constexpr int NSTAGE = 4;
+constexpr int A_BYTES = BM * BK;     // 16 KB
+constexpr int B_BYTES = BN * BK;     // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr size_t TC_SMEM = (size_t)NSTAGE * STAGE_BYTES + 1024 /*alignment slack*/;
+
+// kind::f8f6f4 instruction descriptor (cute::UMMA::InstrDescriptor layout): D=F32, A=B=E4M3, both K-major,
+// N=256 (>>3 at bit 17), M=128 (>>4 at bit 24)
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct FilterParams {
+  int T, T2, KB;
+  int rank, world;
+  float bound;          // block is flagged iff max S > bound,  bound = 3L - 4 thresh
+  uint8_t *flags;       // [T][T], 1 = block (bi, bj) must be swept exactly
+  float *dump;          // tests only: S of every visited tile, [T2*256... rows][dump_ld]
+  long long dump_ld;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major; CUTLASS writes 1)
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+
+// 32 consecutive FP32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Tiles are enumerated by super-rows r = 0..T2-1 (two 128-row blocks each): super-row r holds 2 (T2 - r) tiles,
+// tile u of it is (bi = 2r + (u & 1), bj2 = r + (u >> 1)); consecutive tiles share their B operand.
+struct TileIter {
+  int T, T2, r;
+  long long u;
+  __device__ void start(int T_, int T2_, long long first) {
+    T = T_;
+    T2 = T2_;
+    r = 0;
+    u = 0;
+    advance(first);
+  }
+  __device__ void advance(long long d) {
+    u += d;
+    while (r < T2 && u >= 2ll * (T2 - r)) {
+      u -= 2ll * (T2 - r);
+      ++r;
+    }
+  }
+  __device__ bool done() const { return r >= T2; }
+  __device__ int bi() const { return 2 * r + (int)(u & 1); }
+  __device__ int bj2() const { return r + (int)(u >> 1); }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const __grid_constant__ CUtensorMap tmap, FilterParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bars[2 * NSTAGE + 4];
+  __shared__ uint32_t s_tmem;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B operands need 1024-byte alignment
+  const uint32_t bars = smem_u32(s_bars);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
+  const uint32_t tmem_slot = smem_u32(&s_tmem);
+  volatile uint32_t *tmem_slot_ptr = &s_tmem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const long long first = (long long)blockIdx.x * P.world + P.rank;
+  const long long step = (long long)gridDim.x * P.world;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      TileIter it;
+      long long kq = 0;  // k-block counter over the whole kernel -> ring slot and phase
+      for (it.start(P.T, P.T2, first); !it.done(); it.advance(step)) {
+        const int bi = it.bi(), bj2 = it.bj2();
+        if (bi >= P.T) continue;
+        for (int kb = 0; kb < P.KB; ++kb, ++kq) {
+          const int s = (int)(kq % NSTAGE);
+          const uint32_t ph = (uint32_t)((kq / NSTAGE) & 1);
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const uint32_t sa = base + s * STAGE_BYTES;
+          tma_load_2d(sa, &tmap, full_bar(s), kb * BK, bi * BM);
+          tma_load_2d(sa + A_BYTES, &tmap, full_bar(s), kb * BK, bj2 * BN);
+          tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap, full_bar(s), kb * BK, bj2 * BN + BN / 2);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      TileIter it;
+      long long kq = 0, n = 0;
+      for (it.start(P.T, P.T2, first); !it.done(); it.advance(step)) {
+        if (it.bi() >= P.T) continue;
+        const int as = (int)(n & 1);
+        const uint32_t aph = (uint32_t)((n >> 1) & 1);
+        ++n;
+        mbar_wait(tempty_bar(as), aph ^ 1u);  // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < P.KB; ++kb, ++kq) {
+          const int s = (int)(kq % NSTAGE);
+          const uint32_t ph = (uint32_t)((kq / NSTAGE) & 1);
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the address field
+            umma_f8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (uint32_t)((kb | k) != 0));
+          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(tfull_bar(as));  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: 4 warps, warp w owns TMEM lanes 32 (w & 3) .. +31 = tile rows =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    TileIter it;
+    long long n = 0;
+    for (it.start(P.T, P.T2, first); !it.done(); it.advance(step)) {
+      const int bi = it.bi(), bj2 = it.bj2();
+      if (bi >= P.T) continue;
+      const int as = (int)(n & 1);
+      const uint32_t aph = (uint32_t)((n >> 1) & 1);
+      ++n;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float mx = -3.0e38f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)(half * 128 + c * 32), v);
+          tmem_ld_wait();
+          if (P.dump) {
+            float *d = P.dump + ((long long)bi * BM + row) * P.dump_ld + (long long)bj2 * BN + half * 128 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
+        const int cb = 2 * bj2 + half;
+        const bool hit = __any_sync(0xffffffffu, mx > P.bound);
+        if (hit && lane == 0 && cb >= bi && cb < P.T) P.flags[(long long)bi * P.T + cb] = 1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// V[k][3 i + j] = simplex coordinate j of class (Z[i,k] & 3), as e4m3 (+1.0 = 0x38, -1.0 = 0xB8); zero padding
+__global__ void encode_simplex_kernel(const int8_t *__restrict__ Z, long long L, long long M, long long VM, long long Kpad,
+                                      uint32_t *__restrict__ V) {
+  const long long words_per_row = Kpad / 4;
+  const long long total = VM * words_per_row;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long k = t / words_per_row;
+    const int w = (int)(t - k * words_per_row);
+    uint32_t out = 0;
+    if (k < M) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int b = 4 * w + e;
+        const int site = b / 3, j = b - 3 * site;
+        if (site < L) {
+          const int c = (int)Z[k * L + site] & 3;
+          const bool neg = (c != 0) && (j != c - 1);
+          out |= (neg ? 0xB8u : 0x38u) << (8 * e);
+        }
+      }
+    }
+    V[t] = out;
+  }
+}
+
+// flags [T][T] -> list of blocks (bi <= bj) for the exact sweep
+__global__ void compact_flags_kernel(const uint8_t *__restrict__ flags, int T, int2 *__restrict__ items, int *__restrict__ n_items) {
+  const long long total = (long long)T * T;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    if (flags[t]) {
+      const int bi = (int)(t / T), bj = (int)(t - (long long)bi * T);
+      if (bj >= bi) items[atomicAdd(n_items, 1)] = make_int2(bi, bj);
+    }
+  }
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int32_t make_tensor_map(gdca_ctx *ctx, CUtensorMap *map, void *V, long long VM, long long Kpad) {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GDCA_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess)
+      return gdca_fail(ctx, GDCA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    fn = (encode_tiled_fn)p;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)VM};
+  const cuuint64_t gstride[1] = {(cuuint64_t)Kpad};  // bytes between rows
+  const cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, V, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[96];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    ctx->err = b;
+    return GDCA_ERR_CUDA;
+  }
+  return GDCA_OK;
+}
+
+}  // namespace
+
+// Flags the 128 x 128 blocks (bi <= bj, this rank's share of the tiles) that may contain a pair with
+// hamming < thresh and compacts them into ctx->dItems / ctx->dNItems.  dump (device, optional): S of every tile.
+int32_t gdca_k_tc_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
+  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "tc_filter: no alignment loaded");
+  const long long T = ctx->Mpad / GDCA_TILE;
+  const long long T2 = (T + 1) / 2;
+  const long long VM = T2 * BN;
+  const long long Kpad = ((3 * ctx->L + BK - 1) / BK) * BK;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dV, ctx->capV, (size_t)(VM * Kpad)));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dFlags, ctx->capFlags, (size_t)(T * T)));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dItems, ctx->capItems, (size_t)(T * (T + 1) / 2)));
+
+  if (!ctx->have_V) {
+    const long long words = VM * Kpad / 4;
+    const int grid = (int)((words + 255) / 256 < (long long)ctx->num_sms * 16 ? (words + 255) / 256 : (long long)ctx->num_sms * 16);
+    encode_simplex_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dZ, ctx->L, ctx->M, VM, Kpad, reinterpret_cast<uint32_t *>(ctx->dV));
+    GDCA_LAUNCH_CHECK(ctx);
+    ctx->have_V = true;
+  }
+  CUtensorMap map;
+  GDCA_TRY(make_tensor_map(ctx, &map, ctx->dV, VM, Kpad));
+
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dFlags, 0, (size_t)(T * T), ctx->stream));
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dNItems, 0, sizeof(int), ctx->stream));
+
+  FilterParams P;
+  P.T = (int)T;
+  P.T2 = (int)T2;
+  P.KB = (int)(Kpad / BK);
+  P.rank = ctx->shard_rank;
+  P.world = ctx->shard_world;
+  P.bound = (float)(3 * ctx->L - 4 * (long long)thresh);
+  P.flags = ctx->dFlags;
+  P.dump = dump;
+  P.dump_ld = dump_ld;
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  tc_filter_kernel<<<ctx->num_sms, TC_THREADS, TC_SMEM, ctx->stream>>>(map, P);
+  GDCA_LAUNCH_CHECK(ctx);
+
+  const long long tt = T * T;
+  const int cgrid = (int)((tt + 255) / 256 < (long long)ctx->num_sms * 8 ? (tt + 255) / 256 : (long long)ctx->num_sms * 8);
+  compact_flags_kernel<<<cgrid, 256, 0, ctx->stream>>>(ctx->dFlags, (int)T, ctx->dItems, ctx->dNItems);
+  GDCA_LAUNCH_CHECK(ctx);
+  // tiles visited (host arithmetic; the kernel skips bi >= T), dealt evenly over the ranks
+  long long tiles = 0;
+  for (long long r = 0; r < T2; ++r) tiles += (2 * r + 1 < T ? 2 : 1) * (T2 - r);
+  ctx->tc_filter_tiles = tiles / ctx->shard_world;
+  ctx->tc_filter_tflop = 2.0 * (double)BM * BN * (double)Kpad * 1e-12 * (double)tiles / (double)ctx->shard_world;
+  return GDCA_OK;
+}
