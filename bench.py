@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -340,9 +340,9 @@ def main():
         hs = np.zeros(2, dtype=np.uint64)
         ctx.check(lib.gdca_dev_copy_to_host(ctx.h, glib.ptr(hs), lib.gdca_dev_ham_sum_ptr(ctx.h), 16))
         filt, f_tiles, s_blocks = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
-        f_tflop, ms_f, ms_x = ctypes.c_double(), ctypes.c_float(), ctypes.c_float()
+        f_tflop, ms_f, ms_x, f_l2 = ctypes.c_double(), ctypes.c_float(), ctypes.c_float(), ctypes.c_double()
         ctx.check(lib.gdca_dev_sweep_info(ctx.h, ctypes.byref(filt), ctypes.byref(f_tiles), ctypes.byref(f_tflop),
-                                          ctypes.byref(s_blocks), ctypes.byref(ms_f), ctypes.byref(ms_x)))
+                                          ctypes.byref(s_blocks), ctypes.byref(ms_f), ctypes.byref(ms_x), ctypes.byref(f_l2)))
         pair_words = int(hs[1])                       # (pair, 32-site word) units really executed by the exact sweep
         npairs = M * (M - 1) // 2 // world            # this rank's shard of the sweep
         nwords = (L + 31) // 32
@@ -368,21 +368,27 @@ def main():
             "survey_floor_ops_per_pair": 5 * ((L + 5) // 6),
         }
         if filt.value:
-            # dominant kernel: the tcgen05 prefilter.  algorithmic flop = 2 * 128 * 256 * Kpad per tile x tiles launched
-            fp8_peak = 2.0 * pk["bf16_tflops"] if pk.get("bf16_tflops") else 4500.0
+            # dominant kernel of the sweep: the tcgen05 prefilter.  algorithmic flop = 2 * 128 * BN * Kpad per tile x tiles
+            fp4 = filt.value == 4
+            bf16 = pk.get("bf16_tflops")
+            tc_peak = 9000.0 if fp4 else 4500.0     # nominal dense FP4 / FP8 (B200_PROFILING.md table)
+            scaled = (4.0 if fp4 else 2.0) * bf16 if bf16 else None
             t_f = ms_f.value / 1e3
-            Kpad = (3 * L + 127) // 128 * 128
             roof = {
-                "kernel": "tc_filter_kernel (tcgen05 kind::f8f6f4 128x256x32, TMA ring, TMEM epilogue)"
+                "kernel": ("tc_filter_kernel<fp4> (tcgen05 kind::mxf4.block_scale 128x224x64" if fp4 else
+                           "tc_filter_kernel<fp8> (tcgen05 kind::f8f6f4 128x256x32") + ", TMA ring, TMEM epilogue)"
                           + ("" if world == 1 else f", shard {rank} of {world}"),
-                "bound": "tensor", "achieved": f_tflop.value / t_f, "peak": fp8_peak, "unit": "TFLOP/s",
-                "frac": f_tflop.value / t_f / fp8_peak,
-                "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (burst): FP8 tensor rate = 2 x BF16 on sm_100; "
-                                "MEASURED_PEAKS.json carries no FP8 figure" if pk.get("bf16_tflops") else
-                                "nominal dense FP8 (B200_PROFILING.md fallback)"),
-                "ms_per_launch": t_f * 1e3, "tiles": int(f_tiles.value), "flop_per_tile": 2 * 128 * 256 * Kpad,
-                "l2_operand_bytes_per_launch": int(f_tiles.value) * (128 + 256) * Kpad,
-                "traffic": ncu_traffic("tc_filter_kernel") if world == 1 and args.workload == "C" else None,
+                "bound": "tensor", "achieved": f_tflop.value / t_f, "peak": tc_peak, "unit": "TFLOP/s",
+                "frac": f_tflop.value / t_f / tc_peak,
+                "peak_source": ("nominal dense " + ("FP4" if fp4 else "FP8") + " tensor rate of the B200_PROFILING.md table: "
+                                "MEASURED_PEAKS.json measures bf16 only"),
+                "frac_of_measured_bf16_scaled": (f_tflop.value / t_f / scaled) if scaled else None,
+                "measured_bf16_scaled_note": (f"{4 if fp4 else 2} x MEASURED_PEAKS.json bf16_tflops (burst) = {scaled:.0f} TFLOP/s"
+                                              if scaled else None),
+                "ms_per_launch": t_f * 1e3, "tiles": int(f_tiles.value), "flop_per_launch": f_tflop.value * 1e12,
+                "l2_operand_bytes_per_launch": f_l2.value,
+                "l2_operand_tb_per_s": f_l2.value / t_f / 1e12,
+                "traffic": ncu_traffic("tc_filter_kernel<1>" if fp4 else "tc_filter_kernel<0>") if world == 1 and args.workload == "C" else None,
                 "exact_sweep": exact, **common,
             }
         else:
@@ -413,8 +419,8 @@ def main():
         "config": {"workload": f"synthetic L={L} M={M} theta=auto score={score} pseudocount={pc} min_separation=5 "
                                f"(BASELINE.json configs[{'BCD'.find(args.workload) + 1}])",
                    "seed": SEED, "generator": "SURVEY 8(d) clustered SplitMix64", "l2": "256 MiB flush write between steps",
-                   "sharding": ("single GPU" if world == 1 else f"pair tiles + covariance rows over {world} ranks, "
-                                "NCCL all-reduce(int32 counts)/reduce(f64 C); inverse+scores on rank 0")},
+                   "sharding": ("single GPU" if world == 1 else f"pair-matrix row blocks + covariance rows over {world} ranks, "
+                                "exchange fused into the kernels over CUDA-IPC peer memory; inverse+scores on rank 0")},
         "theta": stats["theta"] if world == 1 else None, "thresh": stats["thresh"] if world == 1 else None,
         "meff": stats["meff"] if world == 1 else None, "top_pair": top,
         "e2e": e2e, "gpu_launches": int(launches2 - launches1),

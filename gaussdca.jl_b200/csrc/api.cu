@@ -79,7 +79,7 @@ int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
   if (ctx->peers_ready && ((size_t)3 * ctx->Mpad > ctx->capCounts || (size_t)ctx->npad * ctx->npad > ctx->capC)) peer_close_all(ctx);
   ctx->have_alignment = true;
   ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
-  ctx->have_V = false;
+  ctx->have_V = 0;
   GDCA_TRY(gdca_k_pack(ctx));  // builds the per-site lists first (site order), then the bit planes
   return GDCA_OK;
 }
@@ -234,6 +234,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
     const int m = atoi(env);
     if (m >= 0 && m <= 2) ctx->tc_filter_mode = m;
   }
+  if (const char *env = getenv("GDCA_TC_FILTER_BITS")) ctx->tc_filter_fp4 = atoi(env) != 8;
   *out = ctx;
   return GDCA_OK;
 }
@@ -248,7 +249,7 @@ void gdca_destroy(gdca_ctx *ctx) {
   void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPerm, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
-                  ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems};
+                  ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)
@@ -351,21 +352,28 @@ int32_t gdca_set_tc_filter(gdca_ctx *ctx, int32_t mode) {
   return GDCA_OK;
 }
 
-int32_t gdca_dev_tc_filter(gdca_ctx *ctx, int64_t thresh, uint8_t *flags_host, float *S_host, int64_t ld) {
+int32_t gdca_set_tc_filter_bits(gdca_ctx *ctx, int32_t bits) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (bits != 4 && bits != 8) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_tc_filter_bits: bits must be 4 or 8");
+  ctx->tc_filter_fp4 = bits == 4;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_tc_filter(gdca_ctx *ctx, int64_t thresh, uint32_t *flags_host, float *S_host, int64_t ld) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   if (!flags_host) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "tc_filter: flags_host is NULL");
   GDCA_TRY(set_device(ctx));
   if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "tc_filter: no alignment loaded");
-  const int64_t T = ctx->Mpad / GDCA_TILE, rows = ((T + 1) / 2) * 256;
+  const int64_t T = ctx->Mpad / GDCA_TILE, rows = T * GDCA_TILE;
   float *dS = nullptr;
   if (S_host) {
-    if (ld < rows) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "tc_filter: ld must be >= ceil(T/2)*256");
+    if (ld < rows + 256) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "tc_filter: ld must be >= 128*T + 256");
     GDCA_CUDA(ctx, cudaMalloc((void **)&dS, (size_t)rows * ld * sizeof(float)));
     GDCA_CUDA(ctx, cudaMemsetAsync(dS, 0, (size_t)rows * ld * sizeof(float), ctx->stream));
   }
   int32_t st = gdca_k_tc_filter(ctx, (int)thresh, dS, ld);
   if (st == GDCA_OK) {
-    cudaError_t e = cudaMemcpyAsync(flags_host, ctx->dFlags, (size_t)(T * T), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(flags_host, ctx->dFlags, (size_t)(T * T) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && dS)
       e = cudaMemcpyAsync(S_host, dS, (size_t)rows * ld * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -379,7 +387,7 @@ int32_t gdca_dev_tc_filter(gdca_ctx *ctx, int64_t thresh, uint8_t *flags_host, f
 }
 
 int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
-                            int64_t *swept_blocks, float *ms_filter, float *ms_exact) {
+                            int64_t *swept_blocks, float *ms_filter, float *ms_exact, double *filter_l2_bytes) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   GDCA_TRY(set_device(ctx));
   GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -387,6 +395,8 @@ int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_ti
   if (filtered) *filtered = f ? 1 : 0;
   if (filter_tiles) *filter_tiles = f ? ctx->tc_filter_tiles : 0;
   if (filter_tflop) *filter_tflop = f ? ctx->tc_filter_tflop : 0.0;
+  if (filter_l2_bytes) *filter_l2_bytes = f ? ctx->tc_filter_l2_bytes : 0.0;
+  if (filtered && f) *filtered = ctx->tc_filter_fp4 ? 4 : 8;
   const int64_t T = ctx->Mpad / GDCA_TILE;
   int64_t blocks = T * (T + 1) / 2 / ctx->shard_world;
   if (f) {

@@ -58,14 +58,17 @@ struct gdca_ctx {
   gdca_rank_t *dR = nullptr; size_t capR = 0;
 
   // ---- tensor-core prefilter of the neighbour-count sweep (tcfilter.cu) ----
-  uint8_t *dV = nullptr; size_t capV = 0;          // [ceil(T/2)*256][roundup(3L,128)] e4m3 simplex code of the state classes
-  uint8_t *dFlags = nullptr; size_t capFlags = 0;  // [T][T] blocks the filter could not clear
-  int2 *dItems = nullptr; size_t capItems = 0;     // compacted (bi, bj) list of flagged blocks
+  uint8_t *dV = nullptr; size_t capV = 0;          // [rows][k-blocks*128 B] simplex code of the state classes, e4m3 or packed e2m1
+  uint32_t *dFlags = nullptr; size_t capFlags = 0; // [T][T] 16-bit masks of the 32x32 cells the filter could not clear
+  int2 *dItems = nullptr; size_t capItems = 0;     // compacted (bi, bj) list of blocks with a non-empty mask
+  uint32_t *dItemMask = nullptr; size_t capItemMask = 0;  // their masks
   int *dNItems = nullptr;                          // [1] its length
-  bool have_V = false;
+  int have_V = 0;                                  // 0: dV stale; 8 / 4: dV holds the FP8 / FP4 encoding of the loaded alignment
   int tc_filter_mode = 1;                          // 0 off, 1 auto (large M), 2 always (tests)
+  bool tc_filter_fp4 = true;                       // operand type of the filter: e4m3 (kind::f8f6f4) or e2m1 (kind::mxf4)
   bool last_sweep_filtered = false;
   double tc_filter_tflop = 0.0;                    // flop of the last filter launch on this rank, in 1e12
+  double tc_filter_l2_bytes = 0.0;                 // operand bytes its TMA loads moved
   long long tc_filter_tiles = 0;
   cudaEvent_t ev_sweep0 = nullptr, ev_filter = nullptr, ev_sweep1 = nullptr;  // filter / exact sweep split
 

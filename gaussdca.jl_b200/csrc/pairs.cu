@@ -72,6 +72,7 @@ struct PairParams {
   long long n_items;   // T(T+1)/2
   const int2 *items;      // optional: explicit list of (bi, bj) blocks (tensor-core prefilter, tcfilter.cu) ...
   const int *n_items_dev; // ... and its length, known only on the device
+  const uint32_t *item_mask;  // ... and per block the 32x32 cells that may hold a neighbour pair (bit 4*(r/32) + c/32)
   int rank, world;
   int thresh;
   int32_t *counts[GDCA_MAX_PEERS];  // [3][Mpad] of every rank that must see the hits (fused all-reduce over peer memory)
@@ -184,12 +185,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
   int cur_c = 0;
   long long cur_it = 0;
   bool warp_done = false;  // MODE 1: this warp's sub-tile can no longer contain a neighbour pair
+  bool warp_skip = false;  // MODE 1 with cell masks: the prefilter cleared every cell this warp owns
+  // this warp owns rows 16 (warp >> 1) .. +15 and columns 32 (warp & 1) .. +31 and 64 + 32 (warp & 1) .. +31
+  const uint32_t my_cells = (1u << (4 * (warp >> 2) + (warp & 1))) | (1u << (4 * (warp >> 2) + 2 + (warp & 1)));
   unsigned long long words_done = 0;  // MODE 1: 32-site words this warp really processed (x 1024 pairs each)
   for (long long f = 0; f < n_flat; ++f) {
     cp_async_wait<0>();
     __syncthreads();  // stage f landed for everyone; everyone is done with stage f-1
     issue_load();     // prefetch stage f+1 into the slot freed by f-1 while f is being computed
 
+    if (MODE == 1 && cur_c == 0 && P.item_mask) {
+      warp_skip = (P.item_mask[(my_first + cur_it * gridDim.x) * P.world + P.rank] & my_cells) == 0;
+      warp_done = warp_skip;
+    }
     const uint32_t *A = smem + (size_t)(f % STAGES) * STAGE_WORDS;
     const uint32_t *B = A + OP_WORDS;
     const int wcount = min(WC, P.nwords - cur_c * WC);  // words really present in this stage
@@ -252,6 +260,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
       int bi, bj;
       tile_of(t, bi, bj);
       const bool diag = (bi == bj);
+      if (MODE == 1 && warp_skip) {  // nothing was accumulated: none of these pairs is a neighbour (proved by the prefilter)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = 0x7fffffffu;
+      }
       const int hi_thresh = (MODE == 2) ? P.thresh + 1 : P.thresh;
       unsigned tile_ham = 0, tile_pairs = 0, any = 0;
       const bool interior = !diag && ((long long)(bj + 1) * TILE <= P.M);  // bi < bj: rows are in range too
@@ -426,9 +440,11 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
   P.world = ctx->shard_world * sample_stride;
   P.items = nullptr;
   P.n_items_dev = nullptr;
+  P.item_mask = nullptr;
   if (filtered) {  // the list is already this rank's share
     P.items = ctx->dItems;
     P.n_items_dev = ctx->dNItems;
+    P.item_mask = ctx->dItemMask;
     P.rank = 0;
     P.world = 1;
   }

@@ -18,13 +18,17 @@
 // The M x M x 3L contraction runs as  V V^T  with V = [Mpad][Kpad] e4m3 (+-1.0, 0 padding), K-major:
 //   * one persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected
 //     lane), warps 2..5 = epilogue (one TMEM lane quarter each);
-//   * CTA tile 128 x 256 (UMMA M=128, N=256, K=32 per instruction, kind::f8f6f4, FP32 accumulators in TMEM),
-//     K streamed in 128-byte blocks through a 4-stage TMA ring (SWIZZLE_128B, 48 KB per stage), full/empty
-//     mbarriers, tcgen05.commit releases the stages;
-//   * two TMEM accumulator stages (2 x 256 columns = all of TMEM): the epilogue of tile t (tcgen05.ld, max over
-//     the block, one vote, one byte store) overlaps the MMAs of tile t+1.  No C matrix is ever written.
-//   * only tiles that touch the upper triangle (column block >= row block) are visited; tiles are dealt
-//     round-robin over (CTA, rank) for the multi-GPU sweep.
+//   * FP8 variant: CTA tile 128 x 256 (UMMA M=128, N=256, K=32, kind::f8f6f4), V = e4m3 +-1.0, two TMEM accumulator
+//     stages of 256 columns.  FP4 variant: CTA tile 128 x 224 (UMMA M=128, N=224, K=64, kind::mxf4.block_scale.block32,
+//     twice the tensor rate, half the operand bytes), V = packed e2m1 +-1.0, two accumulator stages of 224 columns +
+//     64 columns of UE8M0 scale factors that are all 1.0 (written once with tcgen05.st: every byte is 0x7F, so the
+//     scale-factor layout never matters).  Both: FP32 accumulators in TMEM, K streamed in 128-byte blocks through a
+//     4-stage TMA ring (SWIZZLE_128B), full/empty mbarriers, tcgen05.commit releases the stages;
+//   * the epilogue of tile t (tcgen05.ld, max per 32 x 32 cell, one vote and at most one atomicOr per cell) overlaps
+//     the MMAs of tile t+1.  No C matrix is ever written: the output is a 16-bit cell mask per 128 x 128 block.
+//   * only tiles that touch the upper triangle are visited, in bands of 16 row blocks with the row block varying
+//     fastest: the CTAs running at one time share a few column tiles, so V streams from HBM once per band and the
+//     operands come out of L2; multi-GPU: rank r owns the row blocks bi = r (mod world).
 #include <cuda.h>  // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through the runtime)
 
 #include "gdca_internal.cuh"
@@ -32,27 +36,35 @@
 namespace {
 
 constexpr int BM = 128;              // tile rows (sequences)
-constexpr int BN = 256;              // tile columns (sequences)
 constexpr int BK = 128;              // K bytes per stage (= SWIZZLE_128B atom width)
-constexpr int UK = 32;               // K per tcgen05.mma for 8-bit operands
-constexpr int NSTAGE = 4;
-constexpr int A_BYTES = BM * BK;     // 16 KB
-constexpr int B_BYTES = BN * BK;     // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int MAX_STAGE = 5;
 constexpr int TC_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr size_t TC_SMEM = (size_t)NSTAGE * STAGE_BYTES + 1024 /*alignment slack*/;
+constexpr int BAND = 16;             // row blocks per band of the tile order
 
-// kind::f8f6f4 instruction descriptor (cute::UMMA::InstrDescriptor layout): D=F32, A=B=E4M3, both K-major,
-// N=256 (>>3 at bit 17), M=128 (>>4 at bit 24)
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+template <bool FP4>
+struct Cfg {
+  static constexpr int BN = FP4 ? 224 : 256;        // tile columns (sequences)
+  static constexpr int A_BYTES = BM * BK;           // 16 KB
+  static constexpr int B_BYTES = BN * BK;           // 28 / 32 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = FP4 ? 5 : 4;        // 5 x 44 KB / 4 x 48 KB of operands in flight
+  static constexpr int SF_COL = 2 * BN;             // FP4: scale factors behind the two accumulator stages (448..511)
+  static constexpr size_t SMEM = (size_t)NSTAGE * STAGE_BYTES + 1024 /*alignment slack*/;
+  // instruction descriptors (cute::UMMA::InstrDescriptor / InstrDescriptorBlockScaled bit layout), both operands K-major:
+  //   f8f6f4:          D=F32 (bit 4), A=B=E4M3 (0), N>>3 at bit 17, M>>4 at bit 24
+  //   mxf4 block32:    A=B=E2M1 (1 at bits 7 and 10), scale format UE8M0 (bit 23), N>>3 at bit 17, M>>4 at bit 24, K=64
+  static constexpr uint32_t IDESC =
+      FP4 ? ((1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | (1u << 23) | ((uint32_t)(BM >> 4) << 24))
+          : ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24));
+};
 
 struct FilterParams {
-  int T, T2, KB;
+  int T, NT, NB, KB;    // 128-row blocks, column tiles, bands of this rank's rows, 128-byte k-blocks
   int rank, world;
-  float bound;          // block is flagged iff max S > bound,  bound = 3L - 4 thresh
-  uint8_t *flags;       // [T][T], 1 = block (bi, bj) must be swept exactly
-  float *dump;          // tests only: S of every visited tile, [T2*256... rows][dump_ld]
+  float bound;          // a 32 x 32 cell is flagged iff max S > bound,  bound = 3L - 4 thresh
+  uint32_t *flags;      // [T][T] cell masks: bit 4*(row/32) + (col/32) of block (bi, bj)
+  float *dump;          // tests only: S of every visited tile, [T*128][dump_ld]
   long long dump_ld;
 };
 
@@ -102,16 +114,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
       : "memory");
 }
 
-// 32 consecutive FP32 columns of this thread's TMEM lane
+// 32 consecutive 32-bit columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -124,34 +145,60 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same 32-bit word into 32 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st32_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// Tiles are enumerated by super-rows r = 0..T2-1 (two 128-row blocks each): super-row r holds 2 (T2 - r) tiles,
-// tile u of it is (bi = 2r + (u & 1), bj2 = r + (u >> 1)); consecutive tiles share their B operand.
+// Tile order: this rank owns the row blocks bi = rank + world * i; bands of BAND of ITS rows; inside band b the column
+// tile cj runs from the first one that reaches the band's diagonal to NT-1, and the row varies FASTEST -- so the ~148 tiles
+// in flight at one time use 16 A tiles and a few B tiles out of L2.  (row, cj) pairs of a band that lie wholly below the
+// diagonal are skipped (valid() == false).  Whole rows per rank: every 128 x 128 block is flagged by exactly one rank.
 struct TileIter {
-  int T, T2, r;
+  int T, NT, NB, colw, rank, world, b;
   long long u;
-  __device__ void start(int T_, int T2_, long long first) {
-    T = T_;
-    T2 = T2_;
-    r = 0;
-    u = 0;
-    advance(first);
-  }
+  __device__ int row_of(int i) const { return rank + world * i; }
+  __device__ int cmin() const { return (int)(((long long)BM * row_of(b * BAND)) / colw); }
+  __device__ long long band_tiles() const { return (long long)(NT - cmin()) * BAND; }
+  __device__ void start(const struct FilterParams &P, int colw_, long long first);
   __device__ void advance(long long d) {
     u += d;
-    while (r < T2 && u >= 2ll * (T2 - r)) {
-      u -= 2ll * (T2 - r);
-      ++r;
+    while (b < NB && u >= band_tiles()) {
+      u -= band_tiles();
+      ++b;
     }
   }
-  __device__ bool done() const { return r >= T2; }
-  __device__ int bi() const { return 2 * r + (int)(u & 1); }
-  __device__ int bj2() const { return r + (int)(u >> 1); }
+  __device__ bool done() const { return b >= NB; }
+  __device__ int bi() const { return row_of(b * BAND + (int)(u % BAND)); }
+  __device__ int cj() const { return cmin() + (int)(u / BAND); }
+  __device__ bool valid() const { return bi() < T && (long long)colw * (cj() + 1) > (long long)BM * bi(); }
 };
+__device__ void TileIter::start(const FilterParams &P, int colw_, long long first) {
+  T = P.T;
+  NT = P.NT;
+  NB = P.NB;
+  colw = colw_;
+  rank = P.rank;
+  world = P.world;
+  b = 0;
+  u = 0;
+  advance(first);
+}
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const __grid_constant__ CUtensorMap tmap, FilterParams P) {
+template <bool FP4>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_filter_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, FilterParams P) {
+  using C = Cfg<FP4>;
+  constexpr int BN = C::BN;
+  constexpr int NSTAGE = C::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * NSTAGE + 4];
+  __shared__ __align__(8) uint64_t s_bars[2 * MAX_STAGE + 4];
   __shared__ uint32_t s_tmem;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B operands need 1024-byte alignment
   const uint32_t bars = smem_u32(s_bars);
@@ -165,7 +212,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -186,26 +234,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const long long first = (long long)blockIdx.x * P.world + P.rank;
-  const long long step = (long long)gridDim.x * P.world;
+  if (FP4 && warp >= 2) {
+    // UE8M0 scale factors, all 2^0: every byte of the 64 scale columns of all 128 lanes is 0x7F
+    const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)C::SF_COL;
+    tmem_st32_fill(t, 0x7F7F7F7Fu);
+    tmem_st32_fill(t + 32u, 0x7F7F7F7Fu);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const long long first = (long long)blockIdx.x;
+  const long long step = (long long)gridDim.x;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       TileIter it;
       long long kq = 0;  // k-block counter over the whole kernel -> ring slot and phase
-      for (it.start(P.T, P.T2, first); !it.done(); it.advance(step)) {
-        const int bi = it.bi(), bj2 = it.bj2();
-        if (bi >= P.T) continue;
+      for (it.start(P, BN, first); !it.done(); it.advance(step)) {
+        if (!it.valid()) continue;
+        const int bi = it.bi(), cj = it.cj();
         for (int kb = 0; kb < P.KB; ++kb, ++kq) {
           const int s = (int)(kq % NSTAGE);
           const uint32_t ph = (uint32_t)((kq / NSTAGE) & 1);
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          const uint32_t sa = base + s * STAGE_BYTES;
-          tma_load_2d(sa, &tmap, full_bar(s), kb * BK, bi * BM);
-          tma_load_2d(sa + A_BYTES, &tmap, full_bar(s), kb * BK, bj2 * BN);
-          tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap, full_bar(s), kb * BK, bj2 * BN + BN / 2);
+          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+          const uint32_t sa = base + s * C::STAGE_BYTES;
+          tma_load_2d(sa, &tmapA, full_bar(s), kb * BK, bi * BM);
+          tma_load_2d(sa + C::A_BYTES, &tmapB, full_bar(s), kb * BK, cj * BN);
         }
       }
     }
@@ -215,8 +273,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const __grid_c
     if (lane == 0) {
       TileIter it;
       long long kq = 0, n = 0;
-      for (it.start(P.T, P.T2, first); !it.done(); it.advance(step)) {
-        if (it.bi() >= P.T) continue;
+      for (it.start(P, BN, first); !it.done(); it.advance(step)) {
+        if (!it.valid()) continue;
         const int as = (int)(n & 1);
         const uint32_t aph = (uint32_t)((n >> 1) & 1);
         ++n;
@@ -228,11 +286,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const __grid_c
           const uint32_t ph = (uint32_t)((kq / NSTAGE) & 1);
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = base + s * STAGE_BYTES;
-          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
+          const uint32_t sa = base + s * C::STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + C::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the address field
-            umma_f8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < 4; ++k) {  // 32 bytes along K per instruction (32 e4m3 / 64 e2m1) = +2 in the address field
+            if (FP4)
+              umma_mxf4(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), C::IDESC, (uint32_t)((kb | k) != 0),
+                        tmem_base + (uint32_t)C::SF_COL, tmem_base + (uint32_t)C::SF_COL + 32u);
+            else
+              umma_f8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), C::IDESC, (uint32_t)((kb | k) != 0));
+          }
           umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
         }
         umma_commit(tfull_bar(as));  // accumulator complete
@@ -245,34 +308,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const __grid_c
     const int row = quarter * 32 + lane;
     TileIter it;
     long long n = 0;
-    for (it.start(P.T, P.T2, first); !it.done(); it.advance(step)) {
-      const int bi = it.bi(), bj2 = it.bj2();
-      if (bi >= P.T) continue;
+    for (it.start(P, BN, first); !it.done(); it.advance(step)) {
+      if (!it.valid()) continue;
+      const int bi = it.bi(), cj = it.cj();
       const int as = (int)(n & 1);
       const uint32_t aph = (uint32_t)((n >> 1) & 1);
       ++n;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float mx = -3.0e38f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)(half * 128 + c * 32), v);
-          tmem_ld_wait();
-          if (P.dump) {
-            float *d = P.dump + ((long long)bi * BM + row) * P.dump_ld + (long long)bj2 * BN + half * 128 + c * 32;
+      // one 32 x 32 cell per warp and step (a software-pipelined tcgen05.ld measured no faster: the epilogue is hidden
+      // behind the MMAs of the next tile)
+      auto reduce_cell = [&](const uint32_t (&v)[32], int c) {
+        const long long col0 = (long long)cj * BN + c * 32;
+        if (P.dump) {
+          float *d = P.dump + ((long long)bi * BM + row) * P.dump_ld + col0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
         }
-        const int cb = 2 * bj2 + half;
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
         const bool hit = __any_sync(0xffffffffu, mx > P.bound);
-        if (hit && lane == 0 && cb >= bi && cb < P.T) P.flags[(long long)bi * P.T + cb] = 1;
+        const int cb = (int)(col0 >> 7);
+        if (hit && lane == 0 && cb >= bi && cb < P.T)
+          atomicOr(P.flags + (long long)bi * P.T + cb, 1u << (quarter * 4 + (int)((col0 >> 5) & 3)));
+      };
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        reduce_cell(v, c);
       }
       tc_fence_before();
       __syncwarp();
@@ -288,7 +355,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const __grid_c
   }
 }
 
-// V[k][3 i + j] = simplex coordinate j of class (Z[i,k] & 3), as e4m3 (+1.0 = 0x38, -1.0 = 0xB8); zero padding
+// simplex coordinate j of the class of state z: c0=(+,+,+) c1=(+,-,-) c2=(-,+,-) c3=(-,-,+)
+__device__ __forceinline__ bool simplex_neg(int z, int j) {
+  const int c = z & 3;
+  return (c != 0) && (j != c - 1);
+}
+
+// FP8: V[k][3 i + j] as e4m3 (+1.0 = 0x38, -1.0 = 0xB8), one byte per element; zero padding
 __global__ void encode_simplex_kernel(const int8_t *__restrict__ Z, long long L, long long M, long long VM, long long Kpad,
                                       uint32_t *__restrict__ V) {
   const long long words_per_row = Kpad / 4;
@@ -302,24 +375,47 @@ __global__ void encode_simplex_kernel(const int8_t *__restrict__ Z, long long L,
       for (int e = 0; e < 4; ++e) {
         const int b = 4 * w + e;
         const int site = b / 3, j = b - 3 * site;
-        if (site < L) {
-          const int c = (int)Z[k * L + site] & 3;
-          const bool neg = (c != 0) && (j != c - 1);
-          out |= (neg ? 0xB8u : 0x38u) << (8 * e);
-        }
+        if (site < L) out |= (simplex_neg((int)Z[k * L + site], j) ? 0xB8u : 0x38u) << (8 * e);
       }
     }
     V[t] = out;
   }
 }
 
-// flags [T][T] -> list of blocks (bi <= bj) for the exact sweep
-__global__ void compact_flags_kernel(const uint8_t *__restrict__ flags, int T, int2 *__restrict__ items, int *__restrict__ n_items) {
+// FP4: the same elements as packed e2m1 (+1.0 = 0x2, -1.0 = 0xA), element 2b in the low nibble of byte b; zero padding
+__global__ void encode_simplex4_kernel(const int8_t *__restrict__ Z, long long L, long long M, long long VM, long long Kbytes,
+                                       uint32_t *__restrict__ V) {
+  const long long words_per_row = Kbytes / 4;
+  const long long total = VM * words_per_row;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long k = t / words_per_row;
+    const int w = (int)(t - k * words_per_row);
+    uint32_t out = 0;
+    if (k < M) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int b = 8 * w + e;
+        const int site = b / 3, j = b - 3 * site;
+        if (site < L) out |= (simplex_neg((int)Z[k * L + site], j) ? 0xAu : 0x2u) << (4 * e);
+      }
+    }
+    V[t] = out;
+  }
+}
+
+// cell masks [T][T] -> list of blocks (bi <= bj) with their masks for the exact sweep
+__global__ void compact_flags_kernel(const uint32_t *__restrict__ flags, int T, int2 *__restrict__ items,
+                                     uint32_t *__restrict__ masks, int *__restrict__ n_items) {
   const long long total = (long long)T * T;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    if (flags[t]) {
+    const uint32_t m = flags[t];
+    if (m) {
       const int bi = (int)(t / T), bj = (int)(t - (long long)bi * T);
-      if (bj >= bi) items[atomicAdd(n_items, 1)] = make_int2(bi, bj);
+      if (bj >= bi) {
+        const int slot = atomicAdd(n_items, 1);
+        items[slot] = make_int2(bi, bj);
+        masks[slot] = m;
+      }
     }
   }
 }
@@ -328,7 +424,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int32_t make_tensor_map(gdca_ctx *ctx, CUtensorMap *map, void *V, long long VM, long long Kpad) {
+int32_t make_tensor_map(gdca_ctx *ctx, CUtensorMap *map, void *V, long long VM, long long Kbytes, int box_rows) {
   static encode_tiled_fn fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -338,9 +434,9 @@ int32_t make_tensor_map(gdca_ctx *ctx, CUtensorMap *map, void *V, long long VM, 
       return gdca_fail(ctx, GDCA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     fn = (encode_tiled_fn)p;
   }
-  const cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)VM};
-  const cuuint64_t gstride[1] = {(cuuint64_t)Kpad};  // bytes between rows
-  const cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
+  const cuuint64_t gdim[2] = {(cuuint64_t)Kbytes, (cuuint64_t)VM};
+  const cuuint64_t gstride[1] = {(cuuint64_t)Kbytes};  // bytes between rows
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, V, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -353,55 +449,73 @@ int32_t make_tensor_map(gdca_ctx *ctx, CUtensorMap *map, void *V, long long VM, 
   return GDCA_OK;
 }
 
-}  // namespace
-
-// Flags the 128 x 128 blocks (bi <= bj, this rank's share of the tiles) that may contain a pair with
-// hamming < thresh and compacts them into ctx->dItems / ctx->dNItems.  dump (device, optional): S of every tile.
-int32_t gdca_k_tc_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
-  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "tc_filter: no alignment loaded");
+template <bool FP4>
+int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
+  using C = Cfg<FP4>;
   const long long T = ctx->Mpad / GDCA_TILE;
-  const long long T2 = (T + 1) / 2;
-  const long long VM = T2 * BN;
-  const long long Kpad = ((3 * ctx->L + BK - 1) / BK) * BK;
-  GDCA_TRY(gdca_reserve(ctx, ctx->dV, ctx->capV, (size_t)(VM * Kpad)));
+  const long long NT = (T * BM + C::BN - 1) / C::BN;
+  const long long world = ctx->shard_world, rank = ctx->shard_rank;
+  const long long my_rows = T > rank ? (T - rank + world - 1) / world : 0;   // row blocks bi = rank + world * i < T
+  const long long NB = (my_rows + BAND - 1) / BAND;
+  const long long VM = NT * C::BN > T * BM ? NT * C::BN : T * BM;
+  const long long Kel = 3 * ctx->L;                                             // elements per row
+  const long long Kbytes = (((FP4 ? (Kel + 1) / 2 : Kel) + BK - 1) / BK) * BK;  // bytes per row, whole k-blocks
+  GDCA_TRY(gdca_reserve(ctx, ctx->dV, ctx->capV, (size_t)(VM * Kbytes)));
   GDCA_TRY(gdca_reserve(ctx, ctx->dFlags, ctx->capFlags, (size_t)(T * T)));
   GDCA_TRY(gdca_reserve(ctx, ctx->dItems, ctx->capItems, (size_t)(T * (T + 1) / 2)));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dItemMask, ctx->capItemMask, (size_t)(T * (T + 1) / 2)));
 
-  if (!ctx->have_V) {
-    const long long words = VM * Kpad / 4;
+  if (ctx->have_V != (FP4 ? 4 : 8)) {
+    const long long words = VM * Kbytes / 4;
     const int grid = (int)((words + 255) / 256 < (long long)ctx->num_sms * 16 ? (words + 255) / 256 : (long long)ctx->num_sms * 16);
-    encode_simplex_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dZ, ctx->L, ctx->M, VM, Kpad, reinterpret_cast<uint32_t *>(ctx->dV));
+    if (FP4)
+      encode_simplex4_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dZ, ctx->L, ctx->M, VM, Kbytes, reinterpret_cast<uint32_t *>(ctx->dV));
+    else
+      encode_simplex_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dZ, ctx->L, ctx->M, VM, Kbytes, reinterpret_cast<uint32_t *>(ctx->dV));
     GDCA_LAUNCH_CHECK(ctx);
-    ctx->have_V = true;
+    ctx->have_V = FP4 ? 4 : 8;
   }
-  CUtensorMap map;
-  GDCA_TRY(make_tensor_map(ctx, &map, ctx->dV, VM, Kpad));
+  CUtensorMap mapA, mapB;
+  GDCA_TRY(make_tensor_map(ctx, &mapA, ctx->dV, VM, Kbytes, BM));
+  GDCA_TRY(make_tensor_map(ctx, &mapB, ctx->dV, VM, Kbytes, C::BN));
 
-  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dFlags, 0, (size_t)(T * T), ctx->stream));
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dFlags, 0, (size_t)(T * T) * sizeof(uint32_t), ctx->stream));
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dNItems, 0, sizeof(int), ctx->stream));
 
   FilterParams P;
   P.T = (int)T;
-  P.T2 = (int)T2;
-  P.KB = (int)(Kpad / BK);
+  P.NT = (int)NT;
+  P.NB = (int)NB;
+  P.KB = (int)(Kbytes / BK);
   P.rank = ctx->shard_rank;
   P.world = ctx->shard_world;
   P.bound = (float)(3 * ctx->L - 4 * (long long)thresh);
   P.flags = ctx->dFlags;
   P.dump = dump;
   P.dump_ld = dump_ld;
-  GDCA_CUDA(ctx, cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-  tc_filter_kernel<<<ctx->num_sms, TC_THREADS, TC_SMEM, ctx->stream>>>(map, P);
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(tc_filter_kernel<FP4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  tc_filter_kernel<FP4><<<ctx->num_sms, TC_THREADS, C::SMEM, ctx->stream>>>(mapA, mapB, P);
   GDCA_LAUNCH_CHECK(ctx);
 
   const long long tt = T * T;
   const int cgrid = (int)((tt + 255) / 256 < (long long)ctx->num_sms * 8 ? (tt + 255) / 256 : (long long)ctx->num_sms * 8);
-  compact_flags_kernel<<<cgrid, 256, 0, ctx->stream>>>(ctx->dFlags, (int)T, ctx->dItems, ctx->dNItems);
+  compact_flags_kernel<<<cgrid, 256, 0, ctx->stream>>>(ctx->dFlags, (int)T, ctx->dItems, ctx->dItemMask, ctx->dNItems);
   GDCA_LAUNCH_CHECK(ctx);
-  // tiles visited (host arithmetic; the kernel skips bi >= T), dealt evenly over the ranks
+  // tiles this rank visits (host arithmetic, same rule as TileIter::valid)
   long long tiles = 0;
-  for (long long r = 0; r < T2; ++r) tiles += (2 * r + 1 < T ? 2 : 1) * (T2 - r);
-  ctx->tc_filter_tiles = tiles / ctx->shard_world;
-  ctx->tc_filter_tflop = 2.0 * (double)BM * BN * (double)Kpad * 1e-12 * (double)tiles / (double)ctx->shard_world;
+  for (long long bi = rank; bi < T; bi += world) tiles += NT - (BM * bi) / C::BN;
+  ctx->tc_filter_tiles = tiles;
+  ctx->tc_filter_tflop = 2.0 * (double)BM * C::BN * (double)(Kbytes * (FP4 ? 2 : 1)) * 1e-12 * (double)tiles;
+  ctx->tc_filter_l2_bytes = (double)(BM + C::BN) * (double)Kbytes * (double)tiles;
   return GDCA_OK;
+}
+
+}  // namespace
+
+// Flags the 32 x 32 cells of the 128 x 128 blocks (bi <= bj, this rank's share of the tiles) that may contain a pair
+// with hamming < thresh and compacts the blocks with a non-empty mask into ctx->dItems / dItemMask / dNItems.
+// dump (device, optional): S of every visited tile.
+int32_t gdca_k_tc_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
+  if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "tc_filter: no alignment loaded");
+  return ctx->tc_filter_fp4 ? run_filter<true>(ctx, thresh, dump, dump_ld) : run_filter<false>(ctx, thresh, dump, dump_ld);
 }

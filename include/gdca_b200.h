@@ -122,19 +122,24 @@ int32_t gdca_dev_load_resident(gdca_ctx *ctx, const int8_t *Z_dev, int64_t L, in
  * mode 0: accumulate sum of hamming distances (theta :auto);  mode 1: neighbour counts for `thresh`;
  * mode 2: both in one sweep, counts for the three thresholds thresh-1, thresh, thresh+1 (speculative). */
 int32_t gdca_dev_pair_pass(gdca_ctx *ctx, int32_t mode, int64_t thresh);
-/* Tensor-core prefilter of the mode-1 sweep (csrc/tcfilter.cu): whole 128 x 128 blocks of sequence pairs are proved
- * neighbour-free by a tcgen05 FP8 contraction of a 4-class projection of the alignment (a lower bound of the hamming
- * distance), only the remaining blocks go through the exact bit-plane sweep.  Counts are identical in every mode.
- * mode 0: off; 1: auto (default; on for M >= 16384; env GDCA_TC_FILTER overrides the default); 2: always. */
+/* Tensor-core prefilter of the mode-1 sweep (csrc/tcfilter.cu): 32 x 32 cells of sequence pairs are proved
+ * neighbour-free by a tcgen05 contraction of a 4-class projection of the alignment (a lower bound of the hamming
+ * distance); only the 128 x 128 blocks with a cell left go through the exact bit-plane sweep, and only the warps of
+ * that sweep that own such a cell do any work.  Counts are identical in every mode.
+ * mode 0: off; 1: auto (default; on for M >= 16384; env GDCA_TC_FILTER overrides the default); 2: always.
+ * bits 4 (default): packed e2m1 operands, kind::mxf4 with unit block scales; 8: e4m3 operands, kind::f8f6f4
+ * (env GDCA_TC_FILTER_BITS overrides the default). */
 int32_t gdca_set_tc_filter(gdca_ctx *ctx, int32_t mode);
-/* Test hook: run only the prefilter for `thresh` on the loaded alignment.  flags_host: [T*T] bytes, T = ceil(M/128),
- * 1 = block (bi, bj), bi <= bj, must be swept.  S_host (optional): the projected score 4*ident_proj - L of every
- * visited tile, [ceil(T/2)*256][ld] floats (blocks of the lower triangle that no tile covers are left untouched). */
-int32_t gdca_dev_tc_filter(gdca_ctx *ctx, int64_t thresh, uint8_t *flags_host, float *S_host, int64_t ld);
-/* What the last mode-1 sweep did: *filtered 1 if the prefilter ran; 128x256 filter tiles and their flop (1e12);
- * 128x128 blocks that went through the exact sweep; device ms of the two parts. */
+int32_t gdca_set_tc_filter_bits(gdca_ctx *ctx, int32_t bits);
+/* Test hook: run only the prefilter for `thresh` on the loaded alignment.  flags_host: [T*T] uint32, T = ceil(M/128);
+ * bit 4*(r/32) + (c/32) of entry (bi, bj), bi <= bj, is set iff the 32 x 32 cell at rows r.., columns c.. of that
+ * block must be swept.  S_host (optional): the projected score 4*ident_proj - L of every visited tile,
+ * [128*T][ld] floats, ld >= 128*T + 256 (parts of the lower triangle that no tile covers are left at 0). */
+int32_t gdca_dev_tc_filter(gdca_ctx *ctx, int64_t thresh, uint32_t *flags_host, float *S_host, int64_t ld);
+/* What the last mode-1 sweep did: *filtered = 0, or the operand bits (8 / 4) of the prefilter that ran; its tiles,
+ * flop (1e12) and TMA operand bytes; 128x128 blocks that went through the exact sweep; device ms of the two parts. */
 int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
-                            int64_t *swept_blocks, float *ms_filter, float *ms_exact);
+                            int64_t *swept_blocks, float *ms_filter, float *ms_exact, double *filter_l2_bytes);
 /* mode-0 sweep over every stride-th tile of this shard (cheap estimate of the mean identity). */
 int32_t gdca_dev_pair_sample(gdca_ctx *ctx, int32_t stride);
 /* partial results of this shard, device pointers: u64[2] {hamming sum, pairs visited} (after a mode-1 sweep

@@ -20,21 +20,31 @@ def projected_scores(Z):
     return 4 * ident - L
 
 
+BITS = [8, 4]   # e4m3 operands (kind::f8f6f4) and packed e2m1 operands (kind::mxf4, unit block scales)
+
+
+@pytest.fixture(params=BITS, ids=["fp8", "fp4"])
+def bits(request, ctx):
+    ctx.check(ctx.lib.gdca_set_tc_filter_bits(ctx.h, request.param))
+    yield request.param
+    ctx.check(ctx.lib.gdca_set_tc_filter_bits(ctx.h, 4))
+
+
 def run_filter(ctx, Z, thresh, want_scores=True):
     from gaussdca_jl_b200._lib import ptr
     lib = ctx.lib
     M, L = Z.shape
     ctx.check(lib.gdca_dev_load(ctx.h, ptr(Z), L, M))
     T = (M + 127) // 128
-    rows = ((T + 1) // 2) * 256
-    flags = np.zeros(T * T, dtype=np.uint8)
-    S = np.zeros((rows, rows), dtype=np.float32) if want_scores else None
-    ctx.check(lib.gdca_dev_tc_filter(ctx.h, thresh, ptr(flags), ptr(S) if want_scores else None, rows))
+    ld = T * 128 + 256
+    flags = np.zeros(T * T, dtype=np.uint32)
+    S = np.zeros((T * 128, ld), dtype=np.float32) if want_scores else None
+    ctx.check(lib.gdca_dev_tc_filter(ctx.h, thresh, ptr(flags), ptr(S) if want_scores else None, ld))
     return flags.reshape(T, T), S, T
 
 
 @pytest.mark.parametrize("L,M", [(53, 300), (128, 512), (200, 1000), (43, 129), (500, 700), (342, 1500)])
-def test_filter_scores_and_flags_are_exact(orc, ctx, L, M):
+def test_filter_scores_and_flags_are_exact(orc, ctx, bits, L, M):
     Z = orc.synth_alignment(L, M, seed=11 + L + M)
     thresh = int(0.4 * L)
     flags, S, T = run_filter(ctx, Z, thresh)
@@ -44,15 +54,20 @@ def test_filter_scores_and_flags_are_exact(orc, ctx, L, M):
         for bj in range(bi, T):
             r0, r1, c0, c1 = bi * 128, min(M, bi * 128 + 128), bj * 128, min(M, bj * 128 + 128)
             got = S[r0:r1, c0:c1]
-            assert np.array_equal(got, want[r0:r1, c0:c1].astype(np.float32)), (bi, bj)
+            assert np.array_equal(got, want[r0:r1, c0:c1].astype(np.float32)), (bits, bi, bj)
             # padding rows / columns are all-zero vectors: S = 0 there
             blk = np.zeros((128, 128))
             blk[: r1 - r0, : c1 - c0] = want[r0:r1, c0:c1]
-            assert flags[bi, bj] == (1 if blk.max() > bound else 0), (bi, bj)
+            mask = 0
+            for cr in range(4):
+                for cc in range(4):
+                    if blk[32 * cr:32 * cr + 32, 32 * cc:32 * cc + 32].max() > bound:
+                        mask |= 1 << (4 * cr + cc)
+            assert flags[bi, bj] == mask, (bits, bi, bj, hex(int(flags[bi, bj])), hex(mask))
     assert not np.any(np.tril(flags, -1))
 
 
-def test_flagged_blocks_cover_every_neighbour_pair(orc, ctx):
+def test_flagged_blocks_cover_every_neighbour_pair(orc, ctx, bits):
     rng = np.random.default_rng(5)
     L, M = 160, 2000
     Z = orc.synth_alignment(L, M, seed=99)
@@ -64,15 +79,15 @@ def test_flagged_blocks_cover_every_neighbour_pair(orc, ctx):
             ham += np.rint(X @ X.T).astype(np.int64)
         ham = L - ham
         nb = ham < thresh
-        for bi in range(T):
-            for bj in range(bi, T):
-                if nb[bi * 128:(bi + 1) * 128, bj * 128:(bj + 1) * 128].any():
-                    assert flags[bi, bj] == 1, (thresh, bi, bj)
+        rr, cc = np.nonzero(np.triu(nb, 1))              # every neighbour pair lies in a flagged cell
+        bit = 4 * ((rr % 128) // 32) + (cc % 128) // 32
+        ok = (flags[rr // 128, cc // 128].astype(np.int64) >> bit) & 1
+        assert ok.all(), (thresh, int((ok == 0).sum()))
     del rng
 
 
 @pytest.mark.parametrize("L,M", [(53, 300), (200, 1000), (97, 2500), (150, 6000)])
-def test_counts_identical_with_and_without_filter(pkg, orc, ctx, L, M):
+def test_counts_identical_with_and_without_filter(pkg, orc, ctx, bits, L, M):
     Z = orc.synth_alignment(L, M, seed=1 + L + M)
     lib = ctx.lib
     try:
@@ -84,8 +99,8 @@ def test_counts_identical_with_and_without_filter(pkg, orc, ctx, L, M):
             ctx.check(lib.gdca_set_tc_filter(ctx.h, 2))
             w2 = pkg.compute_weights(Z, theta, ctx=ctx, full=True)
             filt = ctypes.c_int32()
-            ctx.check(lib.gdca_dev_sweep_info(ctx.h, ctypes.byref(filt), None, None, None, None, None))
-            assert filt.value == 1
+            ctx.check(lib.gdca_dev_sweep_info(ctx.h, ctypes.byref(filt), None, None, None, None, None, None))
+            assert filt.value == bits
             for w in (w0, w2):
                 assert w["thresh"] == thresh
                 assert np.array_equal(w["counts"], counts), (L, M, theta)
@@ -95,7 +110,7 @@ def test_counts_identical_with_and_without_filter(pkg, orc, ctx, L, M):
         ctx.check(lib.gdca_set_tc_filter(ctx.h, 1))
 
 
-def test_filtered_sweep_adversarial_and_sharded(pkg, orc, ctx):
+def test_filtered_sweep_adversarial_and_sharded(pkg, orc, ctx, bits):
     """Neighbour pairs spread over many blocks, near-threshold pairs, and the multi-GPU partition run sequentially:
     the filter's per-rank tile share plus the exact sweep of its flagged blocks adds up to the unsharded counts."""
     from gaussdca_jl_b200._lib import ptr
@@ -135,7 +150,7 @@ def test_filtered_sweep_adversarial_and_sharded(pkg, orc, ctx):
         ctx.check(lib.gdca_set_tc_filter(ctx.h, 1))
 
 
-def test_large_run_same_ranking_with_and_without_filter(pkg, orc, ctx):
+def test_large_run_same_ranking_with_and_without_filter(pkg, orc, ctx, bits):
     """Config-B-sized sweep (auto mode switches the filter on at M >= 16384): identical weights and ranking."""
     L, M = 64, 20000
     Z = orc.synth_alignment(L, M, seed=20140321)
@@ -147,8 +162,8 @@ def test_large_run_same_ranking_with_and_without_filter(pkg, orc, ctx):
         ctx.check(lib.gdca_set_tc_filter(ctx.h, 1))
         w1 = pkg.compute_weights(Z, "auto", ctx=ctx, full=True)
         filt, blocks = ctypes.c_int32(), ctypes.c_int64()
-        ctx.check(lib.gdca_dev_sweep_info(ctx.h, ctypes.byref(filt), None, None, ctypes.byref(blocks), None, None))
-        assert filt.value == 1
+        ctx.check(lib.gdca_dev_sweep_info(ctx.h, ctypes.byref(filt), None, None, ctypes.byref(blocks), None, None, None))
+        assert filt.value == bits
         T = (M + 127) // 128
         assert 0 < blocks.value <= T * (T + 1) // 2
         R1 = pkg.gdca_from_alignment(Z, 0.8, "auto", "frob", 5, ctx=ctx)

@@ -1,8 +1,20 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel name."""
 import collections, csv, re, sys
+"""   python tools/launch_agg.py launches.csv [--step N]
+--step N keeps only the launches of the N-th hot-path step (1-based): from the N-th maxq_kernel (first kernel of a step)
+up to the next one, without the L2-flush fill between steps."""
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
 hdr = rows[0]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+if "--step" in sys.argv:
+    n = int(sys.argv[sys.argv.index("--step") + 1])
+    starts = [i for i, r in enumerate(rows) if i and "maxq_kernel" in r[ki]]
+    lo = starts[n - 1]
+    hi = starts[n] if n < len(starts) else len(rows)
+    body = rows[lo:hi]
+    while body and ("FillFunctor" in body[-1][ki] or "elementwise" in body[-1][ki]):
+        body.pop()
+    rows = [hdr] + body
 agg, tot = collections.OrderedDict(), 0.0
 for r in rows[1:]:
     name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("<unnamed>::", "")

@@ -6,11 +6,12 @@ OUT = "profiles"
 os.makedirs(OUT, exist_ok=True)
 
 # ---- 1. launch list
-agg = subprocess.run([sys.executable, "tools/launch_agg.py", "gpurun_out/launches_bench.csv"], capture_output=True, text=True).stdout
+agg = subprocess.run([sys.executable, "tools/launch_agg.py", "gpurun_out/launches_bench.csv", "--step", "4"], capture_output=True, text=True).stdout
 open(f"{OUT}/{ROUND}_launches.md", "w").write(
     f"# {ROUND}: ncu launch list of one bench step\n\n"
-    "Command (on the GPU box): `ncu --metrics gpu__time_duration.sum --clock-control none -s <warm-up launches> -c <one step> --csv "
-    "--log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline`\n"
+    "Command (on the GPU box): `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv "
+    "--log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline`; the list below is the "
+    "timed step = the 4th hot-path pass (after 3 warm-up passes), cut out with `tools/launch_agg.py --step 4`\n"
     "(cold-cache, serialised launches: compare SHARES, not absolutes; the bench value itself is never taken under ncu).\n\n```\n" + agg + "```\n")
 
 # ---- 2. full-set metrics of the top kernels
