@@ -192,6 +192,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args, L, M, score, pc)
 
+    # stdout carries exactly ONE line (the JSON): everything libraries print to fd 1 (the NCCL version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     pkg = graft.load_package()
@@ -426,7 +431,8 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches2 - launches1),
         "clocks": clocks, "roofline": roof, "stages": stages, "cpu_baseline": cb,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
