@@ -235,6 +235,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
     if (m >= 0 && m <= 2) ctx->tc_filter_mode = m;
   }
   if (const char *env = getenv("GDCA_TC_FILTER_BITS")) ctx->tc_filter_fp4 = atoi(env) != 8;
+  if (const char *env = getenv("GDCA_TC_MULTICAST")) ctx->tc_filter_want_multicast = atoi(env) != 0;
   *out = ctx;
   return GDCA_OK;
 }
@@ -356,6 +357,12 @@ int32_t gdca_set_tc_filter_bits(gdca_ctx *ctx, int32_t bits) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   if (bits != 4 && bits != 8) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_tc_filter_bits: bits must be 4 or 8");
   ctx->tc_filter_fp4 = bits == 4;
+  return GDCA_OK;
+}
+
+int32_t gdca_set_tc_filter_multicast(gdca_ctx *ctx, int32_t on) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  ctx->tc_filter_want_multicast = on != 0;
   return GDCA_OK;
 }
 

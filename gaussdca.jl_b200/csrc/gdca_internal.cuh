@@ -66,6 +66,8 @@ struct gdca_ctx {
   int have_V = 0;                                  // 0: dV stale; 8 / 4: dV holds the FP8 / FP4 encoding of the loaded alignment
   int tc_filter_mode = 1;                          // 0 off, 1 auto (large M), 2 always (tests)
   bool tc_filter_fp4 = true;                       // operand type of the filter: e4m3 (kind::f8f6f4) or e2m1 (kind::mxf4)
+  bool tc_filter_want_multicast = true;            // 2-CTA clusters + TMA multicast of the B tile (env GDCA_TC_MULTICAST=0: off)
+  bool tc_filter_multicast = false;                // last filter launch used 2-CTA clusters with TMA multicast
   bool last_sweep_filtered = false;
   double tc_filter_tflop = 0.0;                    // flop of the last filter launch on this rank, in 1e12
   double tc_filter_l2_bytes = 0.0;                 // operand bytes its TMA loads moved

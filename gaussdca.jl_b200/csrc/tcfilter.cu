@@ -38,7 +38,7 @@ namespace {
 constexpr int BM = 128;              // tile rows (sequences)
 constexpr int BK = 128;              // K bytes per stage (= SWIZZLE_128B atom width)
 constexpr int MAX_STAGE = 5;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;       // warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int BAND = 16;             // row blocks per band of the tile order
 
@@ -97,11 +97,43 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same box into the same shared-memory offset (and onto the same mbarrier offset) of every CTA of the cluster in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// one lane of the (converged) warp; the compiler keeps warp-uniform operands in uniform registers around it
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -161,40 +193,53 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // in flight at one time use 16 A tiles and a few B tiles out of L2.  (row, cj) pairs of a band that lie wholly below the
 // diagonal are skipped (valid() == false).  Whole rows per rank: every 128 x 128 block is flagged by exactly one rank.
 struct TileIter {
-  int T, NT, NB, colw, rank, world, b;
-  long long u;
-  __device__ int row_of(int i) const { return rank + world * i; }
-  __device__ int cmin() const { return (int)(((long long)BM * row_of(b * BAND)) / colw); }
-  __device__ long long band_tiles() const { return (long long)(NT - cmin()) * BAND; }
-  __device__ void start(const struct FilterParams &P, int colw_, long long first);
-  __device__ void advance(long long d) {
+  int T, NT, NB, colw, rank, world;
+  int b, u, cmin_b, tiles_b;  // band, index inside the band, first column tile and tile count of the band (cached)
+  __device__ __forceinline__ int row_of(int i) const { return rank + world * i; }
+  __device__ __forceinline__ void set_band() {
+    cmin_b = (int)(((long long)BM * row_of(b * BAND)) / colw);
+    tiles_b = (NT - cmin_b) * BAND;
+  }
+  __device__ __forceinline__ void start(const FilterParams &P, int colw_, int first) {
+    T = P.T;
+    NT = P.NT;
+    NB = P.NB;
+    colw = colw_;
+    rank = P.rank;
+    world = P.world;
+    b = 0;
+    u = 0;
+    if (NB > 0) set_band();
+    advance(first);
+  }
+  __device__ __forceinline__ void advance(int d) {
     u += d;
-    while (b < NB && u >= band_tiles()) {
-      u -= band_tiles();
-      ++b;
+    while (b < NB && u >= tiles_b) {
+      u -= tiles_b;
+      if (++b < NB) set_band();
     }
   }
-  __device__ bool done() const { return b >= NB; }
-  __device__ int bi() const { return row_of(b * BAND + (int)(u % BAND)); }
-  __device__ int cj() const { return cmin() + (int)(u / BAND); }
-  __device__ bool valid() const { return bi() < T && (long long)colw * (cj() + 1) > (long long)BM * bi(); }
+  __device__ __forceinline__ bool done() const { return b >= NB; }
+  __device__ __forceinline__ int bi() const { return row_of(b * BAND + (u & (BAND - 1))); }
+  __device__ __forceinline__ int cj() const { return cmin_b + (u / BAND); }
+  __device__ __forceinline__ bool valid_row(int row) const {
+    return row < T && (long long)colw * (cj() + 1) > (long long)BM * row;
+  }
+  __device__ __forceinline__ bool valid() const { return valid_row(bi()); }
+  // the tile of the other CTA of a 2-CTA cluster: the neighbouring row of the same band, same column tile (BAND is even)
+  __device__ __forceinline__ bool peer_valid() const { return valid_row(row_of(b * BAND + ((u & (BAND - 1)) ^ 1))); }
 };
-__device__ void TileIter::start(const FilterParams &P, int colw_, long long first) {
-  T = P.T;
-  NT = P.NT;
-  NB = P.NB;
-  colw = colw_;
-  rank = P.rank;
-  world = P.world;
-  b = 0;
-  u = 0;
-  advance(first);
-}
+static_assert((BAND & (BAND - 1)) == 0, "BAND must be a power of two");
 
-template <bool FP4>
+// MC: launched as clusters of 2 CTAs that work on neighbouring row blocks of the SAME column tile.  Each CTA loads its own A
+// tile and one half of the B tile; the half is TMA-multicast into both CTAs (-32 % L2->SM operand traffic at 128 x 224).  A
+// shared-memory stage is therefore written by both CTAs' producers: its empty barrier counts the tcgen05.commit of BOTH
+// CTAs (multicast commit), its full barrier the bytes of all three boxes.
+template <bool FP4, bool MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_filter_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, FilterParams P) {
   using C = Cfg<FP4>;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
   constexpr int BN = C::BN;
   constexpr int NSTAGE = C::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
@@ -216,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? 2 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -231,6 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything of this CTA can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -245,83 +291,103 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   tc_fence_after();
 
-  const long long first = (long long)blockIdx.x;
-  const long long step = (long long)gridDim.x;
+  const int first = (int)blockIdx.x;
+  const int step = (int)gridDim.x;
 
+  // The producer and the MMA issuer are ONE thread's instruction stream each and the tensor pipe can only be as fast as
+  // they are: the whole warp runs the loops (warp-uniform control flow, operands in uniform registers), one elected lane
+  // issues, slot / phase advance by increments (no divisions), descriptors are a constant plus the stage offset.
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      TileIter it;
-      long long kq = 0;  // k-block counter over the whole kernel -> ring slot and phase
-      for (it.start(P, BN, first); !it.done(); it.advance(step)) {
-        if (!it.valid()) continue;
-        const int bi = it.bi(), cj = it.cj();
-        for (int kb = 0; kb < P.KB; ++kb, ++kq) {
-          const int s = (int)(kq % NSTAGE);
-          const uint32_t ph = (uint32_t)((kq / NSTAGE) & 1);
-          mbar_wait(empty_bar(s), ph ^ 1u);
+    TileIter it;
+    int s = 0;
+    uint32_t ph = 0;  // ring slot and phase, carried across tiles
+    for (it.start(P, BN, first); !it.done(); it.advance(step)) {
+      if (!(it.valid() || (MC && it.peer_valid()))) continue;
+      const int row_a = it.bi() * BM;
+      const int row_b = it.cj() * BN + (MC ? (int)crank * (BN / 2) : 0);
+      for (int kb = 0; kb < P.KB; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t sa = base + (uint32_t)s * (uint32_t)C::STAGE_BYTES;
           mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
-          const uint32_t sa = base + s * C::STAGE_BYTES;
-          tma_load_2d(sa, &tmapA, full_bar(s), kb * BK, bi * BM);
-          tma_load_2d(sa + C::A_BYTES, &tmapB, full_bar(s), kb * BK, cj * BN);
+          tma_load_2d(sa, &tmapA, full_bar(s), kb * BK, row_a);  // rows beyond the matrix are zero-filled
+          if (MC)  // tmapB boxes are BN/2 rows here: my half of the B tile, delivered to both CTAs
+            tma_load_2d_mc(sa + C::A_BYTES + crank * (C::B_BYTES / 2), &tmapB, full_bar(s), kb * BK, row_b, (uint16_t)3);
+          else
+            tma_load_2d(sa + C::A_BYTES, &tmapB, full_bar(s), kb * BK, row_b);
+        }
+        __syncwarp();
+        if (++s == NSTAGE) {
+          s = 0;
+          ph ^= 1u;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      TileIter it;
-      long long kq = 0, n = 0;
-      for (it.start(P, BN, first); !it.done(); it.advance(step)) {
-        if (!it.valid()) continue;
-        const int as = (int)(n & 1);
-        const uint32_t aph = (uint32_t)((n >> 1) & 1);
-        ++n;
-        mbar_wait(tempty_bar(as), aph ^ 1u);  // the epilogue has drained this accumulator stage
+    TileIter it;
+    int s = 0;
+    uint32_t ph = 0, n = 0;
+    // descriptor halves: hi = SBO 1024 B | version 1 | SWIZZLE_128B, lo = start address >> 4 | LBO field 1
+    constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t sfa = tmem_base + (uint32_t)C::SF_COL, sfb = sfa + 32u;
+    for (it.start(P, BN, first); !it.done(); it.advance(step)) {
+      if (!(it.valid() || (MC && it.peer_valid()))) continue;
+      const uint32_t as = n & 1u, aph = (n >> 1) & 1u;
+      ++n;
+      mbar_wait(tempty_bar(as), aph ^ 1u);  // the epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * (uint32_t)BN;
+      for (int kb = 0; kb < P.KB; ++kb) {
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < P.KB; ++kb, ++kq) {
-          const int s = (int)(kq % NSTAGE);
-          const uint32_t ph = (uint32_t)((kq / NSTAGE) & 1);
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t sa = base + s * C::STAGE_BYTES;
-          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + C::A_BYTES);
+        if (elect_one()) {
+          const uint32_t sa = base + (uint32_t)s * (uint32_t)C::STAGE_BYTES;
+          const uint32_t lo_a = ((sa >> 4) & 0x3FFFu) | (1u << 16), lo_b = (((sa + C::A_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 32 bytes along K per instruction (32 e4m3 / 64 e2m1) = +2 in the address field
+            const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(lo_a + 2u * k);
+            const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(lo_b + 2u * k);
+            const uint32_t accumulate = (k > 0) ? 1u : (uint32_t)(kb != 0);
             if (FP4)
-              umma_mxf4(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), C::IDESC, (uint32_t)((kb | k) != 0),
-                        tmem_base + (uint32_t)C::SF_COL, tmem_base + (uint32_t)C::SF_COL + 32u);
+              umma_mxf4(tmem_d, da, db, C::IDESC, accumulate, sfa, sfb);
             else
-              umma_f8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), C::IDESC, (uint32_t)((kb | k) != 0));
+              umma_f8(tmem_d, da, db, C::IDESC, accumulate);
           }
-          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          if (MC)
+            umma_commit_mc(empty_bar(s), (uint16_t)3);  // both producers write this stage: tell both
+          else
+            umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          if (kb == P.KB - 1) umma_commit(tfull_bar(as));  // accumulator complete
         }
-        umma_commit(tfull_bar(as));  // accumulator complete
+        __syncwarp();
+        if (++s == NSTAGE) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
-    __syncwarp();
   } else {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32 (w & 3) .. +31 = tile rows =====
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     TileIter it;
-    long long n = 0;
+    uint32_t n = 0;
     for (it.start(P, BN, first); !it.done(); it.advance(step)) {
-      if (!it.valid()) continue;
+      if (!(it.valid() || (MC && it.peer_valid()))) continue;
       const int bi = it.bi(), cj = it.cj();
-      const int as = (int)(n & 1);
-      const uint32_t aph = (uint32_t)((n >> 1) & 1);
+      const bool mine = it.valid();  // MC: a tile that only exists because the peer's does is computed but never flagged
+      const uint32_t as = n & 1u, aph = (n >> 1) & 1u;
       ++n;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
-      // one 32 x 32 cell per warp and step (a software-pipelined tcgen05.ld measured no faster: the epilogue is hidden
-      // behind the MMAs of the next tile)
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)BN;
+      // one 32 x 32 cell per warp and step.  Measured: neither a software-pipelined tcgen05.ld, nor 8 epilogue warps, nor
+      // skipping the reads altogether changes the kernel time -- the epilogue is hidden behind the MMAs of the next tile.
       auto reduce_cell = [&](const uint32_t (&v)[32], int c) {
         const long long col0 = (long long)cj * BN + c * 32;
-        if (P.dump) {
+        if (P.dump && mine) {
           float *d = P.dump + ((long long)bi * BM + row) * P.dump_ld + col0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
@@ -331,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
         const bool hit = __any_sync(0xffffffffu, mx > P.bound);
         const int cb = (int)(col0 >> 7);
-        if (hit && lane == 0 && cb >= bi && cb < P.T)
+        if (hit && lane == 0 && mine && cb >= bi && cb < P.T)
           atomicOr(P.flags + (long long)bi * P.T + cb, 1u << (quarter * 4 + (int)((col0 >> 5) & 3)));
       };
 #pragma unroll 1
@@ -349,6 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until it is done too
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -475,9 +542,11 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
     GDCA_LAUNCH_CHECK(ctx);
     ctx->have_V = FP4 ? 4 : 8;
   }
+  // 2-CTA clusters with TMA multicast of the B tile unless switched off (gdca_set_tc_filter_multicast) or the grid is odd
+  const bool mc = ctx->tc_filter_want_multicast && (ctx->num_sms % 2 == 0);
   CUtensorMap mapA, mapB;
   GDCA_TRY(make_tensor_map(ctx, &mapA, ctx->dV, VM, Kbytes, BM));
-  GDCA_TRY(make_tensor_map(ctx, &mapB, ctx->dV, VM, Kbytes, C::BN));
+  GDCA_TRY(make_tensor_map(ctx, &mapB, ctx->dV, VM, Kbytes, mc ? C::BN / 2 : C::BN));
 
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dFlags, 0, (size_t)(T * T) * sizeof(uint32_t), ctx->stream));
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dNItems, 0, sizeof(int), ctx->stream));
@@ -493,9 +562,29 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   P.flags = ctx->dFlags;
   P.dump = dump;
   P.dump_ld = dump_ld;
-  GDCA_CUDA(ctx, cudaFuncSetAttribute(tc_filter_kernel<FP4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-  tc_filter_kernel<FP4><<<ctx->num_sms, TC_THREADS, C::SMEM, ctx->stream>>>(mapA, mapB, P);
+  auto launch = [&](auto kern, int threads, bool cluster) -> int32_t {
+    GDCA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctx->num_sms);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster ? 1 : 0;
+    GDCA_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, mapA, mapB, P));
+    return GDCA_OK;
+  };
+  if (mc)
+    GDCA_TRY(launch(tc_filter_kernel<FP4, true>, TC_THREADS, true));
+  else
+    GDCA_TRY(launch(tc_filter_kernel<FP4, false>, TC_THREADS, false));
   GDCA_LAUNCH_CHECK(ctx);
+  ctx->tc_filter_multicast = mc;
 
   const long long tt = T * T;
   const int cgrid = (int)((tt + 255) / 256 < (long long)ctx->num_sms * 8 ? (tt + 255) / 256 : (long long)ctx->num_sms * 8);
@@ -506,7 +595,9 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   for (long long bi = rank; bi < T; bi += world) tiles += NT - (BM * bi) / C::BN;
   ctx->tc_filter_tiles = tiles;
   ctx->tc_filter_tflop = 2.0 * (double)BM * C::BN * (double)(Kbytes * (FP4 ? 2 : 1)) * 1e-12 * (double)tiles;
-  ctx->tc_filter_l2_bytes = (double)(BM + C::BN) * (double)Kbytes * (double)tiles;
+  // TMA operand bytes requested from L2 (multicast: each CTA fetches its A tile and half a B tile; the few tiles computed only
+  // because the cluster peer's tile is valid are not counted)
+  ctx->tc_filter_l2_bytes = (double)(BM + (mc ? C::BN / 2 : C::BN)) * (double)Kbytes * (double)tiles;
   return GDCA_OK;
 }
 

@@ -131,6 +131,9 @@ int32_t gdca_dev_pair_pass(gdca_ctx *ctx, int32_t mode, int64_t thresh);
  * (env GDCA_TC_FILTER_BITS overrides the default). */
 int32_t gdca_set_tc_filter(gdca_ctx *ctx, int32_t mode);
 int32_t gdca_set_tc_filter_bits(gdca_ctx *ctx, int32_t bits);
+/* on (default): the prefilter runs as 2-CTA clusters that share the column tile by TMA multicast; off: independent CTAs
+ * (env GDCA_TC_MULTICAST overrides the default).  Same results either way. */
+int32_t gdca_set_tc_filter_multicast(gdca_ctx *ctx, int32_t on);
 /* Test hook: run only the prefilter for `thresh` on the loaded alignment.  flags_host: [T*T] uint32, T = ceil(M/128);
  * bit 4*(r/32) + (c/32) of entry (bi, bj), bi <= bj, is set iff the 32 x 32 cell at rows r.., columns c.. of that
  * block must be swept.  S_host (optional): the projected score 4*ident_proj - L of every visited tile,

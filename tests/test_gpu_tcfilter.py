@@ -20,14 +20,19 @@ def projected_scores(Z):
     return 4 * ident - L
 
 
-BITS = [8, 4]   # e4m3 operands (kind::f8f6f4) and packed e2m1 operands (kind::mxf4, unit block scales)
+# operands: e4m3 (kind::f8f6f4) / packed e2m1 (kind::mxf4, unit block scales); launch: independent CTAs / 2-CTA clusters
+# sharing the column tile by TMA multicast
+VARIANTS = [(8, 0), (4, 0), (8, 1), (4, 1)]
 
 
-@pytest.fixture(params=BITS, ids=["fp8", "fp4"])
+@pytest.fixture(params=VARIANTS, ids=["fp8", "fp4", "fp8-multicast", "fp4-multicast"])
 def bits(request, ctx):
-    ctx.check(ctx.lib.gdca_set_tc_filter_bits(ctx.h, request.param))
-    yield request.param
+    b, mc = request.param
+    ctx.check(ctx.lib.gdca_set_tc_filter_bits(ctx.h, b))
+    ctx.check(ctx.lib.gdca_set_tc_filter_multicast(ctx.h, mc))
+    yield b
     ctx.check(ctx.lib.gdca_set_tc_filter_bits(ctx.h, 4))
+    ctx.check(ctx.lib.gdca_set_tc_filter_multicast(ctx.h, 1))
 
 
 def run_filter(ctx, Z, thresh, want_scores=True):

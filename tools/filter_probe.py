@@ -20,8 +20,9 @@ Z = np.empty((M, L), dtype=np.int8)
 ctx.check(lib.gdca_synth_alignment(ctx.h, ptr(Z), L, M, 20140321))
 ctx.check(lib.gdca_dev_load(ctx.h, ptr(Z), L, M))
 thresh = L // 2
-for bits in (8, 4):
+for bits, mc in ((8, 0), (8, 1), (4, 0), (4, 1)):
     ctx.check(lib.gdca_set_tc_filter_bits(ctx.h, bits))
+    ctx.check(lib.gdca_set_tc_filter_multicast(ctx.h, mc))
     for rep in range(reps):
         ctx.check(lib.gdca_dev_pair_pass(ctx.h, 1, thresh))
         filt, tiles, blocks = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
@@ -29,6 +30,6 @@ for bits in (8, 4):
         msf, msx = ctypes.c_float(), ctypes.c_float()
         ctx.check(lib.gdca_dev_sweep_info(ctx.h, ctypes.byref(filt), ctypes.byref(tiles), ctypes.byref(tf), ctypes.byref(blocks),
                                           ctypes.byref(msf), ctypes.byref(msx), ctypes.byref(l2)))
-    print(json.dumps(dict(bits=filt.value, tiles=tiles.value, tflop=tf.value, ms_filter=msf.value, ms_exact=msx.value,
+    print(json.dumps(dict(bits=filt.value, multicast=mc, tiles=tiles.value, tflop=tf.value, ms_filter=msf.value, ms_exact=msx.value,
                           blocks=blocks.value, tflops=tf.value / (msf.value / 1e3) if msf.value else None,
                           l2_tb_s=l2.value / (msf.value / 1e3) / 1e12 if msf.value else None)))
