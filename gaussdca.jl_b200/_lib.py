@@ -77,6 +77,7 @@ SIGNATURES = {
     "gdca_dev_tc_filter": (_i32, [_p, _i64, _p, _p, _i64]),
     "gdca_set_tc_filter_bits": (_i32, [_p, _i32]),
     "gdca_set_tc_filter_multicast": (_i32, [_p, _i32]),
+    "gdca_tc_filter_tile_order": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _pi64]),
     "gdca_dev_sweep_info": (_i32, [_p, _pi32, _pi64, _pdbl, _pi64, ctypes.POINTER(ctypes.c_float),
                                    ctypes.POINTER(ctypes.c_float), _pdbl]),
     "gdca_dev_ham_sum_ptr": (_p, [_p]),

@@ -195,12 +195,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 struct TileIter {
   int T, NT, NB, colw, rank, world;
   int b, u, cmin_b, tiles_b;  // band, index inside the band, first column tile and tile count of the band (cached)
-  __device__ __forceinline__ int row_of(int i) const { return rank + world * i; }
-  __device__ __forceinline__ void set_band() {
+  __host__ __device__ __forceinline__ int row_of(int i) const { return rank + world * i; }
+  __host__ __device__ __forceinline__ void set_band() {
     cmin_b = (int)(((long long)BM * row_of(b * BAND)) / colw);
     tiles_b = (NT - cmin_b) * BAND;
   }
-  __device__ __forceinline__ void start(const FilterParams &P, int colw_, int first) {
+  __host__ __device__ __forceinline__ void start(const FilterParams &P, int colw_, int first) {
     T = P.T;
     NT = P.NT;
     NB = P.NB;
@@ -212,22 +212,22 @@ struct TileIter {
     if (NB > 0) set_band();
     advance(first);
   }
-  __device__ __forceinline__ void advance(int d) {
+  __host__ __device__ __forceinline__ void advance(int d) {
     u += d;
     while (b < NB && u >= tiles_b) {
       u -= tiles_b;
       if (++b < NB) set_band();
     }
   }
-  __device__ __forceinline__ bool done() const { return b >= NB; }
-  __device__ __forceinline__ int bi() const { return row_of(b * BAND + (u & (BAND - 1))); }
-  __device__ __forceinline__ int cj() const { return cmin_b + (u / BAND); }
-  __device__ __forceinline__ bool valid_row(int row) const {
+  __host__ __device__ __forceinline__ bool done() const { return b >= NB; }
+  __host__ __device__ __forceinline__ int bi() const { return row_of(b * BAND + (u & (BAND - 1))); }
+  __host__ __device__ __forceinline__ int cj() const { return cmin_b + (u / BAND); }
+  __host__ __device__ __forceinline__ bool valid_row(int row) const {
     return row < T && (long long)colw * (cj() + 1) > (long long)BM * row;
   }
-  __device__ __forceinline__ bool valid() const { return valid_row(bi()); }
+  __host__ __device__ __forceinline__ bool valid() const { return valid_row(bi()); }
   // the tile of the other CTA of a 2-CTA cluster: the neighbouring row of the same band, same column tile (BAND is even)
-  __device__ __forceinline__ bool peer_valid() const { return valid_row(row_of(b * BAND + ((u & (BAND - 1)) ^ 1))); }
+  __host__ __device__ __forceinline__ bool peer_valid() const { return valid_row(row_of(b * BAND + ((u & (BAND - 1)) ^ 1))); }
 };
 static_assert((BAND & (BAND - 1)) == 0, "BAND must be a power of two");
 
@@ -602,6 +602,36 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
 }
 
 }  // namespace
+
+// Host-side replay of the kernel's tile order for one CTA (the same TileIter code, compiled for the host): rows of
+// {bi, cj, valid, peer_valid} in visiting order.  Lets CPU tests check coverage, disjointness across ranks and the
+// lock-step of cluster pairs without a GPU.
+extern "C" int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t rank, int32_t world, int32_t grid, int32_t cta,
+                                             int32_t *out, int64_t cap_rows, int64_t *n_rows) {
+  if (T < 1 || (bits != 4 && bits != 8) || world < 1 || rank < 0 || rank >= world || grid < 1 || cta < 0 || cta >= grid || !n_rows)
+    return GDCA_ERR_INVALID_ARG;
+  const int colw = bits == 4 ? Cfg<true>::BN : Cfg<false>::BN;
+  FilterParams P{};
+  P.T = T;
+  P.NT = (int)(((long long)T * BM + colw - 1) / colw);
+  const long long my_rows = T > rank ? ((long long)T - rank + world - 1) / world : 0;
+  P.NB = (int)((my_rows + BAND - 1) / BAND);
+  P.rank = rank;
+  P.world = world;
+  TileIter it;
+  int64_t n = 0;
+  for (it.start(P, colw, cta); !it.done(); it.advance(grid)) {
+    if (out && n < cap_rows) {
+      out[4 * n + 0] = it.bi();
+      out[4 * n + 1] = it.cj();
+      out[4 * n + 2] = it.valid() ? 1 : 0;
+      out[4 * n + 3] = it.peer_valid() ? 1 : 0;
+    }
+    ++n;
+  }
+  *n_rows = n;
+  return GDCA_OK;
+}
 
 // Flags the 32 x 32 cells of the 128 x 128 blocks (bi <= bj, this rank's share of the tiles) that may contain a pair
 // with hamming < thresh and compacts the blocks with a non-empty mask into ctx->dItems / dItemMask / dNItems.

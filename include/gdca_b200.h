@@ -139,6 +139,10 @@ int32_t gdca_set_tc_filter_multicast(gdca_ctx *ctx, int32_t on);
  * block must be swept.  S_host (optional): the projected score 4*ident_proj - L of every visited tile,
  * [128*T][ld] floats, ld >= 128*T + 256 (parts of the lower triangle that no tile covers are left at 0). */
 int32_t gdca_dev_tc_filter(gdca_ctx *ctx, int64_t thresh, uint32_t *flags_host, float *S_host, int64_t ld);
+/* Host-only (no GPU): the tile order of CTA `cta` of a `grid`-CTA prefilter launch for T = ceil(M/128) row blocks, as rows
+ * {bi, cj, valid, peer_valid} (4 x int32) -- the kernel's own iterator compiled for the host, for CPU tests. */
+int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t rank, int32_t world, int32_t grid, int32_t cta,
+                                  int32_t *out, int64_t cap_rows, int64_t *n_rows);
 /* What the last mode-1 sweep did: *filtered = 0, or the operand bits (8 / 4) of the prefilter that ran; its tiles,
  * flop (1e12) and TMA operand bytes; 128x128 blocks that went through the exact sweep; device ms of the two parts. */
 int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
