@@ -393,7 +393,8 @@ def main():
                 "ms_per_launch": t_f * 1e3, "tiles": int(f_tiles.value), "flop_per_launch": f_tflop.value * 1e12,
                 "l2_operand_bytes_per_launch": f_l2.value,
                 "l2_operand_tb_per_s": f_l2.value / t_f / 1e12,
-                "traffic": ncu_traffic("tc_filter_kernel<1>" if fp4 else "tc_filter_kernel<0>") if world == 1 and args.workload == "C" else None,
+                "traffic": (ncu_traffic(f"tc_filter_kernel<{int(fp4)}, 1>") or ncu_traffic(f"tc_filter_kernel<{int(fp4)}, 0>"))
+                           if world == 1 and args.workload == "C" else None,
                 "exact_sweep": exact, **common,
             }
         else:

@@ -217,6 +217,10 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
   if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail(e);
   if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail(e);
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail(e);
+  for (cudaEvent_t *ev : {&ctx->ev_diag, &ctx->ev_p1, &ctx->ev_u2a, &ctx->ev_u2b})
+    if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if (const char *env = getenv("GDCA_CHOL_LOOKAHEAD")) ctx->chol_inner_lookahead = atoi(env) != 0;
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fact, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dHam, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e);
@@ -259,6 +263,9 @@ void gdca_destroy(gdca_ctx *ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->ev_fact) cudaEventDestroy(ctx->ev_fact);
   if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
+  for (cudaEvent_t e : {ctx->ev_diag, ctx->ev_p1, ctx->ev_u2a, ctx->ev_u2b})
+    if (e) cudaEventDestroy(e);
+  if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

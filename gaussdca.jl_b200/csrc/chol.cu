@@ -399,33 +399,99 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   // inner step (128 columns): diagonal block, panel, update of the remaining columns of the OUTER block only;
   // after OB inner steps one trailing update with K = OB*128 (C tiles read/written n/512 times, not n/128).
   constexpr int OB = 4;
-  cudaStream_t sA = ctx->stream, sB = ctx->stream2;
+  cudaStream_t sA = ctx->stream, sB = ctx->stream2, sP = ctx->stream3;
   bool pending_trail = false;
   for (int K0 = 0; K0 < nb; K0 += OB) {
     const int Kend = (K0 + OB < nb) ? K0 + OB : nb;
+    bool sp_pending = false;  // work of this outer block is still queued on the panel stream
     for (int k = K0; k < Kend; ++k) {
-      diag_block_kernel<<<1, DT, dsmem, ctx->stream>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
+      diag_block_kernel<<<1, DT, dsmem, sA>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
       GDCA_LAUNCH_CHECK(ctx);
       const int rem = nb - k - 1;
       if (rem == 0) break;
-      GemmP p{};
-      // panel: L[I,k] = A[I,k] * X[k,k]'   (in place)
-      p.A = blk(A, k + 1, k); p.lda = np;
-      p.B = blk(X, k, k);     p.ldb = np;
-      p.C = blk(A, k + 1, k); p.ldc = np;
-      p.m = rem * NB; p.n = NB; p.k = NB; p.flags = 0; p.alpha = 1.0; p.beta = 0.0;
-      GDCA_TRY((gemm<false, false>(ctx, p, 1)));
       const int inner_cols = Kend - k - 1;
-      if (inner_cols > 0) {
-        // A[I,J] -= L[I,k] L[J,k]'  for k < J < Kend, I >= J
-        GemmP t{};
-        t.A = blk(A, k + 1, k); t.lda = np;
-        t.B = blk(A, k + 1, k); t.ldb = np;
-        t.C = blk(A, k + 1, k + 1); t.ldc = np;
-        t.m = rem * NB; t.n = inner_cols * NB; t.k = NB; t.flags = G_LOWER_OUT; t.alpha = -1.0; t.beta = 1.0;
-        GDCA_TRY((gemm<false, false>(ctx, t, 1)));
+      if (!ctx->chol_inner_lookahead || inner_cols == 0 || rem < 2) {
+        // last step of the outer block (or look-ahead off): the whole panel on the main stream, then the inner update
+        if (sp_pending) {
+          GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_u2b, 0));
+          sp_pending = false;
+        }
+        GemmP p{};
+        // panel: L[I,k] = A[I,k] * X[k,k]'   (in place)
+        p.A = blk(A, k + 1, k); p.lda = np;
+        p.B = blk(X, k, k);     p.ldb = np;
+        p.C = blk(A, k + 1, k); p.ldc = np;
+        p.m = rem * NB; p.n = NB; p.k = NB; p.flags = 0; p.alpha = 1.0; p.beta = 0.0;
+        GDCA_TRY((gemm<false, false>(ctx, p, 1, sA)));
+        if (inner_cols > 0) {
+          // A[I,J] -= L[I,k] L[J,k]'  for k < J < Kend, I >= J
+          GemmP t{};
+          t.A = blk(A, k + 1, k); t.lda = np;
+          t.B = blk(A, k + 1, k); t.ldb = np;
+          t.C = blk(A, k + 1, k + 1); t.ldc = np;
+          t.m = rem * NB; t.n = inner_cols * NB; t.k = NB; t.flags = G_LOWER_OUT; t.alpha = -1.0; t.beta = 1.0;
+          GDCA_TRY((gemm<false, false>(ctx, t, 1, sA)));
+        }
+        continue;
       }
+      // ---- inner look-ahead: the main stream only does what the NEXT diagonal block needs (its panel tile and its own
+      // update); the rest of the panel and of the inner update run beside it on the panel stream.
+      //   sA: diag(k) | P1: L[k+1,k] | U1: A[k+1,k+1] -= L[k+1,k] L[k+1,k]'            -> diag(k+1) ...
+      //   sP:           P2: L[I,k], I >= k+2 | U2a: column k+1, rows >= k+2 | U2b: columns >= k+2 (lower tiles)
+      // Hand-shakes: P2 needs X[k,k] (ev_diag); U2a needs L[k+1,k] (ev_p1); P1 of step k needs column k final = U2a of
+      // step k-1 (ev_u2a); U1 of step k and U2b of step k-1 both write tile (k+1,k+1) (ev_u2b).
+      GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_diag, sA));
+      if (sp_pending) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_u2a, 0));
+      {
+        GemmP p{};  // P1
+        p.A = blk(A, k + 1, k); p.lda = np;
+        p.B = blk(X, k, k);     p.ldb = np;
+        p.C = blk(A, k + 1, k); p.ldc = np;
+        p.m = NB; p.n = NB; p.k = NB; p.flags = 0; p.alpha = 1.0; p.beta = 0.0;
+        GDCA_TRY((gemm<false, false>(ctx, p, 1, sA)));
+      }
+      GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_p1, sA));
+      if (sp_pending) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_u2b, 0));
+      {
+        GemmP u{};  // U1
+        u.A = blk(A, k + 1, k); u.lda = np;
+        u.B = blk(A, k + 1, k); u.ldb = np;
+        u.C = blk(A, k + 1, k + 1); u.ldc = np;
+        u.m = NB; u.n = NB; u.k = NB; u.flags = 0; u.alpha = -1.0; u.beta = 1.0;
+        GDCA_TRY((gemm<false, false>(ctx, u, 1, sA)));
+      }
+      // panel stream
+      GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, ctx->ev_diag, 0));
+      {
+        GemmP p{};  // P2
+        p.A = blk(A, k + 2, k); p.lda = np;
+        p.B = blk(X, k, k);     p.ldb = np;
+        p.C = blk(A, k + 2, k); p.ldc = np;
+        p.m = (rem - 1) * NB; p.n = NB; p.k = NB; p.flags = 0; p.alpha = 1.0; p.beta = 0.0;
+        GDCA_TRY((gemm<false, false>(ctx, p, 1, sP)));
+      }
+      GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, ctx->ev_p1, 0));
+      {
+        GemmP u{};  // U2a: A[I,k+1] -= L[I,k] L[k+1,k]'  for I >= k+2
+        u.A = blk(A, k + 2, k); u.lda = np;
+        u.B = blk(A, k + 1, k); u.ldb = np;
+        u.C = blk(A, k + 2, k + 1); u.ldc = np;
+        u.m = (rem - 1) * NB; u.n = NB; u.k = NB; u.flags = 0; u.alpha = -1.0; u.beta = 1.0;
+        GDCA_TRY((gemm<false, false>(ctx, u, 1, sP)));
+      }
+      GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_u2a, sP));
+      if (inner_cols > 1) {
+        GemmP u{};  // U2b: A[I,J] -= L[I,k] L[J,k]'  for k+2 <= J < Kend, I >= J
+        u.A = blk(A, k + 2, k); u.lda = np;
+        u.B = blk(A, k + 2, k); u.ldb = np;
+        u.C = blk(A, k + 2, k + 2); u.ldc = np;
+        u.m = (rem - 1) * NB; u.n = (inner_cols - 1) * NB; u.k = NB; u.flags = G_LOWER_OUT; u.alpha = -1.0; u.beta = 1.0;
+        GDCA_TRY((gemm<false, false>(ctx, u, 1, sP)));
+      }
+      GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_u2b, sP));
+      sp_pending = true;
     }
+    if (sp_pending) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_u2b, 0));
     const int rem = nb - Kend;
     if (rem > 0) {
       // Trailing update A[I,J] -= L[I,K0:Kend] L[J,K0:Kend]' (I >= J >= Kend), split for a one-panel look-ahead:

@@ -19,7 +19,10 @@ struct gdca_ctx {
   int num_sms = GDCA_NUM_SMS_DEFAULT;
   cudaStream_t stream = nullptr;   // main stream (created with the highest priority: it carries every critical path)
   cudaStream_t stream2 = nullptr;  // helper stream: bulk trailing updates of the Cholesky (look-ahead)
+  cudaStream_t stream3 = nullptr;  // panel stream of the Cholesky: rest of the panel + inner updates, beside the diagonal chain
   cudaEvent_t ev_fact = nullptr, ev_trail = nullptr;  // look-ahead hand-shakes
+  cudaEvent_t ev_diag = nullptr, ev_p1 = nullptr, ev_u2a = nullptr, ev_u2b = nullptr;  // inner look-ahead hand-shakes
+  int chol_inner_lookahead = 1;    // env GDCA_CHOL_LOOKAHEAD=0: serial inner steps (round-1 first version)
   std::string err;
   int32_t shard_rank = 0, shard_world = 1;
   int64_t launches = 0;
