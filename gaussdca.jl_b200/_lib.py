@@ -71,6 +71,9 @@ SIGNATURES = {
     "gdca_ranking": (_i32, [_p, _p, _i64, _i64, _p, _i64]),
     "gdca_dev_load": (_i32, [_p, _p, _i64, _i64]),
     "gdca_dev_load_resident": (_i32, [_p, _p, _i64, _i64]),
+    "gdca_compute_weighted_frequencies": (_i32, [_p, _p, _i64, _i64, _dbl, _p, _p, _pdbl, _p, _pdbl, _pi32]),
+    "gdca_add_pseudocount": (_i32, [_p, _p, _p, _i64, _i32, _dbl, _p, _p]),
+    "gdca_compute_C": (_i32, [_p, _p, _p, _i64, _p]),
     "gdca_dev_pair_pass": (_i32, [_p, _i32, _i64]),
     "gdca_dev_pair_sample": (_i32, [_p, _i32]),
     "gdca_set_tc_filter": (_i32, [_p, _i32]),

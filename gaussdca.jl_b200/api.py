@@ -21,7 +21,7 @@ from ._lib import RANK_DTYPE, SCORE_CODES, PosDefException, default_context, ptr
 from .fasta import read_fasta_alignment, remove_duplicate_sequences
 
 __all__ = ["gDCA", "printrank", "check_arguments", "gdca_from_alignment", "compute_theta", "compute_weights",
-           "compute_covariance", "inverse", "compute_FN", "compute_DI_gauss", "correct_APC", "compute_ranking",
+           "compute_covariance", "compute_weighted_frequencies", "add_pseudocount", "compute_C", "inverse", "compute_FN", "compute_DI_gauss", "correct_APC", "compute_ranking",
            "read_fasta_alignment", "remove_duplicate_sequences", "PosDefException"]
 
 
@@ -155,6 +155,54 @@ def compute_covariance(Z, W, Meff, pseudocount, *, ctx=None):
     ctx.check(ctx.lib.gdca_compute_covariance(ctx.h, ptr(Z), L, M, ptr(W), float(Meff), float(pseudocount), ptr(C),
                                               ptr(Pi), ctypes.byref(qo)))
     return C, Pi, qo.value
+
+
+def compute_weighted_frequencies(Z, q=None, theta="auto", *, ctx=None):
+    """DCAUtils compute_weighted_frequencies(Z, q, θ) -> (Pi_true, Pij_true, Meff, W); call site src/GaussDCA.jl:28.
+    q must equal max(Z) (the reference passes exactly that, src/GaussDCA.jl:25) or be omitted."""
+    ctx = ctx or default_context()
+    Z = _as_Z(Z)
+    M, L = Z.shape
+    qz = int(Z.max())
+    if q is not None and int(q) != qz:
+        raise ValueError(f"q={q} does not match max(Z)={qz}")
+    if qz >= 32:
+        raise RuntimeError(f"parameter q={qz} is too big (max 31 is allowed)")
+    n = (qz - 1) * L
+    Pi = np.empty(n, dtype=np.float64)
+    Pij = np.empty((n, n), dtype=np.float64)
+    W = np.empty(M, dtype=np.float64)
+    meff, th, qq = ctypes.c_double(), ctypes.c_double(), ctypes.c_int32()
+    ctx.check(ctx.lib.gdca_compute_weighted_frequencies(ctx.h, ptr(Z), L, M, _theta_code(theta), ptr(Pi), ptr(Pij),
+                                                        ctypes.byref(meff), ptr(W), ctypes.byref(th), ctypes.byref(qq)))
+    return Pi, Pij, meff.value, W
+
+
+def add_pseudocount(Pi_true, Pij_true, pseudocount, q, *, ctx=None):
+    """DCAUtils add_pseudocount(Pi_true, Pij_true, pc, q) -> (Pi, Pij); call site src/GaussDCA.jl:30."""
+    ctx = ctx or default_context()
+    Pi_true = np.ascontiguousarray(Pi_true, dtype=np.float64)
+    Pij_true = np.ascontiguousarray(Pij_true, dtype=np.float64)
+    n = Pi_true.shape[0]
+    if Pij_true.shape != (n, n):
+        raise ValueError("Pij_true must be n x n with n = len(Pi_true)")
+    Pi = np.empty(n, dtype=np.float64)
+    Pij = np.empty((n, n), dtype=np.float64)
+    ctx.check(ctx.lib.gdca_add_pseudocount(ctx.h, ptr(Pi_true), ptr(Pij_true), n, int(q), float(pseudocount), ptr(Pi), ptr(Pij)))
+    return Pi, Pij
+
+
+def compute_C(Pi, Pij, *, ctx=None):
+    """compute_C(Pi, Pij) = Pij - Pi * Pi' (src/GaussDCA.jl:32,76)."""
+    ctx = ctx or default_context()
+    Pi = np.ascontiguousarray(Pi, dtype=np.float64)
+    Pij = np.ascontiguousarray(Pij, dtype=np.float64)
+    n = Pi.shape[0]
+    if Pij.shape != (n, n):
+        raise ValueError("Pij must be n x n with n = len(Pi)")
+    C = np.empty((n, n), dtype=np.float64)
+    ctx.check(ctx.lib.gdca_compute_C(ctx.h, ptr(Pi), ptr(Pij), n, ptr(C)))
+    return C
 
 
 def inverse(C, *, ctx=None):

@@ -724,6 +724,67 @@ int32_t gdca_compute_covariance(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64
   return GDCA_OK;
 }
 
+int32_t gdca_compute_weighted_frequencies(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, double *Pi_true,
+                                          double *Pij_true, double *meff, double *W, double *theta_used, int32_t *q_out) {
+  GDCA_TRY(check_LM(ctx, Z, L, M));
+  if (!Pi_true || !Pij_true) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "Pi_true and Pij_true must not be NULL");
+  if (!(theta < 0.0) && !(theta >= 0.0 && theta <= 1.0))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid theta value (must be :auto, or a number between 0 and 1)");
+  if (M < 2 && theta < 0) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "theta = :auto needs at least 2 sequences");
+  ctx->stats = gdca_stats_t{};
+  GDCA_TRY(gdca_dev_load(ctx, Z, L, M));
+  GDCA_TRY(weights_stage(ctx, theta));
+  GDCA_TRY(gdca_k_covariance(ctx, 0.0, /*raw=*/true));  // dPi = Pi_true, dC = Pij_true (upper site blocks)
+  GDCA_TRY(gdca_k_symmetrize_C(ctx));
+  ctx->have_cov = false;  // dC holds frequencies, not a covariance
+  if (W) GDCA_CUDA(ctx, cudaMemcpyAsync(W, ctx->dW, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(Pi_true, ctx->dPi, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_TRY(download_padded(ctx, Pij_true, ctx->dC, ctx->npad, ctx->n));
+  if (meff) *meff = ctx->stats.meff;
+  if (theta_used) *theta_used = ctx->stats.theta;
+  if (q_out) *q_out = ctx->q;
+  return GDCA_OK;
+}
+
+int32_t gdca_add_pseudocount(gdca_ctx *ctx, const double *Pi_true, const double *Pij_true, int64_t n, int32_t q, double pseudocount,
+                             double *Pi, double *Pij) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!Pi_true || !Pij_true || !Pi || !Pij || n < 1 || q < 2 || n % (q - 1) != 0)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "add_pseudocount: NULL buffer, or n is not a multiple of q-1");
+  if (!(pseudocount >= 0.0 && pseudocount <= 1.0))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid pseudocount value (must be between 0 and 1)");
+  GDCA_TRY(set_device(ctx));
+  const size_t nn = (size_t)n * n;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dX, ctx->capX, nn));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dT, ctx->capT, nn));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dPi, ctx->capPi, (size_t)2 * n));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dX, Pij_true, nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dPi, Pi_true, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_TRY(gdca_k_add_pseudocount(ctx, ctx->dPi, ctx->dX, n, q, pseudocount, ctx->dPi + n, ctx->dT));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(Pi, ctx->dPi + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(Pij, ctx->dT, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->have_cov = ctx->have_inv = false;  // scratch buffers reused
+  return GDCA_OK;
+}
+
+int32_t gdca_compute_C(gdca_ctx *ctx, const double *Pi, const double *Pij, int64_t n, double *C) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!Pi || !Pij || !C || n < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "compute_C: Pi, Pij, C must not be NULL and n >= 1");
+  GDCA_TRY(set_device(ctx));
+  const size_t nn = (size_t)n * n;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dX, ctx->capX, nn));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dT, ctx->capT, nn));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dPi, ctx->capPi, (size_t)n));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dX, Pij, nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dPi, Pi, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_TRY(gdca_k_compute_C(ctx, ctx->dPi, ctx->dX, n, ctx->dT));
+  GDCA_CUDA(ctx, cudaMemcpyAsync(C, ctx->dT, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->have_cov = ctx->have_inv = false;
+  return GDCA_OK;
+}
+
 int32_t gdca_inverse(gdca_ctx *ctx, const double *C, int64_t n, double *mJ, int32_t *info) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   if (!C || !mJ || n < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "inverse: C, mJ must not be NULL and n >= 1");

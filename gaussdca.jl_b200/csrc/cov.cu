@@ -152,6 +152,7 @@ struct CovParams {
   long long L, M, n, ld, Lq;
   int q, s, nchunks;
   int rank, world;
+  int raw;    // 1: write Pij_true (no pseudocount, no - Pi Pi'): DCAUtils compute_weighted_frequencies
   double pc;
 };
 
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
       pij = omp * ptrue + ((b == a - 1) ? pcq : 0.0);
     else
       pij = omp * ptrue + pcqq;
-    Crow[c] = pij - pir * P.Pi[c];
+    Crow[c] = P.raw ? ptrue : pij - pir * P.Pi[c];
   }
 }
 
@@ -268,7 +269,47 @@ __global__ void extract_diag_blocks_kernel(const double *__restrict__ C, long lo
   }
 }
 
+// DCAUtils add_pseudocount (call site src/GaussDCA.jl:30) on contiguous n x n / n buffers:
+//   Pi = (1-pc) Pi_true + pc/q;  off-diagonal site blocks: (1-pc) Pij_true + pc/q^2;  diagonal site blocks: (1-pc) Pij_true + delta_ab pc/q
+__global__ void add_pseudocount_kernel(const double *__restrict__ Pi_true, const double *__restrict__ Pij_true, long long n, int s,
+                                       int q, double pc, double *__restrict__ Pi, double *__restrict__ Pij) {
+  const double pcq = pc / q, pcqq = pcq / q, omp = 1.0 - pc;
+  const long long total = n * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / n, c = e - r * n;
+    const double base = omp * Pij_true[e];
+    Pij[e] = (r / s == c / s) ? base + (r == c ? pcq : 0.0) : base + pcqq;
+    if (e < n) Pi[e] = omp * Pi_true[e] + pcq;
+  }
+}
+
+// compute_C(Pi, Pij) = Pij - Pi * Pi'  (src/GaussDCA.jl:32,76)
+__global__ void compute_C_kernel(const double *__restrict__ Pi, const double *__restrict__ Pij, long long n, double *__restrict__ C) {
+  const long long total = n * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / n, c = e - r * n;
+    C[e] = Pij[e] - Pi[r] * Pi[c];
+  }
+}
+
 }  // namespace
+
+int32_t gdca_k_add_pseudocount(gdca_ctx *ctx, const double *Pi_true, const double *Pij_true, long long n, int q, double pc, double *Pi,
+                               double *Pij) {
+  const long long total = n * n;
+  const int grid = (int)((total + 255) / 256 < (long long)ctx->num_sms * 16 ? (total + 255) / 256 : (long long)ctx->num_sms * 16);
+  add_pseudocount_kernel<<<grid, 256, 0, ctx->stream>>>(Pi_true, Pij_true, n, q - 1, q, pc, Pi, Pij);
+  GDCA_LAUNCH_CHECK(ctx);
+  return GDCA_OK;
+}
+
+int32_t gdca_k_compute_C(gdca_ctx *ctx, const double *Pi, const double *Pij, long long n, double *C) {
+  const long long total = n * n;
+  const int grid = (int)((total + 255) / 256 < (long long)ctx->num_sms * 16 ? (total + 255) / 256 : (long long)ctx->num_sms * 16);
+  compute_C_kernel<<<grid, 256, 0, ctx->stream>>>(Pi, Pij, n, C);
+  GDCA_LAUNCH_CHECK(ctx);
+  return GDCA_OK;
+}
 
 int32_t gdca_k_symmetrize_C(gdca_ctx *ctx) {
   const long long n = ctx->n;
@@ -314,7 +355,7 @@ int32_t gdca_k_ident_sum(gdca_ctx *ctx, unsigned long long *ident_out) {
   return GDCA_OK;
 }
 
-int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
+int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw) {
   if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "covariance: no alignment loaded");
   if (!ctx->have_weights) return gdca_fail(ctx, GDCA_ERR_STATE, "covariance: weights not computed");
   const long long L = ctx->L, M = ctx->M, n = ctx->n;
@@ -359,6 +400,7 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc) {
   P.rank = ctx->shard_rank;
   P.world = ctx->shard_world;
   P.pc = pc;
+  P.raw = raw ? 1 : 0;
   const size_t smem = (size_t)ctx->q * SPT * JT * sizeof(double);
   GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cov_rows_kernel<SPT><<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);

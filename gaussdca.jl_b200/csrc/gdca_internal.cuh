@@ -147,7 +147,10 @@ static inline bool gdca_tc_filter_wanted(const gdca_ctx *ctx) {
 int32_t gdca_k_finish_weights(gdca_ctx *ctx, int which);  // weights.cu
 int32_t gdca_k_build_lists(gdca_ctx *ctx);                // cov.cu: per-site lists of sequence ids grouped by state
 int32_t gdca_k_ident_sum(gdca_ctx *ctx, unsigned long long *ident_out);  // cov.cu: sum_{k<l} ident from site histograms
-int32_t gdca_k_covariance(gdca_ctx *ctx, double pc);      // cov.cu
+int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw = false);  // cov.cu (raw: Pij_true instead of C)
+int32_t gdca_k_add_pseudocount(gdca_ctx *ctx, const double *Pi_true, const double *Pij_true, long long n, int q, double pc,
+                               double *Pi, double *Pij);  // cov.cu, contiguous device buffers
+int32_t gdca_k_compute_C(gdca_ctx *ctx, const double *Pi, const double *Pij, long long n, double *C);  // cov.cu
 int32_t gdca_k_symmetrize_C(gdca_ctx *ctx);               // cov.cu: mirror upper site blocks, save diag blocks
 int32_t gdca_k_extract_diag(gdca_ctx *ctx);               // cov.cu: save the s x s diagonal blocks of dC
 int32_t gdca_k_inverse(gdca_ctx *ctx);                    // chol.cu

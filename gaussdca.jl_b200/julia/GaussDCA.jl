@@ -149,4 +149,60 @@ printrank(R::Vector{Tuple{Int,Int,Float64}}) = printrank(stdout, R)   # the refe
 
 printrank(outfile::AbstractString, R::Vector{Tuple{Int,Int,Float64}}) = open(f->printrank(f, R), outfile, "w")
 
+# ---- DCAUtils-shaped staged pieces (not exported, like the DCAUtils functions the reference imports at src/GaussDCA.jl:6) ----
+# Same names, argument order and return tuples as the calls at src/GaussDCA.jl:28-39, each one ccall (include/gdca_b200.h).
+# Julia's column-major n x n arrays are passed as they are: every matrix on this path is symmetric.
+
+function _check(ctx::Context, st::Int32)
+    st == GDCA_OK && return
+    st == GDCA_ERR_INVALID_ARG && throw(ArgumentError(last_error(ctx)))
+    error(last_error(ctx))
+end
+
+function compute_weighted_frequencies(Z::Matrix{Int8}, q::Integer, θ)
+    N, M = size(Z)
+    q == maximum(Z) || throw(ArgumentError("q=$q does not match maximum(Z)"))
+    n = (q - 1) * N
+    Pi_true = Vector{Float64}(undef, n); Pij_true = Matrix{Float64}(undef, n, n); W = Vector{Float64}(undef, M)
+    Meff = Ref(0.0); θused = Ref(0.0); qout = Ref(Int32(0))
+    ctx = context()
+    _check(ctx, ccall((:gdca_compute_weighted_frequencies, libgdca), Int32,
+                      (Ptr{Cvoid}, Ptr{Int8}, Int64, Int64, Float64, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64},
+                       Ref{Float64}, Ref{Int32}),
+                      ctx.handle, Z, N, M, θ === :auto ? -1.0 : Float64(θ), Pi_true, Pij_true, Meff, W, θused, qout))
+    return Pi_true, Pij_true, Meff[], W
+end
+
+function add_pseudocount(Pi_true::Vector{Float64}, Pij_true::Matrix{Float64}, pc::Float64, q::Integer)
+    n = length(Pi_true)
+    Pi = similar(Pi_true); Pij = similar(Pij_true)
+    ctx = context()
+    _check(ctx, ccall((:gdca_add_pseudocount, libgdca), Int32,
+                      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Float64}, Ptr{Float64}),
+                      ctx.handle, Pi_true, Pij_true, n, q, pc, Pi, Pij))
+    return Pi, Pij
+end
+
+function compute_C(Pi::Vector{Float64}, Pij::Matrix{Float64})        # src/GaussDCA.jl:76
+    n = length(Pi)
+    C = similar(Pij)
+    ctx = context()
+    _check(ctx, ccall((:gdca_compute_C, libgdca), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                      ctx.handle, Pi, Pij, n, C))
+    return C
+end
+
+function _score(mJ::Matrix{Float64}, C, q::Integer, which::Int32)
+    n = size(mJ, 1)
+    N = div(n, q - 1)
+    S = Matrix{Float64}(undef, N, N)
+    ctx = context()
+    _check(ctx, ccall((:gdca_score, libgdca), Int32,
+                      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Float64}),
+                      ctx.handle, mJ, C === nothing ? C_NULL : C, n, q, which, S))
+    return S
+end
+compute_FN(mJ::Matrix{Float64}, q::Integer) = _score(mJ, nothing, q, Int32(0))                         # src/GaussDCA.jl:39
+compute_DI_gauss(mJ::Matrix{Float64}, C::Matrix{Float64}, q::Integer) = _score(mJ, C, q, Int32(1))     # src/GaussDCA.jl:37
+
 end # module

@@ -100,6 +100,15 @@ int32_t gdca_compute_weights(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t 
  * by the library.  C is n x n, Pi (with pseudocount) is n; Pi may be NULL. */
 int32_t gdca_compute_covariance(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, const double *W, double meff,
                                 double pseudocount, double *C, double *Pi, int32_t *q_out);
+/* The same stage in DCAUtils' own pieces, for hosts that use them one by one:
+ * compute_weighted_frequencies(Z, q, theta) -> Pi_true [n], Pij_true [n x n, full symmetric], Meff, W (call site
+ * src/GaussDCA.jl:28; W, theta_used, q_out may be NULL); add_pseudocount(Pi_true, Pij_true, pc, q) -> Pi, Pij (:30);
+ * compute_C(Pi, Pij) = Pij - Pi Pi' (:32,:76).  The fused gdca_compute_covariance gives the same C in one pass. */
+int32_t gdca_compute_weighted_frequencies(gdca_ctx *ctx, const int8_t *Z, int64_t L, int64_t M, double theta, double *Pi_true,
+                                          double *Pij_true, double *meff, double *W, double *theta_used, int32_t *q_out);
+int32_t gdca_add_pseudocount(gdca_ctx *ctx, const double *Pi_true, const double *Pij_true, int64_t n, int32_t q, double pseudocount,
+                             double *Pi, double *Pij);
+int32_t gdca_compute_C(gdca_ctx *ctx, const double *Pi, const double *Pij, int64_t n, double *C);
 /* mJ = inv(cholesky(C)) (src/GaussDCA.jl:34).  info: 0 or failing leading minor (1-based). */
 int32_t gdca_inverse(gdca_ctx *ctx, const double *C, int64_t n, double *mJ, int32_t *info);
 /* compute_FN (src/GaussDCA.jl:39) / compute_DI_gauss (:37).  C is only read for DI (may be NULL for FROB).

@@ -464,3 +464,31 @@ def test_site_reordering_keeps_counts_exact_on_pfam_like_columns(pkg, orc, ctx):
         w = pkg.compute_weights(Z, theta, ctx=ctx, full=True)
         assert w["theta"] == tho and w["thresh"] == thresh
         assert np.array_equal(w["counts"], counts) and w["Meff"] == Meff
+
+
+# ----------------------------------------------------------------------------- DCAUtils-shaped staged pieces
+@pytest.mark.parametrize("L,M,theta", [(53, 300, "auto"), (40, 700, 0.3), (17, 90, 0.0)])
+def test_weighted_frequencies_pseudocount_and_C_pieces(pkg, orc, ctx, L, M, theta):
+    """compute_weighted_frequencies / add_pseudocount / compute_C one by one (src/GaussDCA.jl:28-32) against the oracle,
+    and against the fused covariance stage: the pieces compose to the same C."""
+    Z = orc.synth_alignment(L, M, seed=5 + L + M)
+    q = int(Z.max())
+    Pi_o, Pij_o, Meff_o, W_o, info = orc.compute_weighted_frequencies(Z, q, theta)
+    Pi_t, Pij_t, Meff, W = pkg.compute_weighted_frequencies(Z, q, theta, ctx=ctx)
+    assert Meff == Meff_o and np.array_equal(W, W_o)
+    assert np.array_equal(Pij_t, Pij_t.T)
+    assert normwise(Pi_t, Pi_o) <= 1e-14 and normwise(Pij_t, Pij_o) <= 1e-14
+    for pc in (0.8, 0.2, 0.0, 1.0):
+        Pi_po, Pij_po = orc.add_pseudocount(Pi_o, Pij_o, pc, q)
+        Pi_p, Pij_p = pkg.add_pseudocount(Pi_o, Pij_o, pc, q, ctx=ctx)
+        assert normwise(Pi_p, Pi_po) <= 1e-15 and normwise(Pij_p, Pij_po) <= 1e-15
+        C_o = orc.compute_C(Pi_po, Pij_po)
+        C_p = pkg.compute_C(Pi_po, Pij_po, ctx=ctx)
+        assert normwise(C_p, C_o) <= 1e-15
+        # the pieces chained on the GPU == the fused stage
+        C_chain = pkg.compute_C(*pkg.add_pseudocount(Pi_t, Pij_t, pc, q, ctx=ctx), ctx=ctx)
+        C_fused, _, qf = pkg.compute_covariance(Z, W, Meff, pc, ctx=ctx)
+        assert qf == q
+        assert normwise(C_chain, C_fused) <= 1e-13
+    with pytest.raises(Exception):
+        pkg.add_pseudocount(Pi_o, Pij_o, 1.5, q, ctx=ctx)
