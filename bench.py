@@ -269,6 +269,8 @@ def main():
     barrier()
     launches2 = lib.gdca_dev_kernel_launches(ctx.h)
     clocks = sampler.stop()
+    cov_ms = ctypes.c_float()
+    ctx.check(lib.gdca_dev_cov_kernel_ms(ctx.h, ctypes.byref(cov_ms)))   # cov_rows_kernel of the last timed step
     ms = sum(a.elapsed_time(b) for a, b in ev) / K
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
@@ -414,6 +416,34 @@ def main():
             "chol_inv_frac_of_dmma_peak": (n ** 3 / t_chol / 1e12) / dmma.value if t_chol else None,
         }
 
+    # ---- one roofline entry per hot kernel; "roofline" = the kernel with the largest share of the step
+    roof_kernels = None
+    if world == 1 and stages is not None:
+        sm_clk = (clocks.get("sm_mhz") or pk.get("sm_max_mhz") or 1965.0) * 1e6
+        smem_peak = 148 * 128 * sm_clk / 1e12                       # TB/s: 128 B/clk/SM shared-memory crossbar
+        t_cv = cov_ms.value / 1e3
+        rmw = M * L * (L + 1) // 2                                   # FP64 additions = 8-byte smem read + 8-byte write each
+        cov_entry = {
+            "kernel": "cov_rows_kernel<2> (weighted one-hot covariance as M*L(L+1)/2 private shared-memory FP64 adds)",
+            "bound": "shared_memory", "achieved": 16 * rmw / t_cv / 1e12, "peak": smem_peak, "unit": "TB/s",
+            "frac": 16 * rmw / t_cv / 1e12 / smem_peak,
+            "peak_source": "148 SMs x 128 B/clk (B300_MICROARCH.md shared-memory crossbar) x SM clock under load",
+            "ms_per_launch": cov_ms.value, "adds_per_launch": rmw,
+            "fp64_equivalent_dense_tflops": M * n * (n + 1) / t_cv / 1e12,
+            "traffic": ncu_traffic("cov_rows_kernel<2>") if args.workload == "C" else None,
+            "hbm": {"achieved": (L * M + 8 * n * n / 2) / t_cv / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                    "note": "compulsory bytes (recoded alignment once + upper half of C once); not the limiter"},
+            "note": "ncu (profiles/r1_top_kernels.md): 0.79 of the 1 wavefront/clk/SM shared-memory pipe incl. staging",
+        }
+        inv_entry = {
+            "kernel": "dgemm_kernel<*> + diag_block_kernel (blocked Cholesky, trtri by recursive doubling, lauum: ~275 launches)",
+            "bound": "fp64_tensor", "achieved": n ** 3 / t_chol / 1e12, "peak": dmma.value, "unit": "TFLOP/s",
+            "frac": (n ** 3 / t_chol / 1e12) / dmma.value, "peak_source": "measured live: gdca_probe_peaks DMMA.8x8x4 rate",
+            "ms_per_step": t_chol * 1e3,
+        }
+        roof_kernels = [cov_entry, roof, inv_entry]
+        roof = cov_entry if cov_ms.value >= roof.get("ms_per_launch", 0) else roof
+
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(L, M, score, pc)
@@ -430,7 +460,7 @@ def main():
         "theta": stats["theta"] if world == 1 else None, "thresh": stats["thresh"] if world == 1 else None,
         "meff": stats["meff"] if world == 1 else None, "top_pair": top,
         "e2e": e2e, "gpu_launches": int(launches2 - launches1),
-        "clocks": clocks, "roofline": roof, "stages": stages, "cpu_baseline": cb,
+        "clocks": clocks, "roofline": roof, "roofline_kernels": roof_kernels, "stages": stages, "cpu_baseline": cb,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

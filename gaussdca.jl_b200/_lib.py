@@ -78,6 +78,7 @@ SIGNATURES = {
     "gdca_dev_pair_sample": (_i32, [_p, _i32]),
     "gdca_set_tc_filter": (_i32, [_p, _i32]),
     "gdca_dev_tc_filter": (_i32, [_p, _i64, _p, _p, _i64]),
+    "gdca_dev_cov_kernel_ms": (_i32, [_p, ctypes.POINTER(ctypes.c_float)]),
     "gdca_set_tc_filter_bits": (_i32, [_p, _i32]),
     "gdca_set_tc_filter_multicast": (_i32, [_p, _i32]),
     "gdca_tc_filter_tile_order": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _pi64]),

@@ -233,6 +233,8 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaEventCreate(&ctx->ev_sweep0)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreate(&ctx->ev_filter)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreate(&ctx->ev_sweep1)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreate(&ctx->ev_cov0)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreate(&ctx->ev_cov1)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dNItems, sizeof(int))) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_TC_FILTER")) {
     const int m = atoi(env);
@@ -259,7 +261,7 @@ void gdca_destroy(gdca_ctx *ctx) {
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  for (cudaEvent_t e : {ctx->ev_sweep0, ctx->ev_filter, ctx->ev_sweep1})
+  for (cudaEvent_t e : {ctx->ev_sweep0, ctx->ev_filter, ctx->ev_sweep1, ctx->ev_cov0, ctx->ev_cov1})
     if (e) cudaEventDestroy(e);
   if (ctx->ev_fact) cudaEventDestroy(ctx->ev_fact);
   if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
@@ -428,6 +430,17 @@ int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_ti
   }
   if (ms_filter) *ms_filter = a;
   if (ms_exact) *ms_exact = b;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_cov_kernel_ms(gdca_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cudaEventElapsedTime(ms, ctx->ev_cov0, ctx->ev_cov1) != cudaSuccess) {
+    cudaGetLastError();
+    *ms = 0.f;
+  }
   return GDCA_OK;
 }
 

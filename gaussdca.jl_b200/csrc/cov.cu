@@ -152,7 +152,6 @@ struct CovParams {
   long long L, M, n, ld, Lq;
   int q, s, nchunks;
   int rank, world;
-  int raw;    // 1: write Pij_true (no pseudocount, no - Pi Pi'): DCAUtils compute_weighted_frequencies
   double pc;
 };
 
@@ -165,7 +164,7 @@ template <> struct ZLoad<4> { typedef unsigned int type; };
 
 // CTA (row r = (i,a), chunk c): sites [start + c*CH, start + (c+1)*CH), CH = JT*SPT, start = i rounded down to a
 // warp's worth of sites (32*SPT).  Thread t owns the SPT adjacent sites start + c*CH + SPT*t + u.
-template <int SPT>
+template <int SPT, bool RAW>
 __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
   constexpr int CH = JT * SPT;
   extern __shared__ double acc[];      // [q][SPT][JT]; slot s is the dump for the gap state / padding
@@ -239,7 +238,7 @@ __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
       pij = omp * ptrue + ((b == a - 1) ? pcq : 0.0);
     else
       pij = omp * ptrue + pcqq;
-    Crow[c] = P.raw ? ptrue : pij - pir * P.Pi[c];
+    Crow[c] = RAW ? ptrue : pij - pir * P.Pi[c];
   }
 }
 
@@ -400,11 +399,17 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw) {
   P.rank = ctx->shard_rank;
   P.world = ctx->shard_world;
   P.pc = pc;
-  P.raw = raw ? 1 : 0;
   const size_t smem = (size_t)ctx->q * SPT * JT * sizeof(double);
-  GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cov_rows_kernel<SPT><<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
+  // RAW (compile time): write Pij_true (no pseudocount, no - Pi Pi') for DCAUtils compute_weighted_frequencies
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov0, ctx->stream));
+  if (raw)
+    cov_rows_kernel<SPT, true><<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
+  else
+    cov_rows_kernel<SPT, false><<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
   GDCA_LAUNCH_CHECK(ctx);
+  GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov1, ctx->stream));
   ctx->pseudocount = pc;
   ctx->have_cov = true;
   ctx->have_inv = false;

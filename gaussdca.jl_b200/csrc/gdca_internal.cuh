@@ -76,6 +76,7 @@ struct gdca_ctx {
   double tc_filter_l2_bytes = 0.0;                 // operand bytes its TMA loads moved
   long long tc_filter_tiles = 0;
   cudaEvent_t ev_sweep0 = nullptr, ev_filter = nullptr, ev_sweep1 = nullptr;  // filter / exact sweep split
+  cudaEvent_t ev_cov0 = nullptr, ev_cov1 = nullptr;                            // around cov_rows_kernel alone
 
   // ---- peer memory (one process per GPU): IPC-mapped counts / C buffers of the other ranks ----
   bool peers_ready = false;

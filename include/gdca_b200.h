@@ -156,6 +156,8 @@ int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t rank, int32_t
  * flop (1e12) and TMA operand bytes; 128x128 blocks that went through the exact sweep; device ms of the two parts. */
 int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
                             int64_t *swept_blocks, float *ms_filter, float *ms_exact, double *filter_l2_bytes);
+/* device ms of the last cov_rows_kernel launch alone (the covariance stage also runs small preparation kernels) */
+int32_t gdca_dev_cov_kernel_ms(gdca_ctx *ctx, float *ms);
 /* mode-0 sweep over every stride-th tile of this shard (cheap estimate of the mean identity). */
 int32_t gdca_dev_pair_sample(gdca_ctx *ctx, int32_t stride);
 /* partial results of this shard, device pointers: u64[2] {hamming sum, pairs visited} (after a mode-1 sweep
