@@ -142,8 +142,10 @@ int32_t gdca_k_pack(gdca_ctx *ctx);                       // pack.cu: dZ -> dPla
 int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride);   // pairs.cu
 int32_t gdca_k_tc_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld);  // tcfilter.cu
 static inline bool gdca_tc_filter_wanted(const gdca_ctx *ctx) {
-  // auto: the filter pays once the sweep is more than a few tiles per SM
-  return ctx->tc_filter_mode == 2 || (ctx->tc_filter_mode == 1 && ctx->M >= 16384);
+  // auto: the filter pays once the sweep is more than a few tiles per SM; its T x T mask array and work list (T = Mpad/128)
+  // stay below ~3 GB up to M = 2M sequences -- beyond that the plain sweep over all blocks runs
+  const bool fits = ctx->Mpad / GDCA_TILE <= 16384;
+  return fits && (ctx->tc_filter_mode == 2 || (ctx->tc_filter_mode == 1 && ctx->M >= 16384));
 }
 int32_t gdca_k_finish_weights(gdca_ctx *ctx, int which);  // weights.cu
 int32_t gdca_k_build_lists(gdca_ctx *ctx);                // cov.cu: per-site lists of sequence ids grouped by state

@@ -14,6 +14,9 @@
 //     tile for L <= 512 -> one barrier per tile); the ring runs across tile boundaries, so the next
 //     tile is in flight while this one is computed.
 //   * only tiles bi <= bj of the symmetric pair matrix are visited; a hit credits both sequences.
+//   * production (mode 1, M >= 16384): the work list is NOT all tiles but the blocks the tensor-core prefilter
+//     (tcfilter.cu) could not prove neighbour-free, each with a 16-bit mask of its 32 x 32 cells; a warp whose sub-tile
+//     holds no flagged cell skips the block.  Counts are identical with and without the prefilter.
 //   * persistent grid (one CTA per SM), items strided over (rank, world) for multi-GPU sharding; with peer
 //     buffers imported (gdca_dev_peer_import) the epilogue adds the (rare) hits into EVERY rank's counters with
 //     peer atomics over NVLink -- the all-reduce of the counts is fused into the sweep, no collective follows.

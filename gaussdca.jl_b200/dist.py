@@ -6,8 +6,10 @@ sum with zeros (results are bit-identical for any number of ranks):
 
   theta :auto  no exchange: every rank holds the alignment and computes the exact identity sum from per-site
                state histograms (O(M L)).
-  pair sweep   tiles (bi <= bj) of the M x M pair matrix dealt round-robin to ranks; every rank holds the
-               whole packed alignment.  Exchange FUSED into the kernel: the (rare) neighbour hits are added into
+  pair sweep   rank r owns the 128-sequence row blocks bi = r (mod world) of the upper-triangular M x M pair matrix:
+               its tiles of the tensor-core prefilter and the exact sweep of the blocks they flag (without the
+               prefilter: tiles bi <= bj dealt round-robin); every rank holds the whole packed alignment.
+               Exchange FUSED into the kernel: the (rare) neighbour hits are added into
                every rank's int32 counters with peer atomics over NVLink (CUDA-IPC mapped buffers).
   covariance   output rows dealt to ranks by site (i mod world).  Exchange FUSED into the kernel: every rank
                stores its rows straight into rank 0's C over NVLink (disjoint rows, no reduction needed).
