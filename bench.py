@@ -378,11 +378,12 @@ def main():
             # dominant kernel of the sweep: the tcgen05 prefilter.  algorithmic flop = 2 * 128 * BN * Kpad per tile x tiles
             fp4 = filt.value == 4
             bf16 = pk.get("bf16_tflops")
-            tc_peak = 9000.0 if fp4 else 4500.0     # nominal dense FP4 / FP8 (B200_PROFILING.md table)
+            tc_peak = 9000.0 if fp4 else 4500.0     # nominal dense FP4 / FP8 = INT8 (B200_PROFILING.md table)
             scaled = (4.0 if fp4 else 2.0) * bf16 if bf16 else None
             t_f = ms_f.value / 1e3
             roof = {
                 "kernel": ("tc_filter_kernel<fp4> (tcgen05 kind::mxf4.block_scale 128x224x64" if fp4 else
+                           "tc_filter_kernel<int8> (tcgen05 kind::i8 128x256x32" if filt.value == 80 else
                            "tc_filter_kernel<fp8> (tcgen05 kind::f8f6f4 128x256x32") + ", TMA ring, TMEM epilogue)"
                           + ("" if world == 1 else f", shard {rank} of {world}"),
                 "bound": "tensor", "achieved": f_tflop.value / t_f, "peak": tc_peak, "unit": "TFLOP/s",

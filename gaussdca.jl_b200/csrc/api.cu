@@ -240,7 +240,10 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
     const int m = atoi(env);
     if (m >= 0 && m <= 2) ctx->tc_filter_mode = m;
   }
-  if (const char *env = getenv("GDCA_TC_FILTER_BITS")) ctx->tc_filter_fp4 = atoi(env) != 8;
+  if (const char *env = getenv("GDCA_TC_FILTER_BITS")) {
+    const int b = atoi(env);
+    if (b == 4 || b == 8 || b == 80) ctx->tc_filter_bits = b;
+  }
   if (const char *env = getenv("GDCA_TC_MULTICAST")) ctx->tc_filter_want_multicast = atoi(env) != 0;
   *out = ctx;
   return GDCA_OK;
@@ -364,8 +367,9 @@ int32_t gdca_set_tc_filter(gdca_ctx *ctx, int32_t mode) {
 
 int32_t gdca_set_tc_filter_bits(gdca_ctx *ctx, int32_t bits) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
-  if (bits != 4 && bits != 8) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_tc_filter_bits: bits must be 4 or 8");
-  ctx->tc_filter_fp4 = bits == 4;
+  if (bits != 4 && bits != 8 && bits != 80)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_tc_filter_bits: bits must be 4 (e2m1), 8 (e4m3) or 80 (int8)");
+  ctx->tc_filter_bits = bits;
   return GDCA_OK;
 }
 
@@ -412,7 +416,7 @@ int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_ti
   if (filter_tiles) *filter_tiles = f ? ctx->tc_filter_tiles : 0;
   if (filter_tflop) *filter_tflop = f ? ctx->tc_filter_tflop : 0.0;
   if (filter_l2_bytes) *filter_l2_bytes = f ? ctx->tc_filter_l2_bytes : 0.0;
-  if (filtered && f) *filtered = ctx->tc_filter_fp4 ? 4 : 8;
+  if (filtered && f) *filtered = ctx->tc_filter_bits;
   const int64_t T = ctx->Mpad / GDCA_TILE;
   int64_t blocks = T * (T + 1) / 2 / ctx->shard_world;
   if (f) {

@@ -66,9 +66,9 @@ struct gdca_ctx {
   int2 *dItems = nullptr; size_t capItems = 0;     // compacted (bi, bj) list of blocks with a non-empty mask
   uint32_t *dItemMask = nullptr; size_t capItemMask = 0;  // their masks
   int *dNItems = nullptr;                          // [1] its length
-  int have_V = 0;                                  // 0: dV stale; 8 / 4: dV holds the FP8 / FP4 encoding of the loaded alignment
+  int have_V = 0;                                  // 0: dV stale; 8 / 4 / 80: dV holds the FP8 / FP4 / INT8 encoding of the loaded alignment
   int tc_filter_mode = 1;                          // 0 off, 1 auto (large M), 2 always (tests)
-  bool tc_filter_fp4 = true;                       // operand type of the filter: e4m3 (kind::f8f6f4) or e2m1 (kind::mxf4)
+  int tc_filter_bits = 4;                          // operands of the filter: 4 = e2m1 (kind::mxf4), 8 = e4m3 (kind::f8f6f4), 80 = int8 (kind::i8)
   bool tc_filter_want_multicast = true;            // 2-CTA clusters + TMA multicast of the B tile (env GDCA_TC_MULTICAST=0: off)
   bool tc_filter_multicast = false;                // last filter launch used 2-CTA clusters with TMA multicast
   bool last_sweep_filtered = false;

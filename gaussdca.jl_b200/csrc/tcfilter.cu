@@ -42,8 +42,11 @@ constexpr int TC_THREADS = 192;       // warp 0 TMA producer, warp 1 MMA issuer,
 constexpr int TMEM_COLS = 512;
 constexpr int BAND = 16;             // row blocks per band of the tile order
 
-template <bool FP4>
+enum Operand { OP_FP8 = 0, OP_FP4 = 1, OP_I8 = 2 };  // e4m3 / packed e2m1 / signed int8 (exact S32 accumulation)
+
+template <int OP>
 struct Cfg {
+  static constexpr bool FP4 = OP == OP_FP4;
   static constexpr int BN = FP4 ? 224 : 256;        // tile columns (sequences)
   static constexpr int A_BYTES = BM * BK;           // 16 KB
   static constexpr int B_BYTES = BN * BK;           // 28 / 32 KB
@@ -54,9 +57,11 @@ struct Cfg {
   // instruction descriptors (cute::UMMA::InstrDescriptor / InstrDescriptorBlockScaled bit layout), both operands K-major:
   //   f8f6f4:          D=F32 (bit 4), A=B=E4M3 (0), N>>3 at bit 17, M>>4 at bit 24
   //   mxf4 block32:    A=B=E2M1 (1 at bits 7 and 10), scale format UE8M0 (bit 23), N>>3 at bit 17, M>>4 at bit 24, K=64
+  //   i8:              D=S32 (2 at bit 4), A=B=signed INT8 (1 at bits 7 and 10)
   static constexpr uint32_t IDESC =
       FP4 ? ((1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | (1u << 23) | ((uint32_t)(BM >> 4) << 24))
-          : ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24));
+      : OP == OP_I8 ? ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24))
+                    : ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24));
 };
 
 struct FilterParams {
@@ -154,6 +159,14 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t d
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
                                           uint32_t tmem_sfa, uint32_t tmem_sfb) {
   asm volatile(
@@ -235,10 +248,11 @@ static_assert((BAND & (BAND - 1)) == 0, "BAND must be a power of two");
 // tile and one half of the B tile; the half is TMA-multicast into both CTAs (-32 % L2->SM operand traffic at 128 x 224).  A
 // shared-memory stage is therefore written by both CTAs' producers: its empty barrier counts the tcgen05.commit of BOTH
 // CTAs (multicast commit), its full barrier the bytes of all three boxes.
-template <bool FP4, bool MC>
+template <int OP, bool MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_filter_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, FilterParams P) {
-  using C = Cfg<FP4>;
+  using C = Cfg<OP>;
+  constexpr bool FP4 = C::FP4;
   const uint32_t crank = MC ? cluster_ctarank() : 0u;
   constexpr int BN = C::BN;
   constexpr int NSTAGE = C::NSTAGE;
@@ -352,6 +366,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint32_t accumulate = (k > 0) ? 1u : (uint32_t)(kb != 0);
             if (FP4)
               umma_mxf4(tmem_d, da, db, C::IDESC, accumulate, sfa, sfb);
+            else if (OP == OP_I8)
+              umma_i8(tmem_d, da, db, C::IDESC, accumulate);
             else
               umma_f8(tmem_d, da, db, C::IDESC, accumulate);
           }
@@ -390,11 +406,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (P.dump && mine) {
           float *d = P.dump + ((long long)bi * BM + row) * P.dump_ld + col0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) d[j] = OP == OP_I8 ? (float)(int)v[j] : __uint_as_float(v[j]);
         }
         float mx = -3.0e38f;
+        if (OP == OP_I8) {  // S32 accumulators: exact integers, |S| <= 3L < 2^24 converts exactly
+          int mi = (int)0x80000000;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) mi = max(mi, (int)v[j]);
+          mx = (float)mi;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
         const bool hit = __any_sync(0xffffffffu, mx > P.bound);
         const int cb = (int)(col0 >> 7);
         if (hit && lane == 0 && mine && cb >= bi && cb < P.T)
@@ -428,9 +451,9 @@ __device__ __forceinline__ bool simplex_neg(int z, int j) {
   return (c != 0) && (j != c - 1);
 }
 
-// FP8: V[k][3 i + j] as e4m3 (+1.0 = 0x38, -1.0 = 0xB8), one byte per element; zero padding
+// FP8 / INT8: V[k][3 i + j] as e4m3 (+1.0 = 0x38, -1.0 = 0xB8) or int8 (+1 = 0x01, -1 = 0xFF), one byte per element; zero padding
 __global__ void encode_simplex_kernel(const int8_t *__restrict__ Z, long long L, long long M, long long VM, long long Kpad,
-                                      uint32_t *__restrict__ V) {
+                                      uint32_t *__restrict__ V, uint32_t plus, uint32_t minus) {
   const long long words_per_row = Kpad / 4;
   const long long total = VM * words_per_row;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -442,7 +465,7 @@ __global__ void encode_simplex_kernel(const int8_t *__restrict__ Z, long long L,
       for (int e = 0; e < 4; ++e) {
         const int b = 4 * w + e;
         const int site = b / 3, j = b - 3 * site;
-        if (site < L) out |= (simplex_neg((int)Z[k * L + site], j) ? 0xB8u : 0x38u) << (8 * e);
+        if (site < L) out |= (simplex_neg((int)Z[k * L + site], j) ? minus : plus) << (8 * e);
       }
     }
     V[t] = out;
@@ -516,9 +539,11 @@ int32_t make_tensor_map(gdca_ctx *ctx, CUtensorMap *map, void *V, long long VM, 
   return GDCA_OK;
 }
 
-template <bool FP4>
+template <int OP>
 int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
-  using C = Cfg<FP4>;
+  using C = Cfg<OP>;
+  constexpr bool FP4 = C::FP4;
+  constexpr int TAG = FP4 ? 4 : (OP == OP_I8 ? 80 : 8);  // what ctx->dV currently holds
   const long long T = ctx->Mpad / GDCA_TILE;
   const long long NT = (T * BM + C::BN - 1) / C::BN;
   const long long world = ctx->shard_world, rank = ctx->shard_rank;
@@ -532,15 +557,16 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   GDCA_TRY(gdca_reserve(ctx, ctx->dItems, ctx->capItems, (size_t)(T * (T + 1) / 2)));
   GDCA_TRY(gdca_reserve(ctx, ctx->dItemMask, ctx->capItemMask, (size_t)(T * (T + 1) / 2)));
 
-  if (ctx->have_V != (FP4 ? 4 : 8)) {
+  if (ctx->have_V != TAG) {
     const long long words = VM * Kbytes / 4;
     const int grid = (int)((words + 255) / 256 < (long long)ctx->num_sms * 16 ? (words + 255) / 256 : (long long)ctx->num_sms * 16);
     if (FP4)
       encode_simplex4_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dZ, ctx->L, ctx->M, VM, Kbytes, reinterpret_cast<uint32_t *>(ctx->dV));
     else
-      encode_simplex_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dZ, ctx->L, ctx->M, VM, Kbytes, reinterpret_cast<uint32_t *>(ctx->dV));
+      encode_simplex_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dZ, ctx->L, ctx->M, VM, Kbytes, reinterpret_cast<uint32_t *>(ctx->dV),
+                                                           OP == OP_I8 ? 0x01u : 0x38u, OP == OP_I8 ? 0xFFu : 0xB8u);
     GDCA_LAUNCH_CHECK(ctx);
-    ctx->have_V = FP4 ? 4 : 8;
+    ctx->have_V = TAG;
   }
   // 2-CTA clusters with TMA multicast of the B tile unless switched off (gdca_set_tc_filter_multicast) or the grid is odd
   const bool mc = ctx->tc_filter_want_multicast && (ctx->num_sms % 2 == 0);
@@ -580,9 +606,9 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
     return GDCA_OK;
   };
   if (mc)
-    GDCA_TRY(launch(tc_filter_kernel<FP4, true>, TC_THREADS, true));
+    GDCA_TRY(launch(tc_filter_kernel<OP, true>, TC_THREADS, true));
   else
-    GDCA_TRY(launch(tc_filter_kernel<FP4, false>, TC_THREADS, false));
+    GDCA_TRY(launch(tc_filter_kernel<OP, false>, TC_THREADS, false));
   GDCA_LAUNCH_CHECK(ctx);
   ctx->tc_filter_multicast = mc;
 
@@ -610,7 +636,7 @@ extern "C" int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t ra
                                              int32_t *out, int64_t cap_rows, int64_t *n_rows) {
   if (T < 1 || (bits != 4 && bits != 8) || world < 1 || rank < 0 || rank >= world || grid < 1 || cta < 0 || cta >= grid || !n_rows)
     return GDCA_ERR_INVALID_ARG;
-  const int colw = bits == 4 ? Cfg<true>::BN : Cfg<false>::BN;
+  const int colw = bits == 4 ? Cfg<OP_FP4>::BN : Cfg<OP_FP8>::BN;
   FilterParams P{};
   P.T = T;
   P.NT = (int)(((long long)T * BM + colw - 1) / colw);
@@ -638,5 +664,9 @@ extern "C" int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t ra
 // dump (device, optional): S of every visited tile.
 int32_t gdca_k_tc_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   if (!ctx->have_alignment) return gdca_fail(ctx, GDCA_ERR_STATE, "tc_filter: no alignment loaded");
-  return ctx->tc_filter_fp4 ? run_filter<true>(ctx, thresh, dump, dump_ld) : run_filter<false>(ctx, thresh, dump, dump_ld);
+  switch (ctx->tc_filter_bits) {
+    case 8: return run_filter<OP_FP8>(ctx, thresh, dump, dump_ld);
+    case 80: return run_filter<OP_I8>(ctx, thresh, dump, dump_ld);
+    default: return run_filter<OP_FP4>(ctx, thresh, dump, dump_ld);
+  }
 }

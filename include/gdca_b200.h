@@ -136,8 +136,8 @@ int32_t gdca_dev_pair_pass(gdca_ctx *ctx, int32_t mode, int64_t thresh);
  * distance); only the 128 x 128 blocks with a cell left go through the exact bit-plane sweep, and only the warps of
  * that sweep that own such a cell do any work.  Counts are identical in every mode.
  * mode 0: off; 1: auto (default; on for M >= 16384; env GDCA_TC_FILTER overrides the default); 2: always.
- * bits 4 (default): packed e2m1 operands, kind::mxf4 with unit block scales; 8: e4m3 operands, kind::f8f6f4
- * (env GDCA_TC_FILTER_BITS overrides the default). */
+ * bits 4 (default): packed e2m1 operands, kind::mxf4 with unit block scales; 8: e4m3 operands, kind::f8f6f4;
+ * 80: signed int8 operands, kind::i8 with S32 accumulators (env GDCA_TC_FILTER_BITS overrides the default). */
 int32_t gdca_set_tc_filter(gdca_ctx *ctx, int32_t mode);
 int32_t gdca_set_tc_filter_bits(gdca_ctx *ctx, int32_t bits);
 /* on (default): the prefilter runs as 2-CTA clusters that share the column tile by TMA multicast; off: independent CTAs
@@ -152,7 +152,7 @@ int32_t gdca_dev_tc_filter(gdca_ctx *ctx, int64_t thresh, uint32_t *flags_host, 
  * {bi, cj, valid, peer_valid} (4 x int32) -- the kernel's own iterator compiled for the host, for CPU tests. */
 int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t rank, int32_t world, int32_t grid, int32_t cta,
                                   int32_t *out, int64_t cap_rows, int64_t *n_rows);
-/* What the last mode-1 sweep did: *filtered = 0, or the operand bits (8 / 4) of the prefilter that ran; its tiles,
+/* What the last mode-1 sweep did: *filtered = 0, or the operand code (4 / 8 / 80) of the prefilter that ran; its tiles,
  * flop (1e12) and TMA operand bytes; 128x128 blocks that went through the exact sweep; device ms of the two parts. */
 int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
                             int64_t *swept_blocks, float *ms_filter, float *ms_exact, double *filter_l2_bytes);

@@ -20,12 +20,12 @@ def projected_scores(Z):
     return 4 * ident - L
 
 
-# operands: e4m3 (kind::f8f6f4) / packed e2m1 (kind::mxf4, unit block scales); launch: independent CTAs / 2-CTA clusters
+# operands: e4m3 (kind::f8f6f4) / packed e2m1 (kind::mxf4, unit block scales) / int8 (kind::i8, code 80); launch: independent CTAs / 2-CTA clusters
 # sharing the column tile by TMA multicast
-VARIANTS = [(8, 0), (4, 0), (8, 1), (4, 1)]
+VARIANTS = [(8, 0), (4, 0), (8, 1), (4, 1), (80, 1)]
 
 
-@pytest.fixture(params=VARIANTS, ids=["fp8", "fp4", "fp8-multicast", "fp4-multicast"])
+@pytest.fixture(params=VARIANTS, ids=["fp8", "fp4", "fp8-multicast", "fp4-multicast", "int8-multicast"])
 def bits(request, ctx):
     b, mc = request.param
     ctx.check(ctx.lib.gdca_set_tc_filter_bits(ctx.h, b))
