@@ -2,28 +2,31 @@
 //
 // Part of the replacement of DCAUtils compute_weights (un-vendored; reference call site src/GaussDCA.jl:28):
 //   count[k] = 1 + #{l != k : hamming(k,l) < thresh}.
-// On real and synthetic alignments almost every pair is far beyond thresh.  This kernel PROVES that for whole
-// 128 x 128 blocks of sequence pairs on the tensor cores, and only the blocks it cannot clear go to the exact
-// bit-plane sweep (pairs.cu).  The result is unchanged by construction:
+// On real and synthetic alignments almost every pair is far beyond thresh.  This kernel PROVES that for whole 32 x 32 cells
+// of sequence pairs on the tensor cores; only the 128 x 128 blocks with a cell left go to the exact bit-plane sweep
+// (pairs.cu), and there only the warps that own such a cell work.  The result is unchanged by construction:
 //
 //   * every residue state is mapped to one of 4 classes (state & 3) and each class to a vertex of the regular
 //     simplex in {-1,+1}^3:  c0=(+,+,+) c1=(+,-,-) c2=(-,+,-) c3=(-,-,+);  v_a . v_b = 3 if a == b else -1.
 //   * for two sequences  S = sum_i v(Z_ik) . v(Z_il) = 4 * ident_proj - L,  ident_proj = #sites with equal CLASS
 //     >= ident (equal states have equal classes), so  hamming_proj = (3L - S) / 4  <=  hamming.
-//   * a pair with hamming_proj >= thresh cannot be a neighbour.  A block is cleared iff that holds for all its
-//     pairs, i.e. iff max S <= 3L - 4 thresh.  S is an exact integer (|S| <= 3L < 2^24, FP32 accumulation of
-//     +-1 products), so the test is exact and conservative: flagged blocks are a superset of the blocks that
-//     contain a neighbour pair; the sweep counts exactly in those.
+//   * a pair with hamming_proj >= thresh cannot be a neighbour.  A cell is cleared iff that holds for all its pairs, i.e.
+//     iff max S <= 3L - 4 thresh.  S is an exact integer (|S| <= 3L < 2^24: FP32 accumulation of +-1 products, or S32
+//     for the INT8 variant), so the test is exact and conservative: flagged cells are a superset of the cells that contain
+//     a neighbour pair; the sweep counts exactly in those.
 //
-// The M x M x 3L contraction runs as  V V^T  with V = [Mpad][Kpad] e4m3 (+-1.0, 0 padding), K-major:
-//   * one persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected
-//     lane), warps 2..5 = epilogue (one TMEM lane quarter each);
-//   * FP8 variant: CTA tile 128 x 256 (UMMA M=128, N=256, K=32, kind::f8f6f4), V = e4m3 +-1.0, two TMEM accumulator
-//     stages of 256 columns.  FP4 variant: CTA tile 128 x 224 (UMMA M=128, N=224, K=64, kind::mxf4.block_scale.block32,
-//     twice the tensor rate, half the operand bytes), V = packed e2m1 +-1.0, two accumulator stages of 224 columns +
-//     64 columns of UE8M0 scale factors that are all 1.0 (written once with tcgen05.st: every byte is 0x7F, so the
-//     scale-factor layout never matters).  Both: FP32 accumulators in TMEM, K streamed in 128-byte blocks through a
-//     4-stage TMA ring (SWIZZLE_128B), full/empty mbarriers, tcgen05.commit releases the stages;
+// The M x M x 3L contraction runs as  V V^T  with V = [rows][3L padded to whole 128-byte k-blocks], K-major:
+//   * one persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane),
+//     warps 2..5 = epilogue (one TMEM lane quarter each);
+//   * operand variants of one kernel template:
+//       FP4 (default)  packed e2m1 +-1.0, kind::mxf4.block_scale.block32, UMMA 128 x 224 x 64, two accumulator stages of
+//                      224 TMEM columns + 64 columns of UE8M0 scale factors that are all 1.0 (written once with tcgen05.st:
+//                      every byte is 0x7F, so the scale-factor layout never matters); 5-stage TMA ring of 44 KB;
+//       FP8            e4m3 +-1.0, kind::f8f6f4, UMMA 128 x 256 x 32, two stages of 256 columns, 4-stage ring of 48 KB;
+//       INT8           +-1 bytes, kind::i8, S32 accumulators, same shape as FP8;
+//     K is streamed in 128-byte blocks (SWIZZLE_128B), full/empty mbarriers, tcgen05.commit releases the stages;
+//   * default launch: clusters of 2 CTAs on neighbouring row blocks of the same column tile; each CTA fetches its A tile and
+//     half of the B tile, the half is TMA-multicast into both (-32 % L2->SM operand bytes);
 //   * the epilogue of tile t (tcgen05.ld, max per 32 x 32 cell, one vote and at most one atomicOr per cell) overlaps
 //     the MMAs of tile t+1.  No C matrix is ever written: the output is a 16-bit cell mask per 128 x 128 block.
 //   * only tiles that touch the upper triangle are visited, in bands of 16 row blocks with the row block varying
