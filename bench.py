@@ -320,6 +320,9 @@ def main():
 
     if rank != 0:
         if dist is not None:
+            # rank 0 still times its shard of the sweep below, and that kernel adds its hits into EVERY rank's counters over
+            # peer memory: keep this rank's buffers alive until rank 0 is through
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -404,6 +407,9 @@ def main():
             roof = {**exact, "traffic": ncu_traffic("pair_sweep_kernel<5, 1>") if world == 1 and args.workload == "C" else None,
                     **common}
         ctx.check(lib.gdca_set_shard(ctx.h, 0, 1))
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()          # releases the other ranks (see above)
         n = 20 * L
         t_cov, t_chol = stage_acc.get("ms_cov", 0) / 1e3, (stage_acc.get("ms_chol", 0) + stage_acc.get("ms_inv", 0)) / 1e3
         stages = None if world > 1 else {
