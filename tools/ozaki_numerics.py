@@ -25,7 +25,7 @@ NB = 128
 def slices(A, w, s):
     """rows of A -> exponents e (A = 2^e * A'), and s digit matrices D_t with A' ~ sum_t D_t 2^(-w (t+1)), |D_t| <= 2^(w-1)."""
     amax = np.max(np.abs(A), axis=1)
-    e = np.where(amax > 0, np.ceil(np.log2(np.maximum(amax, 1e-300))) + 1, 0.0)   # |A'| <= 1/2
+    e = (np.frexp(amax)[1] + 1).astype(np.float64)          # amax = f 2^e0, f in [1/2, 1)  ->  |A / 2^(e0+1)| < 1/2, exactly
     R = A / np.exp2(e)[:, None]
     D = []
     for t in range(s):
