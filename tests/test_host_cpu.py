@@ -196,3 +196,30 @@ def test_julia_wrapper_is_consistent_with_header():
                "min_separation::Integer = 5", "remove_dups::Bool = false"):
         assert kw in jl
     assert "Vector{Tuple{Int,Int,Float64}}" in jl and "PosDefException" in jl
+
+
+def test_rank_writer_is_byte_identical_across_chunk_boundaries(pkg, tmp_path):
+    """gdca_write_rank / gdca_format_rank format rows in parallel chunks of 4096: the bytes must be those of the serial
+    "%i %i %e\\n" loop of printrank (src/GaussDCA.jl:67-74) for any length, including inf / nan / signed zero."""
+    import ctypes
+    from gaussdca_jl_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    n = 3 * 4096 + 17
+    R = np.zeros(n, dtype=_lib.RANK_DTYPE)
+    R["i"] = rng.integers(1, 70000, n)
+    R["j"] = rng.integers(1, 70000, n)
+    R["score"] = rng.standard_normal(n) * 10.0 ** rng.integers(-300, 300, n)
+    R["score"][:5] = [0.0, -0.0, np.inf, -np.inf, np.nan]
+    path = str(tmp_path / "rank.txt")
+    for m in (0, 1, 4095, 4096, 4097, 8192, n):
+        want = "".join("%d %d %e\n" % t for t in zip(R["i"][:m].tolist(), R["j"][:m].tolist(), R["score"][:m].tolist()))
+        assert lib.gdca_write_rank(path.encode(), _lib.ptr(R), m) == 0
+        assert open(path).read() == want, m
+        used = ctypes.c_int64()
+        assert lib.gdca_format_rank(_lib.ptr(R), m, None, 0, ctypes.byref(used)) == 0 and used.value == len(want)
+        buf = ctypes.create_string_buffer(max(1, used.value))
+        assert lib.gdca_format_rank(_lib.ptr(R), m, buf, used.value, ctypes.byref(used)) == 0
+        assert buf.raw[: used.value].decode() == want
+        if m > 1:
+            assert lib.gdca_format_rank(_lib.ptr(R), m, buf, used.value - 1, ctypes.byref(used)) != 0   # buffer too small
