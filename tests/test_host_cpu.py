@@ -223,3 +223,61 @@ def test_rank_writer_is_byte_identical_across_chunk_boundaries(pkg, tmp_path):
         assert buf.raw[: used.value].decode() == want
         if m > 1:
             assert lib.gdca_format_rank(_lib.ptr(R), m, buf, used.value - 1, ctypes.byref(used)) != 0   # buffer too small
+
+
+def test_fasta_reader_fuzz_against_oracle(pkg, orc, tmp_path):
+    """Property test (hypothesis): the C reader (csrc/host_io.cpp) and the oracle's reader agree on randomly generated
+    alignments -- random letters incl. non-standard ones, consistent insert columns ('.' / lowercase), random line wrapping,
+    LF / CRLF, blank lines, random max_gap_fraction; errors are raised by both or by neither."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    upper = "ACDEFGHIKLMNPQRSTVWYBJOUXZ-"
+
+    @st.composite
+    def alignment(draw):
+        ncols = draw(st.integers(1, 40))
+        insert = [draw(st.booleans()) and draw(st.booleans()) for _ in range(ncols)]      # ~25 % insert columns
+        if all(insert):
+            insert[draw(st.integers(0, ncols - 1))] = False
+        nseq = draw(st.integers(1, 12))
+        recs = []
+        for _ in range(nseq):
+            chars = []
+            for c in range(ncols):
+                if insert[c]:
+                    chars.append(draw(st.sampled_from("." + "acdefghiklmnpqrstvwy")))
+                else:
+                    chars.append(draw(st.sampled_from(upper)))
+            recs.append("".join(chars))
+        eol = draw(st.sampled_from(["\n", "\r\n"]))
+        wrap = draw(st.integers(1, 50))
+        text = ""
+        for k, r in enumerate(recs):
+            text += f">s{k} d{eol}"
+            for o in range(0, len(r), wrap):
+                text += r[o:o + wrap] + eol
+            if draw(st.booleans()):
+                text += eol
+        mg = draw(st.sampled_from([0.0, 0.1, 0.5, 0.9, 1.0]))
+        return text, mg
+
+    path = tmp_path / "fuzz.fasta"
+
+    @settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(alignment())
+    def run(case):
+        text, mg = case
+        path.write_bytes(text.encode())
+        try:
+            want = orc.read_fasta_alignment(str(path), mg)
+        except ValueError as e:
+            with pytest.raises(ValueError):
+                pkg.read_fasta_alignment(str(path), mg)
+            assert "none passed" in str(e) or "inconsistent" in str(e) or "aligned" in str(e)
+            return
+        got = pkg.read_fasta_alignment(str(path), mg)
+        assert got.dtype == np.int8 and np.array_equal(got, want)
+        d_got, keep = pkg.remove_duplicate_sequences(got)
+        assert np.array_equal(d_got, orc.remove_duplicate_sequences(want)) and np.array_equal(d_got, got[keep])
+
+    run()
