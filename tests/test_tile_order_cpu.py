@@ -58,3 +58,28 @@ def test_cluster_pairs_walk_in_lock_step(lib, T, bits, world):
         assert np.array_equal(a[:, 1], b[:, 1])                    # same column tile
         assert np.array_equal(a[:, 2], b[:, 3]) and np.array_equal(a[:, 3], b[:, 2])   # each sees the other's validity
         assert np.array_equal(b[:, 0] - a[:, 0], np.full(len(a), world))               # neighbouring rows of the rank
+
+
+def test_projection_bound_is_conservative_for_every_alphabet():
+    """The exactness argument of the prefilter, checked in integers on the CPU: with classes = state & 3 and the simplex code,
+    S = 4 ident_proj - L and hamming_proj = (3L - S)/4 <= hamming for EVERY pair, for every alphabet size q <= 31; hence a
+    neighbour pair (hamming < thresh) always has S > 3L - 4 thresh and its cell can never be cleared."""
+    rng = np.random.default_rng(11)
+    code = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]])     # v_a . v_b = 3 if a == b else -1
+    assert np.array_equal(code @ code.T, 4 * np.eye(4, dtype=int) - 1)
+    for q in (2, 4, 5, 21, 31):
+        for L in (1, 7, 53, 200):
+            M = 60
+            base = rng.integers(1, q + 1, size=(6, L))
+            Z = base[rng.integers(0, 6, M)].copy()
+            mut = rng.random((M, L)) < rng.random((M, 1))                     # per-sequence mutation rates 0..1
+            Z[mut] = rng.integers(1, q + 1, size=int(mut.sum()))
+            V = code[Z & 3].reshape(M, 3 * L)                                 # what encode_simplex*_kernel writes
+            S = V @ V.T
+            ham = (Z[:, None, :] != Z[None, :, :]).sum(-1)
+            ident_proj = ((Z[:, None, :] & 3) == (Z[None, :, :] & 3)).sum(-1)
+            assert np.array_equal(S, 4 * ident_proj - L)
+            ham_proj = (3 * L - S) // 4
+            assert np.array_equal(4 * ham_proj, 3 * L - S) and np.all(ham_proj <= ham)
+            for thresh in (0, 1, L // 4, L // 2, L):
+                assert np.all(S[ham < thresh] > 3 * L - 4 * thresh)
