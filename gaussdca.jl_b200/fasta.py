@@ -16,6 +16,18 @@ def _host_error(lib) -> str:
     return lib.gdca_host_last_error().decode()
 
 
+class _HostBlock:
+    """Owner of a block returned by the C front-end (gdca_free_host on collection)."""
+
+    def __init__(self, lib, address):
+        self._lib, self._address = lib, address
+
+    def __del__(self):
+        if self._address:
+            self._lib.gdca_free_host(ctypes.c_void_p(self._address))
+            self._address = 0
+
+
 def read_fasta_alignment(filename, max_gap_fraction: float) -> np.ndarray:
     """-> Z int8, shape (M, L), C-contiguous: Z[k] is sequence k.  Memory-identical to the reference's
     L x M column-major Matrix{Int8} (src/GaussDCA.jl:20,24)."""
@@ -25,11 +37,10 @@ def read_fasta_alignment(filename, max_gap_fraction: float) -> np.ndarray:
                                        ctypes.byref(L), ctypes.byref(M))
     if st != _lib.GDCA_OK:
         raise ValueError(_host_error(lib))
-    try:
-        buf = (ctypes.c_int8 * (L.value * M.value)).from_address(zp.value)
-        return np.frombuffer(buf, dtype=np.int8).reshape(M.value, L.value).copy()
-    finally:
-        lib.gdca_free_host(zp)
+    # zero-copy: the array views the block the C reader allocated; the block is released when the last view is gone
+    buf = (ctypes.c_int8 * (L.value * M.value)).from_address(zp.value)
+    buf._owner = _HostBlock(lib, zp.value)            # numpy keeps `buf` alive as the array's base object
+    return np.frombuffer(buf, dtype=np.int8).reshape(M.value, L.value)
 
 
 def remove_duplicate_sequences(Z: np.ndarray):
