@@ -64,9 +64,16 @@ int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
   ctx->L = L;
   ctx->M = M;
   GDCA_TRY(gdca_k_maxq(ctx));
-  int q = 0;
-  GDCA_CUDA(ctx, cudaMemcpyAsync(&q, ctx->dQ, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  int qq[2] = {0, 0};
+  GDCA_CUDA(ctx, cudaMemcpyAsync(qq, ctx->dQ, sizeof qq, cudaMemcpyDeviceToHost, ctx->stream));
   GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int q = qq[0];
+  if (qq[1] < 1) {
+    char b[128];
+    snprintf(b, sizeof b, "alignment holds the residue code %d: codes must be >= 1 (A=1 ... Y=20, everything else 21)", qq[1]);
+    ctx->err = b;
+    return GDCA_ERR_INVALID_ARG;
+  }
   if (q >= 32) {
     char b[96];
     snprintf(b, sizeof b, "parameter q=%d is too big (max 31 is allowed)", q);
@@ -88,7 +95,8 @@ int32_t check_LM(gdca_ctx *ctx, const void *Z, int64_t L, int64_t M) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   if (!Z) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "Z is NULL");
   if (L < 1 || M < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "alignment must have L >= 1 and M >= 1");
-  if (L >= 65536) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "L must be < 65536");
+  // pack_planes_kernel parks ceil(L/32) x 5 planes x 128 B of one 32-sequence group in shared memory (<= 227 KB)
+  if (L > GDCA_MAX_L) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "L must be <= 11616 (GDCA_MAX_L, see include/gdca_b200.h)");
   if (M >= (1ll << 31) - GDCA_TILE) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "M must be < 2^31");
   return GDCA_OK;
 }
@@ -129,6 +137,19 @@ int32_t weights_stage(gdca_ctx *ctx, double theta) {
   st.meff = ctx->meff;
   GDCA_TRY(rec(ctx, EV_WEIGHTS));
   return GDCA_OK;
+}
+
+// A staged host-buffer entry point is about to change L / n / q under the loaded alignment: every piece of device state
+// derived from that alignment (lists, planes, weights, filter operands, covariance, inverse) stops being usable, so a later
+// gdca_dev_* call reports GDCA_ERR_STATE instead of mixing the new shape with the old buffers.
+void drop_alignment_state(gdca_ctx *ctx) {
+  ctx->have_alignment = ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  ctx->have_V = 0;
+  if (ctx->dZ_borrowed) {
+    ctx->dZ = nullptr;
+    ctx->capZ = 0;
+    ctx->dZ_borrowed = false;
+  }
 }
 
 float ev_ms(gdca_ctx *ctx, int a, int b) {
@@ -224,7 +245,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fact, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dHam, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc((void **)&ctx->dQ, sizeof(int))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dQ, 2 * sizeof(int))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dMeff, 2 * sizeof(double))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dInfo, sizeof(int))) != cudaSuccess) return fail(e);
   for (int i = 0; i < EV_COUNT; ++i)
@@ -665,6 +686,8 @@ static int32_t run_impl(gdca_ctx *ctx, const int8_t *Z, bool resident, int64_t L
   const int32_t status = body();
   ctx->shard_rank = saved_rank;
   ctx->shard_world = saved_world;
+  // a resident run borrows the caller's device buffer only for the duration of the call (the caller may free it afterwards)
+  if (resident) drop_alignment_state(ctx);
   gdca_stats_t &st = ctx->stats;
   if (status == GDCA_OK) {
     st.ms_h2d = ev_ms(ctx, EV_BEGIN, EV_H2D);
@@ -806,12 +829,12 @@ int32_t gdca_inverse(gdca_ctx *ctx, const double *C, int64_t n, double *mJ, int3
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   if (!C || !mJ || n < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "inverse: C, mJ must not be NULL and n >= 1");
   GDCA_TRY(set_device(ctx));
+  drop_alignment_state(ctx);
   ctx->n = n;
   ctx->npad = (n + GDCA_NB - 1) / GDCA_NB * GDCA_NB;
   GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)ctx->npad * ctx->npad));
   GDCA_TRY(upload_padded(ctx, ctx->dC, ctx->npad, C, n));
   ctx->have_cov = true;
-  ctx->have_alignment = false;
   const int32_t st = gdca_k_inverse(ctx);
   if (info) *info = ctx->stats.posdef_info;
   if (st != GDCA_OK) return st;
@@ -825,12 +848,12 @@ int32_t gdca_score(gdca_ctx *ctx, const double *mJ, const double *C, int64_t n, 
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "score: need 2 <= q <= 31 and n divisible by q-1");
   if (score == GDCA_SCORE_DI && !C) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "score: DI needs C");
   GDCA_TRY(set_device(ctx));
+  drop_alignment_state(ctx);
   ctx->n = n;
   ctx->npad = (n + GDCA_NB - 1) / GDCA_NB * GDCA_NB;
   ctx->q = q;
   ctx->s = q - 1;
   ctx->L = n / (q - 1);
-  ctx->have_alignment = false;
   GDCA_TRY(gdca_reserve(ctx, ctx->dmJ, ctx->capmJ, (size_t)ctx->npad * ctx->npad));
   GDCA_TRY(upload_padded(ctx, ctx->dmJ, ctx->npad, mJ, n));
   if (score == GDCA_SCORE_DI) {
@@ -850,6 +873,7 @@ int32_t gdca_apc(gdca_ctx *ctx, const double *S, int64_t L, double *S_out) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   if (!S || !S_out || L < 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "apc: S, S_out must not be NULL and L >= 2");
   GDCA_TRY(set_device(ctx));
+  drop_alignment_state(ctx);
   ctx->L = L;
   GDCA_TRY(gdca_reserve(ctx, ctx->dS, ctx->capS, (size_t)L * L));
   GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dS, S, (size_t)L * L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -864,6 +888,7 @@ int32_t gdca_ranking(gdca_ctx *ctx, const double *S, int64_t L, int64_t min_sepa
   if (!S || L < 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "ranking: S must not be NULL and L >= 1");
   if (R_len > 0 && !R) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R is NULL");
   GDCA_TRY(set_device(ctx));
+  drop_alignment_state(ctx);
   ctx->L = L;
   GDCA_TRY(gdca_reserve(ctx, ctx->dS2, ctx->capS2, (size_t)L * L));
   GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dS2, S, (size_t)L * L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

@@ -40,6 +40,7 @@ struct GemmP {
   int m, n, k;
   int flags;
   double alpha, beta;
+  const int *info;  // not-SPD flag of the factorisation (or nullptr): once it is set every later launch of the chain returns at once
 };
 
 __device__ __forceinline__ void cp16(void *smem, const void *gmem) {
@@ -124,9 +125,16 @@ __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(GemmP p) {
   // Ring invariant at the top of iteration kt: stages <= kt+1 have landed and are visible to every thread, so the
   // first fragments of stage kt+1 can be fetched while the last DMMAs of stage kt issue -- the barrier and the
   // shared-memory latency no longer sit in front of the tensor pipe.
+  // The reference throws at the failing pivot (cholesky(C), src/GaussDCA.jl:34).  Here the ~250 launches behind a failed diagonal
+  // block are already queued: each of them reads the flag (under the latency of its first operand loads) and leaves.
+  const int failed = p.info ? *reinterpret_cast<const volatile int *>(p.info) : 0;
   load_stage(0);
   load_stage(1);
   load_stage(2);
+  if (failed) {
+    cp_wait<0>();
+    return;
+  }
   double fa[2][8], fb[2][4];  // ping-pong fragment registers (BK/4 is even: every stage starts on buffer 0)
   cp_wait<2>();  // stage 0
   __syncthreads();
@@ -202,6 +210,7 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel(const double *__restr
   __shared__ double rdiag[NB];    // 1 / L[j][j]
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   DIAG_STAMP(0);
+  if (*reinterpret_cast<const volatile int *>(info) != 0) return;  // an earlier block already failed: nothing left to factor
 
   // coalesced load through shared memory (rows contiguous), then pick own elements
   for (int e = tid; e < NB * NB; e += DT) {
@@ -364,7 +373,9 @@ __global__ void mirror_lower_kernel(double *__restrict__ A, long long n, long lo
 }
 
 template <bool AT, bool BT>
-int32_t gemm(gdca_ctx *ctx, const GemmP &p, int batch, cudaStream_t stream = nullptr) {
+int32_t gemm(gdca_ctx *ctx, const GemmP &p_in, int batch, cudaStream_t stream = nullptr) {
+  GemmP p = p_in;
+  p.info = ctx->dInfo;
   if (!stream) stream = ctx->stream;
   if (p.m <= 0 || p.n <= 0 || batch <= 0) return GDCA_OK;
   const size_t smem = (size_t)GSTAGES * 2 * TILE_D * sizeof(double);

@@ -170,10 +170,12 @@ __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
   extern __shared__ double acc[];      // [q][SPT][JT]; slot s is the dump for the gap state / padding
   __shared__ unsigned stage_off[STG];  // row offset k*Lq of the staged sequences
   __shared__ double stage_w[STG];      // W[k]
-  const int r = blockIdx.y;            // output row (i, a)
+  // 1-D grid, row-major over (row, chunk): the same CTA order as a (chunks, rows) grid without its 65535-row limit
+  const int r = (int)(blockIdx.x / (unsigned)P.nchunks);  // output row (i, a)
+  const int chunk = (int)(blockIdx.x - (unsigned)r * (unsigned)P.nchunks);
   const int i = r / P.s, a = r - i * P.s + 1;
   if (P.world > 1 && (i % P.world) != P.rank) return;  // rows are dealt to ranks by site
-  const int start = (i / (32 * SPT)) * (32 * SPT) + blockIdx.x * CH;
+  const int start = (i / (32 * SPT)) * (32 * SPT) + chunk * CH;
   if (start >= P.L) return;
   const int t = threadIdx.x;
   const int j0 = start + SPT * t;                 // first site of this thread
@@ -405,9 +407,9 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw) {
   GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov0, ctx->stream));
   if (raw)
-    cov_rows_kernel<SPT, true><<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
+    cov_rows_kernel<SPT, true><<<(unsigned)((long long)P.nchunks * n), JT, smem, ctx->stream>>>(P);
   else
-    cov_rows_kernel<SPT, false><<<dim3((unsigned)P.nchunks, (unsigned)n), JT, smem, ctx->stream>>>(P);
+    cov_rows_kernel<SPT, false><<<(unsigned)((long long)P.nchunks * n), JT, smem, ctx->stream>>>(P);
   GDCA_LAUNCH_CHECK(ctx);
   GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov1, ctx->stream));
   ctx->pseudocount = pc;

@@ -14,30 +14,42 @@
 // Also here: q = max(Z) (src/GaussDCA.jl:25).
 #include "gdca_internal.cuh"
 
+// out[0] = max(Z), out[1] = min(Z) as SIGNED bytes (Julia's maximum(Z) on a Matrix{Int8}); the caller's pointer may sit
+// at any byte offset (gdca_run_resident takes device views), so a scalar head runs up to the first 16-byte boundary.
 __global__ void maxq_kernel(const int8_t *__restrict__ Z, size_t nbytes, int *__restrict__ out) {
-  int m = 0;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int mx = -128, mn = 127;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t nvec = nbytes / 16;
-  const int4 *Z4 = reinterpret_cast<const int4 *>(Z);
+  size_t head = (16 - ((size_t)Z & 15)) & 15;
+  if (head > nbytes) head = nbytes;
+  const size_t nvec = (nbytes - head) / 16;
+  const int4 *Z4 = reinterpret_cast<const int4 *>(Z + head);
+  unsigned vmx = 0x80808080u, vmn = 0x7f7f7f7fu;  // per-byte signed running max / min
   for (size_t v = i; v < nvec; v += stride) {
-    int4 x = Z4[v];
-    unsigned w[4] = {(unsigned)x.x, (unsigned)x.y, (unsigned)x.z, (unsigned)x.w};
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      // per-byte max via __vmaxu4 against the running max replicated in all bytes
-      unsigned mm = __vmaxu4(w[t], (unsigned)m * 0x01010101u);
-      mm = max(max(mm & 0xff, (mm >> 8) & 0xff), max((mm >> 16) & 0xff, mm >> 24));
-      m = (int)mm;
-    }
+    const int4 x = Z4[v];
+    vmx = __vmaxs4(__vmaxs4(vmx, (unsigned)x.x), __vmaxs4(__vmaxs4((unsigned)x.y, (unsigned)x.z), (unsigned)x.w));
+    vmn = __vmins4(__vmins4(vmn, (unsigned)x.x), __vmins4(__vmins4((unsigned)x.y, (unsigned)x.z), (unsigned)x.w));
   }
-  for (size_t b = nvec * 16 + i; b < nbytes; b += stride) m = max(m, (int)(uint8_t)Z[b]);
-  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    mx = max(mx, (int)(int8_t)(vmx >> (8 * b)));
+    mn = min(mn, (int)(int8_t)(vmn >> (8 * b)));
+  }
+  for (size_t b = i; b < head; b += stride) mx = max(mx, (int)Z[b]), mn = min(mn, (int)Z[b]);
+  for (size_t b = head + nvec * 16 + i; b < nbytes; b += stride) mx = max(mx, (int)Z[b]), mn = min(mn, (int)Z[b]);
+  for (int o = 16; o; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, mx);
+    atomicMin(out + 1, mn);
+  }
 }
 
 int32_t gdca_k_maxq(gdca_ctx *ctx) {
-  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dQ, 0, sizeof(int), ctx->stream));
+  const int init[2] = {-128, 127};
+  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dQ, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
   const size_t nbytes = (size_t)ctx->L * ctx->M;
   maxq_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->dZ, nbytes, ctx->dQ);
   GDCA_LAUNCH_CHECK(ctx);

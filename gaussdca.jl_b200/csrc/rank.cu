@@ -10,14 +10,17 @@
 
 namespace {
 
-// deterministic row sums: one warp per row
-__global__ void row_sums_kernel(const double *__restrict__ S, int L, double *__restrict__ rows) {
+// deterministic row sums (warps 0..L-1) and column sums (warps L..2L-1): one warp per line, the SAME association of the
+// additions for both, so a symmetric S gives bit-identical row and column sums and the corrected matrix stays symmetric
+__global__ void line_sums_kernel(const double *__restrict__ S, int L, double *__restrict__ rows, double *__restrict__ cols) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= L) return;
+  if (warp >= 2 * L) return;
+  const bool col = warp >= L;
+  const int line = col ? warp - L : warp;
   double acc = 0.0;
-  for (int c = lane; c < L; c += 32) acc += S[(long long)warp * L + c];
+  for (int c = lane; c < L; c += 32) acc += col ? S[(long long)c * L + line] : S[(long long)line * L + c];
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) rows[warp] = acc;
+  if (lane == 0) (col ? cols : rows)[line] = acc;
 }
 
 __global__ void __launch_bounds__(1024) total_kernel(const double *__restrict__ rows, int L, double *__restrict__ out) {
@@ -34,17 +37,20 @@ __global__ void __launch_bounds__(1024) total_kernel(const double *__restrict__ 
   }
 }
 
-__global__ void apc_kernel(const double *__restrict__ S, const double *__restrict__ rows, const double *__restrict__ tot,
-                           int L, double *__restrict__ out) {
+// out[r][c] = S[r][c] - Sj[r] * Si[c] / Sa with Sj = sum(S, dims=2) (row sums) and Si = sum(S, dims=1) (column sums),
+// src/GaussDCA.jl:80-84 -- correct for a non-symmetric S too (the formula reads the same in Julia's column-major view)
+__global__ void apc_kernel(const double *__restrict__ S, const double *__restrict__ rows, const double *__restrict__ cols,
+                           const double *__restrict__ tot, int L, double *__restrict__ out) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)L * L) return;
   const int r = (int)(e / L), c = (int)(e - (long long)r * L);
   const double Sa = tot[0] * (1.0 - 1.0 / L);
-  out[e] = S[e] - (rows[r] * rows[c]) / Sa;  // S symmetric: column sums == row sums, bit for bit
+  out[e] = S[e] - (rows[r] * cols[c]) / Sa;
 }
 
 __device__ __forceinline__ unsigned long long desc_key(double x) {
   unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  if (x != x) b = 0x7FF8000000000000ull;  // Julia's isless: every NaN, whatever its sign bit, sorts above +Inf and NaNs tie
   const unsigned long long asc = b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
   return ~asc;  // ascending sort of this key == descending score
 }
@@ -150,14 +156,14 @@ __global__ void emit_kernel(const uint32_t *__restrict__ vals, const double *__r
 int32_t gdca_k_apc(gdca_ctx *ctx) {
   const int L = (int)ctx->L;
   GDCA_TRY(gdca_reserve(ctx, ctx->dS2, ctx->capS2, (size_t)L * L));
-  GDCA_TRY(gdca_reserve(ctx, ctx->dRed, ctx->capRed, (size_t)L + 4096));
-  double *rows = ctx->dRed, *tot = ctx->dRed + L;
-  row_sums_kernel<<<(unsigned)((L * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->dS, L, rows);
+  GDCA_TRY(gdca_reserve(ctx, ctx->dRed, ctx->capRed, (size_t)2 * L + 4096));
+  double *rows = ctx->dRed, *cols = ctx->dRed + L, *tot = ctx->dRed + 2 * L;
+  line_sums_kernel<<<(unsigned)((2 * L * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->dS, L, rows, cols);
   GDCA_LAUNCH_CHECK(ctx);
   total_kernel<<<1, 1024, 0, ctx->stream>>>(rows, L, tot);
   GDCA_LAUNCH_CHECK(ctx);
   const long long ne = (long long)L * L;
-  apc_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(ctx->dS, rows, tot, L, ctx->dS2);
+  apc_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(ctx->dS, rows, cols, tot, L, ctx->dS2);
   GDCA_LAUNCH_CHECK(ctx);
   return GDCA_OK;
 }

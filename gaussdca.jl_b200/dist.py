@@ -197,8 +197,8 @@ class GpuBackend:
 class _StreamDist:
     """torch.distributed with every collective enqueued on the library's CUDA stream."""
 
-    def __init__(self, dist, torch, stream):
-        self.d, self.torch, self.stream = dist, torch, stream
+    def __init__(self, dist, torch, stream, device):
+        self.d, self.torch, self.stream, self.device = dist, torch, stream, device
 
     def get_rank(self):
         return self.d.get_rank()
@@ -214,7 +214,7 @@ class _StreamDist:
         """numpy uint8[k] on every rank -> numpy uint8[world, k] (control-plane data: IPC handles)."""
         torch = self.torch
         with torch.cuda.stream(self.stream):
-            mine = torch.from_numpy(arr).to(f"cuda:{torch.cuda.current_device()}")
+            mine = torch.from_numpy(arr).to(f"cuda:{self.device}")   # the context's device, not torch's current one
             out = torch.empty((self.d.get_world_size(), arr.size), dtype=torch.uint8, device=mine.device)
             self.d.all_gather_into_tensor(out, mine)
             return out.cpu().numpy()
@@ -229,7 +229,18 @@ def gdca_sharded(Z, pseudocount=0.8, theta="auto", score="frob", min_separation=
     -> (R structured array on rank 0 / None elsewhere, info)."""
     import torch
     import torch.distributed as dist
+    # the ranges of check_arguments (src/GaussDCA.jl:49-65), as gdca_run() re-checks them
+    if not (0 <= pseudocount <= 1):
+        raise ValueError(f"invalid pseudocount value: {pseudocount} (must be between 0 and 1)")
+    if not ((isinstance(theta, str) and theta == "auto") or (not isinstance(theta, str) and 0 <= theta <= 1)):
+        raise ValueError(f"invalid θ value: {theta} (must be either :auto, or a number between 0 and 1)")
+    if score not in ("DI", "frob"):
+        raise ValueError(f"invalid score value: {score} (must be either :DI or :frob)")
+    if not (min_separation >= 1):
+        raise ValueError(f"invalid min_separation value: {min_separation} (must be >= 1)")
+    if Z.shape[0] < 2 and isinstance(theta, str):
+        raise ValueError("theta = :auto needs at least 2 sequences")
     be = GpuBackend(ctx)
     be.load(Z, resident=resident)
-    sd = _StreamDist(dist, torch, be.stream)
+    sd = _StreamDist(dist, torch, be.stream, ctx.device)
     return run_sharded(be, sd, be.L, be.M, theta, pseudocount, score, min_separation)

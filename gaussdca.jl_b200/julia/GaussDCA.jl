@@ -8,6 +8,11 @@
 # Julia is not installed in the build image of this repository, so this file is checked statically
 # (tests/test_host_cpu.py::test_julia_wrapper_is_consistent_with_header) and mirrored call-for-call by
 # the executable Python host layer gaussdca.jl_b200/api.py.  See INTEGRATION.md.
+#
+# Licence: the keyword signature of gDCA, check_arguments and the three printrank methods are taken from
+# GaussDCA.jl (Copyright (C) Carlo Baldassi and contributors), which is free software under the GNU General Public
+# License, version 3 or (at your option) any later version (reference LICENSE.md, COPYING).  This file is therefore
+# distributed under the same terms: GPL-3.0-or-later, WITHOUT ANY WARRANTY; see <https://www.gnu.org/licenses/>.
 module GaussDCA
 
 export gDCA, printrank

@@ -26,7 +26,18 @@
 extern "C" {
 #endif
 
-#define GDCA_ABI_VERSION 1
+#define GDCA_ABI_VERSION 2
+
+/* Size limits (every violation is reported as GDCA_ERR_INVALID_ARG with a message, never as a CUDA fault):
+ *   L <= GDCA_MAX_L = 11616     the bit-plane packer keeps ceil(L/32) x 5 planes of 32 sequences in shared memory
+ *   M <  2^31 - 128
+ *   M * roundup(L,128) < 2^32   32-bit row offsets of the recoded alignment in the covariance kernel
+ *                               (L=500: M < 8.3e6; L=1500: M < 2.7e6)
+ *   M <= 2 097 152 for the tensor-core prefilter (its T x T block-mask array, T = ceil(M/128) <= 16384); above that the
+ *                               neighbour-count sweep still runs, unfiltered
+ *   residue codes 1 <= Z <= 31  (q = max(Z) <= 31, src/GaussDCA.jl:25-26; a code < 1 is rejected)
+ *   n = (q-1) L: four n x n FP64 buffers must fit in HBM (n = 30 000 -> 29 GB; n ~ 70 000 on one 180 GB B200) */
+#define GDCA_MAX_L 11616
 
 typedef enum {
   GDCA_OK = 0,

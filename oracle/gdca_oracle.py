@@ -60,6 +60,7 @@ def lib():
         L.oracle_words_per_seq.restype = i64
         L.oracle_words_per_seq.argtypes = [i64]
         L.oracle_max_threads.restype = ctypes.c_int
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_compress_Z.argtypes = [p, i64, i64, p]
         L.oracle_ident_sum_packed.restype = u64
         L.oracle_ident_sum_packed.argtypes = [p, i64, i64]
@@ -338,7 +339,8 @@ def compute_ranking(S, min_separation: int = 5):
     ii, jj, vv = np.concatenate(ii), np.concatenate(jj), np.concatenate(vv)
     # Julia sorts with isless (a total order: -0.0 < 0.0), stable, rev=true.  Map doubles to integers
     # that sort the same way, complement for descending, and let a stable argsort keep enumeration order on ties.
-    u = np.ascontiguousarray(vv, dtype=np.float64).view(np.uint64)
+    u = np.ascontiguousarray(vv, dtype=np.float64).view(np.uint64).copy()
+    u[np.isnan(vv)] = np.uint64(0x7FF8000000000000)  # isless: any NaN (either sign bit) is above +Inf, NaNs tie
     asc = np.where((u >> np.uint64(63)).astype(bool), ~u, u | np.uint64(1 << 63))
     order = np.argsort(~asc, kind="stable")
     return [(int(ii[o]) + 1, int(jj[o]) + 1, float(vv[o])) for o in order]

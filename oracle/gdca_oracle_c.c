@@ -46,6 +46,16 @@ int oracle_max_threads(void) {
 #endif
 }
 
+/* `julia -t N` (README.md:92-94): the thread count is the caller's choice.  Launchers such as torchrun export
+ * OMP_NUM_THREADS=1 into the environment; bench.py sets the count explicitly through this instead. */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* Z is L x M column-major Int8 (one sequence per column, src/GaussDCA.jl:24). */
 void oracle_compress_Z(const int8_t *Z, int64_t L, int64_t M, uint64_t *cZ) {
   const int64_t nw = oracle_words_per_seq(L);

@@ -492,3 +492,82 @@ def test_weighted_frequencies_pseudocount_and_C_pieces(pkg, orc, ctx, L, M, thet
         assert normwise(C_chain, C_fused) <= 1e-13
     with pytest.raises(Exception):
         pkg.add_pseudocount(Pi_o, Pij_o, 1.5, q, ctx=ctx)
+
+
+# ----------------------------------------------------------------------------- round-2 robustness fixes
+def test_apc_on_a_non_symmetric_matrix(pkg, orc, ctx):
+    """correct_APC uses row sums x column sums (src/GaussDCA.jl:80-84); the staged entry point takes any S."""
+    rng = np.random.default_rng(4)
+    S = rng.random((37, 37))
+    np.fill_diagonal(S, 0.0)
+    assert normwise(pkg.correct_APC(S, ctx=ctx), orc.correct_APC(S)) <= 1e-14
+    Ss = S + S.T
+    out = pkg.correct_APC(Ss, ctx=ctx)
+    assert np.array_equal(out, out.T)     # symmetric in -> symmetric out, bit for bit
+
+
+def test_ranking_nan_sorts_first_like_julia_isless(pkg, orc, ctx):
+    """Julia's sort!(rev=true) uses isless: every NaN (either sign bit) is above +Inf; ties keep enumeration order."""
+    L = 12
+    S = np.random.default_rng(6).standard_normal((L, L))
+    S = S + S.T
+    S[5, 1] = S[1, 5] = np.nan
+    S[9, 2] = S[2, 9] = -np.nan
+    S[8, 3] = S[3, 8] = np.inf
+    R = pkg.compute_ranking(S, 1, ctx=ctx)
+    Ro = orc.compute_ranking(S, 1)
+    assert [(i, j) for i, j, _ in R] == [(i, j) for i, j, _ in Ro]
+    assert [(i, j) for i, j, _ in R[:3]] == [(2, 6), (3, 10), (4, 9)]
+
+
+def test_residue_code_below_one_is_rejected(pkg, ctx):
+    Z = np.ones((20, 9), dtype=np.int8)
+    Z[3, 4] = -5
+    with pytest.raises(ValueError, match="codes must be >= 1"):
+        pkg.gdca_from_alignment(Z, ctx=ctx)
+    Z[3, 4] = 0
+    with pytest.raises(ValueError, match="codes must be >= 1"):
+        pkg.compute_weights(Z, 0.2, ctx=ctx)
+
+
+def test_resident_run_on_an_unaligned_device_view_and_state_drop(pkg, orc, ctx):
+    """gdca_run_resident takes any device pointer (odd byte offsets included) and lets go of it when it returns."""
+    import ctypes
+    import torch
+    from gaussdca_jl_b200 import _lib as glib
+    L, M = 45, 900
+    Z = orc.synth_alignment(L, M, seed=8)
+    R_host = pkg.gdca_from_alignment(Z, ctx=ctx, as_array=True)
+    buf = torch.zeros(L * M + 64, dtype=torch.int8, device="cuda")
+    for off in (1, 7, 16, 33):
+        buf[off:off + L * M] = torch.from_numpy(Z.reshape(-1)).cuda()
+        n_out = int(ctx.lib.gdca_ranking_length(L, 5))
+        R = np.empty(n_out, dtype=glib.RANK_DTYPE)
+        ctx.check(ctx.lib.gdca_run_resident(ctx.h, ctypes.c_void_p(buf.data_ptr() + off), L, M, -1.0, 0.8, 0, 5, glib.ptr(R),
+                                            n_out, None))
+        assert np.array_equal(R, R_host)
+    # the borrowed pointer is gone: a device-resident stage now reports a state error instead of reading freed memory
+    assert ctx.lib.gdca_dev_covariance(ctx.h, 0.8) == glib.GDCA_ERR_STATE
+    # and a staged host-buffer call that changes L invalidates the alignment of an earlier gdca_dev_load
+    ctx.check(ctx.lib.gdca_dev_load(ctx.h, glib.ptr(Z), L, M))
+    pkg.correct_APC(np.ones((7, 7)), ctx=ctx)
+    assert ctx.lib.gdca_dev_pair_pass(ctx.h, 1, 10) == glib.GDCA_ERR_STATE
+
+
+def test_not_spd_chain_stops_early(pkg, ctx):
+    """A failed pivot in the first diagonal block: the launches queued behind it return at once (the reference throws at the
+    pivot, src/GaussDCA.jl:34) -- the call still reports LAPACK's info."""
+    import time
+    n = 4000
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((n, n + 5))
+    C = A @ A.T / n + np.eye(n)
+    pkg.inverse(C, ctx=ctx)                     # warm-up (allocations)
+    t0 = time.perf_counter(); pkg.inverse(C, ctx=ctx); t_ok = time.perf_counter() - t0
+    C[2, 2] = -1.0
+    t0 = time.perf_counter()
+    with pytest.raises(pkg.PosDefException) as ei:
+        pkg.inverse(C, ctx=ctx)
+    t_bad = time.perf_counter() - t0
+    assert ei.value.info == 3
+    assert t_bad < t_ok                          # both include the same H2D of C; the failed run skips D2H and the flop

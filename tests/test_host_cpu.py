@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} declared in the header but not bound in _lib.SIGNATURES"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.gdca_abi_version() == 1
+    assert lib.gdca_abi_version() == 2
     assert lib.gdca_ranking_length(53, 5) == 48 * 49 // 2 == 1176           # src/GaussDCA.jl:90
     assert lib.gdca_ranking_length(53, 4) == 1225 and lib.gdca_ranking_length(400, 5) == 78210
     assert lib.gdca_ranking_length(5, 5) == 0 and lib.gdca_ranking_length(3, 5) == 0

@@ -403,7 +403,8 @@ int main(int argc, char **argv) {
   long long mismatches = 0, checked = 0;
   double max_rel = 0, max_ref = 0;
   std::vector<int8_t> digA;
-  for (long long i = 0; i < m; i += (m > 64 ? m / 64 : 1)) {
+  const long long nsample = (m * n * k > (1ll << 31)) ? 8 : 64;
+  for (long long i = 0; i < m; i += (m > nsample ? m / nsample : 1)) {
     int eA;
     slice_row(&A[(size_t)i * k], digA, eA);
     for (long long j = 0; j < n; ++j) {
