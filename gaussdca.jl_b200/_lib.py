@@ -98,6 +98,9 @@ SIGNATURES = {
     "gdca_dev_W_ptr": (_p, [_p]),
     "gdca_dev_inverse": (_i32, [_p, _pi32]),
     "gdca_dev_mJ_ptr": (_p, [_p]),
+    "gdca_set_ozaki": (_i32, [_p, _i32]),
+    "gdca_dev_inverse_info": (_i32, [_p, _pi32, _pdbl, _pdbl]),
+    "gdca_test_fp64_gemm": (_i32, [_p, _i32, _p, _i32, _p, _i32, _p, _i64, _i64, _i64, _i32, _dbl, _dbl]),
     "gdca_dev_score_rank": (_i32, [_p, _i32, _i64, _p, _i64]),
     "gdca_dev_S_ptr": (_p, [_p]),
     "gdca_dev_peer_export": (_i32, [_p, _p]),

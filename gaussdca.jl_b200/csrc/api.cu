@@ -244,6 +244,12 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if (const char *env = getenv("GDCA_CHOL_LOOKAHEAD")) ctx->chol_inner_lookahead = atoi(env) != 0;
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fact, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_sliced, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if (const char *env = getenv("GDCA_OZAKI")) ctx->ozaki_mode = atoi(env) != 0;
+  if (const char *env = getenv("GDCA_OZ_TPC")) {
+    const int v = atoi(env);
+    if (v >= 0 && v <= 1024) ctx->ozaki_tpc = v;
+  }
   if ((e = cudaMalloc((void **)&ctx->dHam, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dQ, 2 * sizeof(int))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dMeff, 2 * sizeof(double))) != cudaSuccess) return fail(e);
@@ -280,7 +286,8 @@ void gdca_destroy(gdca_ctx *ctx) {
   void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPerm, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
-                  ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask};
+                  ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask,
+                  ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)
@@ -289,6 +296,7 @@ void gdca_destroy(gdca_ctx *ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->ev_fact) cudaEventDestroy(ctx->ev_fact);
   if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
+  if (ctx->ev_sliced) cudaEventDestroy(ctx->ev_sliced);
   for (cudaEvent_t e : {ctx->ev_diag, ctx->ev_p1, ctx->ev_u2a, ctx->ev_u2b})
     if (e) cudaEventDestroy(e);
   if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
@@ -526,6 +534,21 @@ int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info) {
   const int32_t st = gdca_k_inverse(ctx);
   if (info) *info = ctx->stats.posdef_info;
   return st;
+}
+
+int32_t gdca_set_ozaki(gdca_ctx *ctx, int32_t mode) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_ozaki: mode must be 0 (DMMA only) or 1 (INT8-sliced tcgen05 GEMMs)");
+  ctx->ozaki_mode = mode;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_inverse_info(gdca_ctx *ctx, int32_t *ozaki, double *int8_ops, double *fp64_flop_on_int8) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (ozaki) *ozaki = ctx->last_inverse_ozaki ? 1 : 0;
+  if (int8_ops) *int8_ops = ctx->oz_int8_ops;
+  if (fp64_flop_on_int8) *fp64_flop_on_int8 = ctx->oz_fp64_flop;
+  return GDCA_OK;
 }
 
 int32_t gdca_dev_score_rank(gdca_ctx *ctx, int32_t score, int64_t min_separation, gdca_rank_t *R_host, int64_t R_len) {

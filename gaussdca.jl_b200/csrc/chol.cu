@@ -127,10 +127,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(GemmP p) {
   // shared-memory latency no longer sit in front of the tensor pipe.
   // The reference throws at the failing pivot (cholesky(C), src/GaussDCA.jl:34).  Here the ~250 launches behind a failed diagonal
   // block are already queued: each of them reads the flag (under the latency of its first operand loads) and leaves.
-  const int failed = p.info ? *reinterpret_cast<const volatile int *>(p.info) : 0;
+  // One thread reads, the CTA votes: a diagonal block on another stream may set the flag while this launch is starting, and
+  // the threads of a CTA must agree on leaving.
+  int failed = (p.info && tid == 0) ? *reinterpret_cast<const volatile int *>(p.info) : 0;
   load_stage(0);
   load_stage(1);
   load_stage(2);
+  failed = __syncthreads_or(failed);
   if (failed) {
     cp_wait<0>();
     return;
@@ -395,6 +398,20 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   GDCA_TRY(gdca_reserve(ctx, ctx->dX, ctx->capX, (size_t)np * np));
   GDCA_TRY(gdca_reserve(ctx, ctx->dT, ctx->capT, (size_t)np * np));
   GDCA_TRY(gdca_reserve(ctx, ctx->dmJ, ctx->capmJ, (size_t)np * np));
+  // INT8-sliced tcgen05 GEMMs (ozaki.cu) for the big products; DMMA for diagonal blocks, K = 128 panels and small shapes
+  const bool oz = ctx->ozaki_mode != 0 && nb >= 16;
+  ctx->last_inverse_ozaki = oz;
+  ctx->oz_int8_ops = 0.0;
+  ctx->oz_fp64_flop = 0.0;
+  if (oz) {
+    GDCA_TRY(gdca_reserve(ctx, ctx->dDigA, ctx->capDigA, (size_t)np * np * 8));   // lauum: all of X', 8 digit slots per element
+    GDCA_TRY(gdca_reserve(ctx, ctx->dDigB, ctx->capDigB, (size_t)np * np * 8));   // trtri operands (the top block of the last level
+                                                                                   // is up to (nb - 1) blocks wide), potrf panels
+    GDCA_TRY(gdca_reserve(ctx, ctx->dScaleA, ctx->capScaleA, (size_t)np));
+    GDCA_TRY(gdca_reserve(ctx, ctx->dScaleB, ctx->capScaleB, (size_t)np));
+  }
+  constexpr int OZ_MIN_REM = 8;   // trailing updates with at least this many block rows left
+  constexpr int OZ_MIN_H = 4;     // trtri levels with K >= 512
   double *A = ctx->dC, *X = ctx->dX, *T = ctx->dT, *J = ctx->dmJ;
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dInfo, 0, sizeof(int), ctx->stream));
   GDCA_CUDA(ctx, cudaMemsetAsync(X, 0, (size_t)np * np * sizeof(double), ctx->stream));
@@ -511,6 +528,30 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
       const int Kn = (Kend + OB < nb) ? Kend + OB : nb;
       GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_fact, sA));          // panel [K0,Kend) is final
       if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));  // columns >= Kend carry update K0-OB
+      if (oz && rem >= OZ_MIN_REM) {
+        // the panel rows L[Kend.., K0:Kend) are sliced ONCE into int8 digits (after the previous bulk update has finished
+        // reading the digit buffer: the wait above); both parts of the update read them
+        const int kk = (Kend - K0) * NB;
+        gdca_oz_operand P{};
+        GDCA_TRY(gdca_oz_slice(ctx, sA, blk(A, Kend, K0), np, 0, false, rem * NB, kk, 1, rem * NB, ctx->dDigB, ctx->dScaleB, &P));
+        GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_sliced, sA));
+        GDCA_TRY(gdca_oz_gemm(ctx, sA, P, P, blk(A, Kend, Kend), np, 0, rem * NB, (Kn - Kend) * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1, 0));
+        ctx->oz_fp64_flop += 2.0 * (double)kk * NB * NB * ((double)(Kn - Kend) * rem - 0.5 * (Kn - Kend) * (Kn - Kend - 1));
+        const int rem2 = nb - Kn;
+        if (rem2 > 0) {
+          GDCA_CUDA(ctx, cudaStreamWaitEvent(sB, ctx->ev_sliced, 0));
+          gdca_oz_operand P2 = P;
+          P2.dig += (long long)(Kn - Kend) * NB * P.pitch;
+          P2.scale += (long long)(Kn - Kend) * NB;
+          P2.rows_total = P2.rows_b = (long long)rem2 * NB;
+          GDCA_TRY(gdca_oz_gemm(ctx, sB, P2, P2, blk(A, Kn, Kn), np, 0, rem2 * NB, rem2 * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1,
+                                ctx->ozaki_tpc));
+          ctx->oz_fp64_flop += 2.0 * (double)kk * NB * NB * (0.5 * (double)rem2 * (rem2 + 1));
+          GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_trail, sB));
+          pending_trail = true;
+        }
+        continue;
+      }
       GemmP t{};
       t.A = blk(A, Kend, K0); t.lda = np;
       t.B = blk(A, Kend, K0); t.ldb = np;
@@ -541,6 +582,20 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
     const int rest = nb - ngroups_full * 2 * h;       // blocks left after the full groups
     const long long gstride = (long long)2 * h * NB * (np + 1);  // along the diagonal
     auto level = [&](int g0, int mb, int batch) -> int32_t {  // mb = bottom blocks
+      if (oz && h >= OZ_MIN_H) {
+        cudaStream_t st = ctx->stream;
+        gdca_oz_operand oa{}, ob{};
+        // T[bottom, top] = L[bottom, top] * X[top, top]: rows of L21 against the COLUMNS of the lower-triangular X11 (k >= n0)
+        GDCA_TRY(gdca_oz_slice(ctx, st, blk(A, g0 + h, g0), np, gstride, false, mb * NB, h * NB, batch, mb * NB, ctx->dDigA, ctx->dScaleA, &oa));
+        GDCA_TRY(gdca_oz_slice(ctx, st, blk(X, g0, g0), np, gstride, true, h * NB, h * NB, batch, h * NB, ctx->dDigB, ctx->dScaleB, &ob));
+        GDCA_TRY(gdca_oz_gemm(ctx, st, oa, ob, blk(T, g0 + h, g0), np, gstride, mb * NB, h * NB, h * NB, batch, GDCA_OZ_KBEG_N, 1.0, 0, 0));
+        // X[bottom, top] = - X[bottom, bottom] * T[bottom, top]: rows of the lower-triangular X22 (k < m0 + 128) against columns of T
+        GDCA_TRY(gdca_oz_slice(ctx, st, blk(X, g0 + h, g0 + h), np, gstride, false, mb * NB, mb * NB, batch, mb * NB, ctx->dDigA, ctx->dScaleA, &oa));
+        GDCA_TRY(gdca_oz_slice(ctx, st, blk(T, g0 + h, g0), np, gstride, true, h * NB, mb * NB, batch, h * NB, ctx->dDigB, ctx->dScaleB, &ob));
+        GDCA_TRY(gdca_oz_gemm(ctx, st, oa, ob, blk(X, g0 + h, g0), np, gstride, mb * NB, h * NB, mb * NB, batch, GDCA_OZ_KEND_M, -1.0, 0, 0));
+        ctx->oz_fp64_flop += (double)batch * 2.0 * NB * NB * NB * ((double)mb * h * (h + 1) / 2 + (double)h * mb * (mb + 1) / 2);
+        return GDCA_OK;
+      }
       GemmP a{};
       // T[bottom, top] = L[bottom, top] * X[top, top]         (B as [k][n], lower triangular: k >= n0)
       a.A = blk(A, g0 + h, g0); a.lda = np; a.strideA = gstride;
@@ -562,7 +617,16 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   }
 
   // ---------------- lauum: mJ = X' X (lower tiles), then mirror ----------------
-  {
+  if (oz) {
+    // operand rows = columns of X: ONE transposed slice serves both sides; k >= m0 (X is lower triangular)
+    gdca_oz_operand ox{};
+    GDCA_TRY(gdca_oz_slice(ctx, ctx->stream, X, np, 0, true, (int)np, (int)np, 1, np, ctx->dDigA, ctx->dScaleA, &ox));
+    GDCA_TRY(gdca_oz_gemm(ctx, ctx->stream, ox, ox, J, np, 0, (int)np, (int)np, (int)np, 1, GDCA_OZ_LOWER_OUT | GDCA_OZ_KBEG_M, 1.0, 0, 0));
+    ctx->oz_fp64_flop += (double)np * np * np / 3.0;
+    const unsigned nt = (unsigned)((np + 31) / 32);
+    mirror_lower_kernel<<<dim3(nt, nt), 256, 0, ctx->stream>>>(J, np, np);
+    GDCA_LAUNCH_CHECK(ctx);
+  } else {
     GemmP l{};
     l.A = X; l.lda = np;
     l.B = X; l.ldb = np;
@@ -586,4 +650,58 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   }
   ctx->have_inv = true;
   return GDCA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- test hook
+// C[m x n] = beta C + alpha opA opB^T on one of the two FP64 GEMM engines, host buffers (tests/test_gpu_ozaki.py).
+extern "C" int32_t gdca_test_fp64_gemm(gdca_ctx *ctx, int32_t engine, const double *A, int32_t a_cols, const double *B, int32_t b_cols,
+                                       double *C, int64_t m, int64_t n, int64_t k, int32_t flags, double alpha, double beta) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (!A || !B || !C || m < 128 || n < 128 || k < 128 || m % 128 || n % 128 || k % 128)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "test_fp64_gemm: m, n, k must be positive multiples of 128");
+  if (engine == 1 && beta != 0.0 && beta != 1.0) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "test_fp64_gemm: engine 1 takes beta 0 or 1");
+  GDCA_CUDA(ctx, cudaSetDevice(ctx->device));
+  double *dA = nullptr, *dB = nullptr, *dCm = nullptr;
+  int8_t *dgA = nullptr, *dgB = nullptr;
+  double *scA = nullptr, *scB = nullptr;
+  int32_t st = GDCA_OK;
+  auto body = [&]() -> int32_t {
+    GDCA_CUDA(ctx, cudaMalloc((void **)&dA, (size_t)m * k * 8));
+    GDCA_CUDA(ctx, cudaMalloc((void **)&dB, (size_t)n * k * 8));
+    GDCA_CUDA(ctx, cudaMalloc((void **)&dCm, (size_t)m * n * 8));
+    GDCA_CUDA(ctx, cudaMemcpyAsync(dA, A, (size_t)m * k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GDCA_CUDA(ctx, cudaMemcpyAsync(dB, B, (size_t)n * k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GDCA_CUDA(ctx, cudaMemcpyAsync(dCm, C, (size_t)m * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dInfo, 0, sizeof(int), ctx->stream));
+    if (engine == 0) {
+      GemmP p{};
+      p.A = dA; p.lda = a_cols ? m : k;
+      p.B = dB; p.ldb = b_cols ? n : k;
+      p.C = dCm; p.ldc = n;
+      p.m = (int)m; p.n = (int)n; p.k = (int)k; p.flags = flags; p.alpha = alpha; p.beta = beta;
+      if (!a_cols && !b_cols) GDCA_TRY((gemm<false, false>(ctx, p, 1)));
+      if (!a_cols && b_cols) GDCA_TRY((gemm<false, true>(ctx, p, 1)));
+      if (a_cols && b_cols) GDCA_TRY((gemm<true, true>(ctx, p, 1)));
+      if (a_cols && !b_cols) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "test_fp64_gemm: engine 0 has no (A as [k][m], B as [n][k]) kernel");
+    } else {
+      GDCA_CUDA(ctx, cudaMalloc((void **)&dgA, (size_t)m * k * 8));
+      GDCA_CUDA(ctx, cudaMalloc((void **)&dgB, (size_t)n * k * 8));
+      GDCA_CUDA(ctx, cudaMalloc((void **)&scA, (size_t)m * 8));
+      GDCA_CUDA(ctx, cudaMalloc((void **)&scB, (size_t)n * 8));
+      GDCA_CUDA(ctx, cudaMemsetAsync(dgA, 0, (size_t)m * k * 8, ctx->stream));
+      GDCA_CUDA(ctx, cudaMemsetAsync(dgB, 0, (size_t)n * k * 8, ctx->stream));
+      gdca_oz_operand oa{}, ob{};
+      GDCA_TRY(gdca_oz_slice(ctx, ctx->stream, dA, a_cols ? m : k, 0, a_cols != 0, (int)m, (int)k, 1, m, dgA, scA, &oa));
+      GDCA_TRY(gdca_oz_slice(ctx, ctx->stream, dB, b_cols ? n : k, 0, b_cols != 0, (int)n, (int)k, 1, n, dgB, scB, &ob));
+      GDCA_TRY(gdca_oz_gemm(ctx, ctx->stream, oa, ob, dCm, n, 0, (int)m, (int)n, (int)k, 1, flags, alpha, beta != 0.0, 0));
+    }
+    GDCA_CUDA(ctx, cudaMemcpyAsync(C, dCm, (size_t)m * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GDCA_OK;
+  };
+  st = body();
+  cudaStreamSynchronize(ctx->stream);
+  for (void *q : {(void *)dA, (void *)dB, (void *)dCm, (void *)dgA, (void *)dgB, (void *)scA, (void *)scB})
+    if (q) cudaFree(q);
+  return st;
 }

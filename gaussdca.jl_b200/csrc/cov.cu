@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
   extern __shared__ double acc[];      // [q][SPT][JT]; slot s is the dump for the gap state / padding
   __shared__ unsigned stage_off[STG];  // row offset k*Lq of the staged sequences
   __shared__ double stage_w[STG];      // W[k]
-  // 1-D grid, row-major over (row, chunk): the same CTA order as a (chunks, rows) grid without its 65535-row limit
-  const int r = (int)(blockIdx.x / (unsigned)P.nchunks);  // output row (i, a)
-  const int chunk = (int)(blockIdx.x - (unsigned)r * (unsigned)P.nchunks);
+  // (chunks, rows) grid; beyond its 65535-row limit (L > 3276 at q = 21) a 1-D grid, row-major over (row, chunk)
+  const int r = gridDim.y > 1 ? (int)blockIdx.y : (int)(blockIdx.x / (unsigned)P.nchunks);  // output row (i, a)
+  const int chunk = gridDim.y > 1 ? (int)blockIdx.x : (int)(blockIdx.x - (unsigned)r * (unsigned)P.nchunks);
   const int i = r / P.s, a = r - i * P.s + 1;
   if (P.world > 1 && (i % P.world) != P.rank) return;  // rows are dealt to ranks by site
   const int start = (i / (32 * SPT)) * (32 * SPT) + chunk * CH;
@@ -406,10 +406,11 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw) {
   GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov0, ctx->stream));
+  const dim3 cgrid = (n <= 65535 && n > 1) ? dim3((unsigned)P.nchunks, (unsigned)n) : dim3((unsigned)((long long)P.nchunks * n));
   if (raw)
-    cov_rows_kernel<SPT, true><<<(unsigned)((long long)P.nchunks * n), JT, smem, ctx->stream>>>(P);
+    cov_rows_kernel<SPT, true><<<cgrid, JT, smem, ctx->stream>>>(P);
   else
-    cov_rows_kernel<SPT, false><<<(unsigned)((long long)P.nchunks * n), JT, smem, ctx->stream>>>(P);
+    cov_rows_kernel<SPT, false><<<cgrid, JT, smem, ctx->stream>>>(P);
   GDCA_LAUNCH_CHECK(ctx);
   GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov1, ctx->stream));
   ctx->pseudocount = pc;

@@ -53,6 +53,18 @@ struct gdca_ctx {
   double *dCdiag = nullptr; size_t capCdiag = 0;  // [L][s][s] diagonal blocks of C (for DI)
   double *dT = nullptr; size_t capT = 0;       // [npad][npad] GEMM workspace (trtri)
   int *dInfo = nullptr;                        // [1] not-SPD info
+  // ---- INT8-sliced FP64 GEMMs of the inversion (ozaki.cu) ----
+  int ozaki_mode = 1;                          // 1 (default): big products of potrf / trtri / lauum on tcgen05 kind::i8; 0: DMMA only (env GDCA_OZAKI)
+  int ozaki_tpc = 4;                           // tiles per CTA of the bulk trailing update (short CTAs: the look-ahead chain keeps getting SMs)
+  int8_t *dDigA = nullptr; size_t capDigA = 0; // digit matrices [rows][k/64][8][64] int8
+  int8_t *dDigB = nullptr; size_t capDigB = 0;
+  double *dScaleA = nullptr; size_t capScaleA = 0;  // 2^e per operand row
+  double *dScaleB = nullptr; size_t capScaleB = 0;
+  unsigned long long *dOzMax = nullptr; size_t capOzMax = 0;  // column maxima of a transposed slice
+  cudaEvent_t ev_sliced = nullptr;             // panel digits ready (potrf trailing update on two streams)
+  double oz_int8_ops = 0.0;                    // INT8 operations of the last inversion
+  double oz_fp64_flop = 0.0;                   // FP64 flop those products stand for
+  bool last_inverse_ozaki = false;
   double *dS = nullptr; size_t capS = 0;       // [L][L] raw score
   double *dS2 = nullptr; size_t capS2 = 0;     // [L][L] APC-corrected
   double *dRed = nullptr; size_t capRed = 0;   // reductions for APC
@@ -135,6 +147,20 @@ static inline int32_t gdca_fail(gdca_ctx *ctx, int32_t status, const char *msg) 
   if (ctx) ctx->err = msg;
   return status;
 }
+
+// ---- INT8-sliced FP64 GEMM (ozaki.cu) ----
+enum : int { GDCA_OZ_LOWER_OUT = 1, GDCA_OZ_KBEG_N = 2, GDCA_OZ_KBEG_M = 4, GDCA_OZ_KEND_M = 8 };  // = the G_* flags of chol.cu
+struct gdca_oz_operand {
+  const int8_t *dig;      // [rows_total][pitch] bytes
+  const double *scale;    // [rows_total] 2^e
+  long long pitch;        // bytes per row = (k / 64) * 512
+  long long rows_total;   // rows of all batch members
+  long long rows_b;       // rows between consecutive batch members
+};
+int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, long long ld, long long stride_b, bool cols, int rows,
+                      int k, int batch, long long rows_b, int8_t *dig, double *scale, gdca_oz_operand *out);
+int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &A, const gdca_oz_operand &B, double *C, long long ldc,
+                     long long strideC, int m, int n, int k, int batch, int flags, double alpha, int beta, int tiles_per_cta);
 
 // ---- stage entry points implemented across the .cu files ----
 int32_t gdca_k_maxq(gdca_ctx *ctx);                       // pack.cu: dQ <- max(Z)

@@ -1,0 +1,618 @@
+// ozaki.cu -- the big FP64 GEMMs of K5 (mJ = inv(cholesky(C)), reference src/GaussDCA.jl:34) on the INT8 tensor cores.
+//
+// tcgen05 has no FP64 kind; the FP64 tensor path of sm_100a is the warp-level DMMA (37 TFLOP/s measured), and chol.cu's
+// products run at 0.7-0.9 of it.  This file gets past that wall with an Ozaki-style error-free split:
+//
+//   slice    every operand row is scaled by a power of two 2^e (|a / 2^e| < 1/2) and cut into S = 7 signed 7-bit digits,
+//                a / 2^e = sum_t d_t 2^(-7 (t+1)) + r,   |d_t| <= 64,  |r| <= 2^-50,
+//            stored as int8, K-major: dig[row][k-block of 64][digit slot 0..7][64 bytes]  (slot 7 unused), so that one
+//            128-byte row of a TMA box carries the SAME 64 k-elements of two consecutive digits;
+//   multiply D_d = sum_{t+u=d} A_t B_u^T for d = 0..6 (28 digit products, t + u < 7) with tcgen05.mma kind::i8: exact S32
+//            accumulation (|D_d| <= 7 k 64^2 < 2^31 for k <= 74 000), one 128 x 64 output tile with all seven diagonal
+//            accumulators resident in TMEM (7 x 64 = 448 of the 512 columns);
+//   combine  hi = D_0 2^21 + D_1 2^14 + D_2 2^7 + D_3 and lo = D_4 2^14 + D_5 2^7 + D_6 as exact int64, then
+//            C (+)= alpha 2^(e_i + f_j) (hi 2^-35 + lo 2^-56): two exact conversions and ONE rounding -- the correctly
+//            rounded value of the exact sum of the 28 digit products.
+//
+// Error: the product differs from the FP64 one by <= ~2^-49 |row scale| |column scale| k (the dropped digits), which keeps
+// the blocked Cholesky + inverse at ~4e-13 normwise on mJ (tools/ozaki_numerics.py; tolerance 1e-9, blocked FP64 3e-15).
+//
+// Kernel: the warp-specialised structure of tcfilter.cu -- warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps
+// 2..5 epilogue (one TMEM lane quarter each) -- 2-stage ring of 96 KB (4 + 4 SWIZZLE_128B boxes per 64-wide k-block), 56 MMAs
+// of 128 x 64 x 32 per stage, triangular operands handled as per-tile k ranges, batched launches for the trtri levels.
+// The epilogue goes through a small padded shared-memory tile so that the FP64 read-modify-write of C is coalesced.
+#include <cuda.h>  // CUtensorMap (types only)
+
+#include "gdca_internal.cuh"
+
+namespace {
+
+constexpr int S = 7;             // digits per operand
+constexpr int BM = 128;          // tile rows
+constexpr int BN = 64;           // tile columns: 7 accumulators x 64 columns = 448 TMEM columns
+constexpr int KBLK = 64;         // k elements per k-block (= bytes per digit and row in a stage)
+constexpr int SLOTS = 8;         // digit slots per k-block in memory (7 used)
+constexpr int NPAIR = 4;         // TMA boxes per operand and k-block: digit pairs (0,1) (2,3) (4,5) (6,-)
+constexpr int A_BOX = BM * 128;  // 16 KB
+constexpr int B_BOX = BN * 128;  // 8 KB
+constexpr int STAGE_BYTES = NPAIR * (A_BOX + B_BOX);  // 96 KB
+constexpr int NSTAGE = 2;
+constexpr int OZ_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int EPI_COLS = 16;                 // columns per epilogue chunk
+constexpr int EPI_LD = EPI_COLS + 1;         // padded row of the staging tile (doubles)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 8;
+constexpr size_t OZ_SMEM = (size_t)NSTAGE * STAGE_BYTES + EPI_BYTES + 1024 /* alignment slack */;
+// kind::i8: D = S32 (2 at bit 4), A = B = signed int8 (1 at bits 7 and 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct OzGemmP {
+  double *C;
+  long long ldc, strideC;        // strideC: elements between the C tiles of consecutive batch members
+  const double *sa, *sb;         // 2^e per operand row (rows of all batch members stacked)
+  long long rowsA, rowsB;        // operand rows per batch member (>= m, n)
+  int m, n, k, batch;            // per batch member; m % 128 == 0, n % 64 == 0, k % 128 == 0
+  int flags;                     // GDCA_OZ_*
+  int beta;                      // 0: C = alpha A B^T, 1: C += alpha A B^T
+  int tiles_per_cta;             // 0: persistent grid (tile t = blockIdx.x + i gridDim.x); else contiguous chunks
+  int tri;                       // square lower-triangular output (n == m, batch == 1): only the tm (tm + 1) valid tiles are listed
+  int total;                     // tiles in the list
+  double alpha;
+  const int *info;               // not-SPD flag of the factorisation: once set, the launch returns at once
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------- tile order
+// Tiles of all batch members in one list, longest k range first (round-robin over a descending list balances the CTAs):
+//   GDCA_OZ_KBEG_N  k starts at the 128-block of n0 (B lower triangular as [k][n])  -> column tile outermost, ascending
+//   GDCA_OZ_KEND_M  k ends at m0 + 128            (A lower triangular as [m][k])   -> row tile outermost, descending
+//   GDCA_OZ_KBEG_M  k starts at m0                (A lower triangular as [k][m])   -> row tile outermost, ascending
+struct Tile {
+  int b, im, jn, kb0, kb1;
+  bool valid;
+};
+__device__ __forceinline__ Tile decode_tile(const OzGemmP &P, int t, int tm, int tn) {
+  Tile T;
+  if (P.tri) {
+    // row tile im holds the 2 (im + 1) column tiles left of and on the diagonal: t = im (im + 1) + jn
+    int im = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (im * (im + 1) > t) --im;
+    while ((im + 1) * (im + 2) <= t) ++im;
+    T.b = 0;
+    T.im = im;
+    T.jn = t - im * (im + 1);
+  } else if (P.flags & GDCA_OZ_KBEG_N) {
+    const int per = P.batch * tm;
+    T.jn = t / per;
+    const int r = t - T.jn * per;
+    T.b = r / tm;
+    T.im = r - T.b * tm;
+  } else {
+    const int per = P.batch * tn;
+    const int o = t / per;
+    const int r = t - o * per;
+    T.b = r / tn;
+    T.jn = r - T.b * tn;
+    T.im = (P.flags & GDCA_OZ_KEND_M) ? tm - 1 - o : o;
+  }
+  const int m0 = T.im * BM, n0 = T.jn * BN;
+  T.valid = !((P.flags & GDCA_OZ_LOWER_OUT) && n0 >= m0 + BM);
+  int kbeg = 0, kend = P.k;
+  if (P.flags & GDCA_OZ_KBEG_N) kbeg = max(kbeg, (n0 / 128) * 128);
+  if (P.flags & GDCA_OZ_KBEG_M) kbeg = max(kbeg, m0);
+  if (P.flags & GDCA_OZ_KEND_M) kend = min(kend, m0 + BM);
+  T.kb0 = kbeg / KBLK;
+  T.kb1 = kend / KBLK;
+  return T;
+}
+
+// ---------------------------------------------------------------------------------------------- the GEMM
+// tmapA / tmapB: the digit matrices as 2-D byte tensors {pitch, rows}, boxes {128 B, 128 rows} / {128 B, 64 rows}, SWIZZLE_128B.
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, OzGemmP P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bars[2 * NSTAGE + 2];
+  __shared__ uint32_t s_tmem;
+  if (P.info && *reinterpret_cast<const volatile int *>(P.info) != 0) return;  // the factorisation has already failed
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B boxes need 1024-byte alignment
+  const uint32_t bars = smem_u32(s_bars);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  const uint32_t tfull_bar = bars + 8u * (2 * NSTAGE), tempty_bar = bars + 8u * (2 * NSTAGE + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);  // one arrival per epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *(volatile uint32_t *)&s_tmem;
+
+  const int tm = P.m / BM, tn = P.n / BN;
+  const int total = P.total;
+  int first, last, step;
+  if (P.tiles_per_cta > 0) {
+    first = (int)blockIdx.x * P.tiles_per_cta;
+    last = min(first + P.tiles_per_cta, total);
+    step = 1;
+  } else {
+    first = (int)blockIdx.x;
+    last = total;
+    step = (int)gridDim.x;
+  }
+
+  if (warp == 0) {
+    // ===== TMA producer: the 4 + 4 digit-pair boxes of one k-block per stage =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = first; t < last; t += step) {
+      const Tile T = decode_tile(P, t, tm, tn);
+      if (!T.valid) continue;
+      const int rowA = (int)(T.b * P.rowsA) + T.im * BM, rowB = (int)(T.b * P.rowsB) + T.jn * BN;
+      for (int kb = T.kb0; kb < T.kb1; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t sa = base + (uint32_t)s * (uint32_t)STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+#pragma unroll
+          for (int p = 0; p < NPAIR; ++p) tma_load_2d(sa + p * A_BOX, &tmapA, full_bar(s), kb * (SLOTS * KBLK) + p * 128, rowA);
+#pragma unroll
+          for (int p = 0; p < NPAIR; ++p)
+            tma_load_2d(sa + NPAIR * A_BOX + p * B_BOX, &tmapB, full_bar(s), kb * (SLOTS * KBLK) + p * 128, rowB);
+        }
+        __syncwarp();
+        if (++s == NSTAGE) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: D[d] += A_t B_u^T for all t + u = d < 7, two K = 32 steps per digit and k-block =====
+    int s = 0;
+    uint32_t ph = 0, nt = 0;
+    // descriptor halves: hi = SBO 1024 B | version 1 | SWIZZLE_128B, lo = start address >> 4 | LBO field 1
+    constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    for (int t = first; t < last; t += step) {
+      const Tile T = decode_tile(P, t, tm, tn);
+      if (!T.valid) continue;
+      mbar_wait(tempty_bar, (nt & 1u) ^ 1u);  // the epilogue has drained the accumulators of the previous tile
+      ++nt;
+      tc_fence_after();
+      for (int kb = T.kb0; kb < T.kb1; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = base + (uint32_t)s * (uint32_t)STAGE_BYTES;
+          const uint32_t lo_a = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t lo_b = (((sa + NPAIR * A_BOX) >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t first_kb = (uint32_t)(kb != T.kb0);
+#pragma unroll
+          for (int d = 0; d < S; ++d) {
+#pragma unroll
+            for (int tt = 0; tt <= d; ++tt) {
+              const int u = d - tt;
+              // digit x of an operand: box x >> 1, bytes 64 (x & 1) .. +63 of its 128-byte rows (+4 in the address field)
+              const uint32_t a0 = lo_a + (uint32_t)((tt >> 1) * (A_BOX >> 4) + (tt & 1) * 4);
+              const uint32_t b0 = lo_b + (uint32_t)((u >> 1) * (B_BOX >> 4) + (u & 1) * 4);
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {  // 32 bytes along K per instruction = +2 in the address field
+                const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(a0 + 2u * kk);
+                const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(b0 + 2u * kk);
+                // the first product of a diagonal in this tile overwrites its accumulator
+                umma_i8(tmem_base + (uint32_t)(d * BN), da, db, (tt == 0 && kk == 0) ? first_kb : 1u);
+              }
+            }
+          }
+          umma_commit(empty_bar(s));                    // frees the stage once these MMAs have read it
+          if (kb == T.kb1 - 1) umma_commit(tfull_bar);  // accumulators complete
+        }
+        __syncwarp();
+        if (++s == NSTAGE) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes 32 (w & 3) .. +31 = tile rows =====
+    // Phase 1 drains the seven accumulators into 64 FP64 values per thread and hands TMEM back at once, so the MMAs of the next
+    // tile run under phase 2, the slow part: the read-modify-write of C, coalesced through a small per-warp staging tile.
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    double *stg = reinterpret_cast<double *>(smem_raw + (base - smem_u32(smem_raw)) + (size_t)NSTAGE * STAGE_BYTES) +
+                  (size_t)quarter * 32 * EPI_LD;
+    const double c35 = 2.9103830456733704e-11 /* 2^-35 */, c56 = 1.3877787807814457e-17 /* 2^-56 */;
+    const int cc = lane & 15, rr = lane >> 4;
+    uint32_t nt = 0;
+    for (int t = first; t < last; t += step) {
+      const Tile T = decode_tile(P, t, tm, tn);
+      if (!T.valid) continue;
+      const long long m0 = (long long)T.im * BM, n0 = (long long)T.jn * BN;
+      const double ra = P.alpha * P.sa[T.b * P.rowsA + m0 + row];
+      const double *sb = P.sb + T.b * P.rowsB + n0;
+      double *Ct = P.C + T.b * P.strideC + (m0 + quarter * 32) * P.ldc + n0;
+      double old[16];
+      if (P.beta) {  // the first 16 columns of C are on their way while the accumulators are still being computed
+#pragma unroll
+        for (int i = 0; i < 16; ++i) old[i] = Ct[(long long)(2 * i + rr) * P.ldc + cc];
+      }
+      mbar_wait(tfull_bar, nt & 1u);
+      ++nt;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      double val[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 8; ++c) {
+        long long hi[8], lo[8];
+#pragma unroll
+        for (int d = 0; d < S; ++d) {
+          uint32_t v[8];
+          tmem_ld8(taddr + (uint32_t)(d * BN + c * 8), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long x = (long long)(int)v[j];
+            if (d == 0) hi[j] = x << 21;
+            if (d == 1) hi[j] += x << 14;
+            if (d == 2) hi[j] += x << 7;
+            if (d == 3) hi[j] += x;
+            if (d == 4) lo[j] = x << 14;
+            if (d == 5) lo[j] += x << 7;
+            if (d == 6) lo[j] += x;
+          }
+        }
+        // both conversions are exact (|hi|, |lo| < 2^53), the sum rounds once; row scale folded in (a power of two times +-1)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) val[c * 8 + j] = ra * fma((double)hi[j], c35, (double)lo[j] * c56);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);  // TMEM is free again
+#pragma unroll
+      for (int c = 0; c < BN / EPI_COLS; ++c) {
+#pragma unroll
+        for (int j = 0; j < EPI_COLS; ++j) stg[lane * EPI_LD + j] = val[c * EPI_COLS + j];
+        __syncwarp();
+        const double cs = sb[c * EPI_COLS + cc];
+        // coalesced: 2 rows x 16 columns (2 x 128 bytes) per warp instruction
+        double out[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const double x = stg[(2 * i + rr) * EPI_LD + cc] * cs;
+          out[i] = P.beta ? old[i] + x : x;
+        }
+        if (P.beta && c + 1 < BN / EPI_COLS) {  // next chunk's C values: in flight during this chunk's stores
+#pragma unroll
+          for (int i = 0; i < 16; ++i) old[i] = Ct[(long long)(2 * i + rr) * P.ldc + (c + 1) * EPI_COLS + cc];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Ct[(long long)(2 * i + rr) * P.ldc + c * EPI_COLS + cc] = out[i];
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- slicing
+// digits of one value already scaled to |x| < 1/2:  d_t = rint(rem 2^(7 (t+1))), rem -= d_t 2^(-7 (t+1))  (every step exact)
+__device__ __forceinline__ void digits7(double x, int (&d)[S]) {
+  double scale = 128.0;
+#pragma unroll
+  for (int t = 0; t < S; ++t) {
+    const double q = rint(x * scale);
+    x -= q / scale;
+    d[t] = (int)q;
+    scale *= 128.0;
+  }
+}
+// exponent e with |mx / 2^e| < 1/2 (0 for an all-zero row) and the two powers of two that go with it
+__device__ __forceinline__ void row_exponent(double mx, double &inv_scale, double &scale) {
+  int e0 = 0;
+  frexp(mx, &e0);  // mx = f 2^e0, f in [1/2, 1)
+  const int e = (mx > 0.0) ? e0 + 1 : 0;
+  inv_scale = ldexp(1.0, -e);
+  scale = ldexp(1.0, e);
+}
+
+// operand element (r, kk) = src[r * ld + kk]: one warp per row; lanes take 4 consecutive k each
+__global__ void __launch_bounds__(256) slice_rows_kernel(const double *__restrict__ src, long long ld, long long stride_b, int rows,
+                                                         int k, int batch, long long rows_b, int8_t *__restrict__ dig,
+                                                         long long pitch, double *__restrict__ scale_out) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)rows * batch) return;
+  const int b = (int)(wid / rows), r = (int)(wid - (long long)b * rows);
+  const double *a = src + b * stride_b + (long long)r * ld;
+  const long long R = b * rows_b + r;
+  double mx = 0.0;
+  for (int j = lane * 2; j < k; j += 64) {
+    const double2 v = *reinterpret_cast<const double2 *>(a + j);
+    mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+  }
+  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  double inv, sc;
+  row_exponent(mx, inv, sc);
+  if (lane == 0) scale_out[R] = sc;
+  int8_t *drow = dig + R * pitch;
+  for (int j = lane * 4; j < k; j += 128) {
+    const double2 v0 = *reinterpret_cast<const double2 *>(a + j), v1 = *reinterpret_cast<const double2 *>(a + j + 2);
+    int d0[S], d1[S], d2[S], d3[S];
+    digits7(v0.x * inv, d0);
+    digits7(v0.y * inv, d1);
+    digits7(v1.x * inv, d2);
+    digits7(v1.y * inv, d3);
+    int8_t *p = drow + (long long)(j / KBLK) * (SLOTS * KBLK) + (j % KBLK);
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      const uint32_t w = (uint32_t)(d0[t] & 0xff) | ((uint32_t)(d1[t] & 0xff) << 8) | ((uint32_t)(d2[t] & 0xff) << 16) |
+                         ((uint32_t)(d3[t] & 0xff) << 24);
+      *reinterpret_cast<uint32_t *>(p + t * KBLK) = w;
+    }
+  }
+}
+
+// operand element (r, kk) = src[kk * ld + r] (operand rows = columns of a row-major matrix)
+// pass 1: column maxima (|x| as ordered 64-bit patterns, atomicMax)
+__global__ void __launch_bounds__(256) col_absmax_kernel(const double *__restrict__ src, long long ld, long long stride_b, int rows,
+                                                         int k, long long rows_b, unsigned long long *__restrict__ mx_out) {
+  __shared__ double sh[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int r = blockIdx.x * 32 + x;
+  const int kchunk = (k + gridDim.y - 1) / gridDim.y;
+  const int k0 = blockIdx.y * kchunk, k1 = min(k, k0 + kchunk);
+  const double *a = src + b * stride_b + r;
+  double mx = 0.0;
+  if (r < rows)
+    for (int kk = k0 + y; kk < k1; kk += 8) mx = fmax(mx, fabs(a[(long long)kk * ld]));
+  sh[y][x] = mx;
+  __syncthreads();
+  if (y == 0 && r < rows) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmax(mx, sh[i][x]);
+    atomicMax(mx_out + b * rows_b + r, (unsigned long long)__double_as_longlong(mx));
+  }
+}
+// pass 2: 64 (k) x 64 (r) tiles through shared memory, digits written 64 bytes per (row, digit)
+__global__ void __launch_bounds__(256) slice_cols_kernel(const double *__restrict__ src, long long ld, long long stride_b, int rows,
+                                                         int k, long long rows_b, const unsigned long long *__restrict__ mx_in,
+                                                         int8_t *__restrict__ dig, long long pitch, double *__restrict__ scale_out) {
+  __shared__ double tile[64][65];  // [r][kk]
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.x * 64, kb = blockIdx.y;
+  const double *a = src + b * stride_b + (long long)kb * KBLK * ld + r0;
+  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+    const int kk = e >> 6, r = e & 63;
+    tile[r][kk] = a[(long long)kk * ld + r];
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < 64 * 16; item += 256) {
+    const int r = item >> 4, g = item & 15;
+    const long long R = b * rows_b + r0 + r;
+    double inv, sc;
+    row_exponent(__longlong_as_double((long long)mx_in[R]), inv, sc);
+    if (kb == 0 && g == 0) scale_out[R] = sc;
+    int d0[S], d1[S], d2[S], d3[S];
+    digits7(tile[r][4 * g + 0] * inv, d0);
+    digits7(tile[r][4 * g + 1] * inv, d1);
+    digits7(tile[r][4 * g + 2] * inv, d2);
+    digits7(tile[r][4 * g + 3] * inv, d3);
+    int8_t *p = dig + R * pitch + (long long)kb * (SLOTS * KBLK) + 4 * g;
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      const uint32_t w = (uint32_t)(d0[t] & 0xff) | ((uint32_t)(d1[t] & 0xff) << 8) | ((uint32_t)(d2[t] & 0xff) << 16) |
+                         ((uint32_t)(d3[t] & 0xff) << 24);
+      *reinterpret_cast<uint32_t *>(p + t * KBLK) = w;
+    }
+  }
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int32_t make_digit_map(gdca_ctx *ctx, CUtensorMap *map, const void *dig, long long rows_total, long long pitch, int box_rows) {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GDCA_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess)
+      return gdca_fail(ctx, GDCA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    fn = (encode_tiled_fn)p;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)rows_total};
+  const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+  const cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(dig), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[96];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled (digit matrix) failed with CUresult %d", (int)r);
+    ctx->err = b;
+    return GDCA_ERR_CUDA;
+  }
+  return GDCA_OK;
+}
+
+}  // namespace
+
+// Slice `batch` operands of `rows` x `k` (rows stacked rows_b apart in the digit matrix) into `out`.
+//   cols == false: element (r, kk) = src[b * stride_b + r * ld + kk];  cols == true: element (r, kk) = src[b * stride_b + kk * ld + r]
+int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, long long ld, long long stride_b, bool cols, int rows,
+                      int k, int batch, long long rows_b, int8_t *dig, double *scale, gdca_oz_operand *out) {
+  if (rows % 64 || k % 128 || rows <= 0 || k <= 0 || batch <= 0)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "oz_slice: rows must be a multiple of 64 and k a multiple of 128");
+  const long long pitch = (long long)(k / KBLK) * SLOTS * KBLK;
+  const long long rows_total = (long long)(batch - 1) * rows_b + rows;
+  if (!cols) {
+    const long long warps = (long long)rows * batch;
+    slice_rows_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(src, ld, stride_b, rows, k, batch, rows_b, dig, pitch, scale);
+    GDCA_LAUNCH_CHECK(ctx);
+  } else {
+    GDCA_TRY(gdca_reserve(ctx, ctx->dOzMax, ctx->capOzMax, (size_t)ctx->npad > (size_t)rows_total ? (size_t)ctx->npad : (size_t)rows_total));
+    GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dOzMax, 0, (size_t)rows_total * sizeof(unsigned long long), stream));
+    int ksplit = k / 512;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > 32) ksplit = 32;
+    col_absmax_kernel<<<dim3((unsigned)((rows + 31) / 32), (unsigned)ksplit, (unsigned)batch), 256, 0, stream>>>(
+        src, ld, stride_b, rows, k, rows_b, ctx->dOzMax);
+    GDCA_LAUNCH_CHECK(ctx);
+    slice_cols_kernel<<<dim3((unsigned)(rows / 64), (unsigned)(k / KBLK), (unsigned)batch), 256, 0, stream>>>(
+        src, ld, stride_b, rows, k, rows_b, ctx->dOzMax, dig, pitch, scale);
+    GDCA_LAUNCH_CHECK(ctx);
+  }
+  out->dig = dig;
+  out->scale = scale;
+  out->pitch = pitch;
+  out->rows_total = rows_total;
+  out->rows_b = rows_b;
+  return GDCA_OK;
+}
+
+// C[b] (+)= alpha A[b] B[b]^T on the INT8 tensor cores.  m % 128 == 0, n % 64 == 0, k % 128 == 0.
+int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &A, const gdca_oz_operand &B, double *C, long long ldc,
+                     long long strideC, int m, int n, int k, int batch, int flags, double alpha, int beta, int tiles_per_cta) {
+  if (m <= 0 || n <= 0 || batch <= 0) return GDCA_OK;
+  if (m % BM || n % BN || k % 128 || (long long)(k / KBLK) * SLOTS * KBLK > A.pitch || A.pitch != B.pitch)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "oz_gemm: shape / pitch mismatch (m % 128, n % 64, k % 128, same k padding)");
+  if (((flags & GDCA_OZ_KBEG_M) && m > k) || ((flags & GDCA_OZ_KBEG_N) && n > k))
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "oz_gemm: triangular k range would be empty");
+  CUtensorMap mapA, mapB;
+  GDCA_TRY(make_digit_map(ctx, &mapA, A.dig, A.rows_total, A.pitch, BM));
+  GDCA_TRY(make_digit_map(ctx, &mapB, B.dig, B.rows_total, B.pitch, BN));
+  OzGemmP P;
+  P.C = C;
+  P.ldc = ldc;
+  P.strideC = strideC;
+  P.sa = A.scale;
+  P.sb = B.scale;
+  P.rowsA = A.rows_b;
+  P.rowsB = B.rows_b;
+  P.m = m;
+  P.n = n;
+  P.k = k;
+  P.batch = batch;
+  P.flags = flags;
+  P.beta = beta;
+  P.tiles_per_cta = tiles_per_cta;
+  P.alpha = alpha;
+  P.info = ctx->dInfo;
+  P.tri = ((flags & GDCA_OZ_LOWER_OUT) && batch == 1 && m == n && !(flags & GDCA_OZ_KBEG_N)) ? 1 : 0;
+  const long long total = P.tri ? (long long)(m / BM) * (m / BM + 1) : (long long)batch * (m / BM) * (n / BN);
+  P.total = (int)total;
+  long long grid = tiles_per_cta > 0 ? (total + tiles_per_cta - 1) / tiles_per_cta : (total < ctx->num_sms ? total : ctx->num_sms);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GDCA_CUDA(ctx, cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    attr_set = true;
+  }
+  ozaki_gemm_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, stream>>>(mapA, mapB, P);
+  GDCA_LAUNCH_CHECK(ctx);
+  // INT8 operations this launch executes (valid tiles x their k ranges x 28 digit products), for the bench line
+  double ops = 0.0;
+  const int tm = m / BM, tn = n / BN;
+  for (int im = 0; im < tm; ++im)
+    for (int jn = 0; jn < tn; ++jn) {
+      const int m0 = im * BM, n0 = jn * BN;
+      if ((flags & GDCA_OZ_LOWER_OUT) && n0 >= m0 + BM) continue;
+      int kbeg = 0, kend = k;
+      if (flags & GDCA_OZ_KBEG_N) kbeg = kbeg > (n0 / 128) * 128 ? kbeg : (n0 / 128) * 128;
+      if (flags & GDCA_OZ_KBEG_M) kbeg = kbeg > m0 ? kbeg : m0;
+      if (flags & GDCA_OZ_KEND_M) kend = kend < m0 + BM ? kend : m0 + BM;
+      if (kend > kbeg) ops += 2.0 * BM * BN * (double)(kend - kbeg) * 28.0;
+    }
+  ctx->oz_int8_ops += ops * batch;
+  return GDCA_OK;
+}

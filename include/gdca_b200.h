@@ -193,6 +193,19 @@ void *gdca_dev_C_ptr(gdca_ctx *ctx);  /* [npad][npad] f64, leading dimension gdc
 int64_t gdca_dev_npad(gdca_ctx *ctx);
 void *gdca_dev_W_ptr(gdca_ctx *ctx);  /* f64[M] */
 int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info); /* C -> mJ on this device */
+/* Engine of the big FP64 products of the inversion (trailing updates of the Cholesky, trtri levels, lauum) for n >= 2048:
+ * 1 (default; env GDCA_OZAKI overrides): INT8-sliced on the tcgen05 tensor cores -- every operand row is split exactly into seven
+ * signed 7-bit digits, the 28 digit products with t + u < 7 accumulate exactly in S32 (tcgen05.mma kind::i8, TMEM) and are recombined
+ * in FP64 with one rounding (csrc/ozaki.cu; mJ stays within ~1e-12 normwise of the DMMA path);  0: FP64 tensor cores (DMMA) only. */
+int32_t gdca_set_ozaki(gdca_ctx *ctx, int32_t mode);
+/* what the last inversion ran: *ozaki 0/1, the INT8 operations executed and the FP64 flop they stand for */
+int32_t gdca_dev_inverse_info(gdca_ctx *ctx, int32_t *ozaki, double *int8_ops, double *fp64_flop_on_int8);
+/* Test hook (tests/test_gpu_ozaki.py): C[m x n] = beta C + alpha opA opB^T on one FP64 GEMM engine, host buffers, contiguous
+ * matrices.  engine 0: dgemm_kernel (DMMA), 1: INT8-sliced tcgen05 kernel (beta 0 or 1).  A is [m][k] (a_cols = 0) or [k][m]
+ * (a_cols = 1), B is [n][k] (b_cols = 0) or [k][n] (b_cols = 1).  flags: 1 skip output tiles above the diagonal, 2 k starts at
+ * n0 (B lower triangular as [k][n]), 4 k starts at m0 (A lower triangular as [k][m]), 8 k ends at m0 + 128.  m, n, k % 128 == 0. */
+int32_t gdca_test_fp64_gemm(gdca_ctx *ctx, int32_t engine, const double *A, int32_t a_cols, const double *B, int32_t b_cols,
+                            double *C, int64_t m, int64_t n, int64_t k, int32_t flags, double alpha, double beta);
 void *gdca_dev_mJ_ptr(gdca_ctx *ctx);
 int32_t gdca_dev_score_rank(gdca_ctx *ctx, int32_t score, int64_t min_separation, gdca_rank_t *R_host, int64_t R_len);
 void *gdca_dev_S_ptr(gdca_ctx *ctx); /* L x L APC-corrected scores after gdca_dev_score_rank */

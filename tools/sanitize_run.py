@@ -6,6 +6,11 @@ import __graft_entry__ as g
 pkg = g.load_package()
 orc = g.load_oracle()
 ctx = pkg.Context(0)
+# force the tcgen05 / TMA / TMEM prefilter on (it switches itself on only for M >= 16384): the sanitized path is then the
+# whole production path -- prefilter -> exact sweep of the flagged blocks -> covariance -> inverse -> scores -> ranking
+import os
+if os.environ.get("GDCA_SANITIZE_FILTER", "1") != "0":
+    ctx.check(ctx.lib.gdca_set_tc_filter(ctx.h, 2))
 R = pkg.gDCA("tests/golden/small.fasta.gz", ctx=ctx)
 print("small frob", R[0])
 R = pkg.gDCA("tests/golden/small.fasta.gz", pseudocount=0.2, score="DI", remove_dups=True, ctx=ctx)
