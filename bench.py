@@ -665,7 +665,7 @@ def _inverse_info(ctx, lib):
         ctx.check(fn(ctx.h, ctypes.byref(mode), ctypes.byref(ms_oz), ctypes.byref(tops)))
         if not mode.value:
             return {}
-        return {"kernel": "ozaki_gemm_kernel (FP64 GEMMs of potrf / trtri / lauum as 28 INT8 tcgen05 kind::i8 digit products, S32 in "
+        return {"kernel": "ozaki_gemm_kernel (FP64 GEMMs of potrf / trtri / lauum as 36 INT8 tcgen05 kind::i8 digit products, S32 in "
                           "TMEM, FP64 recombination) + dgemm_kernel<*> / diag_block_kernel (DMMA) for panels and diagonal blocks",
                 "int8_tops_executed": tops.value, "int8_peak_nominal_tops": 4500.0}
     except Exception:  # noqa: BLE001

@@ -3,22 +3,24 @@
 // tcgen05 has no FP64 kind; the FP64 tensor path of sm_100a is the warp-level DMMA (37 TFLOP/s measured), and chol.cu's
 // products run at 0.7-0.9 of it.  This file gets past that wall with an Ozaki-style error-free split:
 //
-//   slice    every operand row is scaled by a power of two 2^e (|a / 2^e| < 1/2) and cut into S = 7 signed 7-bit digits,
-//                a / 2^e = sum_t d_t 2^(-7 (t+1)) + r,   |d_t| <= 64,  |r| <= 2^-50,
-//            stored as int8, K-major: dig[row][k-block of 64][digit slot 0..7][64 bytes]  (slot 7 unused), so that one
-//            128-byte row of a TMA box carries the SAME 64 k-elements of two consecutive digits;
-//   multiply D_d = sum_{t+u=d} A_t B_u^T for d = 0..6 (28 digit products, t + u < 7) with tcgen05.mma kind::i8: exact S32
-//            accumulation (|D_d| <= 7 k 64^2 < 2^31 for k <= 74 000), one 128 x 64 output tile with all seven diagonal
-//            accumulators resident in TMEM (7 x 64 = 448 of the 512 columns);
-//   combine  hi = D_0 2^21 + D_1 2^14 + D_2 2^7 + D_3 and lo = D_4 2^14 + D_5 2^7 + D_6 as exact int64, then
-//            C (+)= alpha 2^(e_i + f_j) (hi 2^-35 + lo 2^-56): two exact conversions and ONE rounding -- the correctly
-//            rounded value of the exact sum of the 28 digit products.
+//   slice    every operand row is scaled by a power of two 2^e (|a / 2^e| < 1/2) and cut into S = 8 signed 7-bit digits,
+//                a / 2^e = sum_t d_t 2^(-7 (t+1)) + r,   |d_t| <= 64,  |r| <= 2^-57,
+//            stored as int8, K-major: dig[row][k-block of 64][digit 0..7][64 bytes], so that one 128-byte row of a TMA box
+//            carries the SAME 64 k-elements of two consecutive digits;
+//   multiply D_d = sum_{t+u=d} A_t B_u^T for d = 0..7 (36 digit products, t + u < 8) with tcgen05.mma kind::i8: exact S32
+//            accumulation (|D_d| <= 8 k 64^2 < 2^31 for k <= 65 000), one 128 x 64 output tile with all eight diagonal
+//            accumulators resident in TMEM (8 x 64 = all 512 columns);
+//   combine  hi = D_0 2^21 + D_1 2^14 + D_2 2^7 + D_3 and lo = D_4 2^21 + D_5 2^14 + D_6 2^7 + D_7 as exact int64, then
+//            C (+)= alpha 2^(e_i + f_j) (hi 2^-35 + lo 2^-63): two exact conversions and ONE rounding -- the correctly
+//            rounded value of the exact sum of the 36 digit products.
 //
-// Error: the product differs from the FP64 one by <= ~2^-49 |row scale| |column scale| k (the dropped digits), which keeps
-// the blocked Cholesky + inverse at ~4e-13 normwise on mJ (tools/ozaki_numerics.py; tolerance 1e-9, blocked FP64 3e-15).
+// Error: the product differs from the exact one by <= ~2^-56 |row scale| |column scale| per term (the dropped digits):
+// finer than the rounding of an FP64 dot product.  Seven digits (28 products, 2^-49) already keep mJ at ~4e-13 normwise
+// (tools/ozaki_numerics.py), but the reference's own golden test compares near-zero APC scores at 7 printed digits
+// (test/runtests.jl:41-50, large.DIRout.txt) and that needs FP64-grade noise -- hence eight.
 //
 // Kernel: the warp-specialised structure of tcfilter.cu -- warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps
-// 2..5 epilogue (one TMEM lane quarter each) -- 2-stage ring of 96 KB (4 + 4 SWIZZLE_128B boxes per 64-wide k-block), 56 MMAs
+// 2..5 epilogue (one TMEM lane quarter each) -- 2-stage ring of 96 KB (4 + 4 SWIZZLE_128B boxes per 64-wide k-block), 72 MMAs
 // of 128 x 64 x 32 per stage, triangular operands handled as per-tile k ranges, batched launches for the trtri levels.
 // The epilogue goes through a small padded shared-memory tile so that the FP64 read-modify-write of C is coalesced.
 #include <cuda.h>  // CUtensorMap (types only)
@@ -27,12 +29,12 @@
 
 namespace {
 
-constexpr int S = 7;             // digits per operand
+constexpr int S = 8;             // digits per operand (56 bits below the row exponent: finer than the FP64 significand)
 constexpr int BM = 128;          // tile rows
-constexpr int BN = 64;           // tile columns: 7 accumulators x 64 columns = 448 TMEM columns
+constexpr int BN = 64;           // tile columns: 8 accumulators x 64 columns = all 512 TMEM columns
 constexpr int KBLK = 64;         // k elements per k-block (= bytes per digit and row in a stage)
-constexpr int SLOTS = 8;         // digit slots per k-block in memory (7 used)
-constexpr int NPAIR = 4;         // TMA boxes per operand and k-block: digit pairs (0,1) (2,3) (4,5) (6,-)
+constexpr int SLOTS = 8;         // digit slots per k-block in memory
+constexpr int NPAIR = 4;         // TMA boxes per operand and k-block: digit pairs (0,1) (2,3) (4,5) (6,7)
 constexpr int A_BOX = BM * 128;  // 16 KB
 constexpr int B_BOX = BN * 128;  // 8 KB
 constexpr int STAGE_BYTES = NPAIR * (A_BOX + B_BOX);  // 96 KB
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     const int row = quarter * 32 + lane;
     double *stg = reinterpret_cast<double *>(smem_raw + (base - smem_u32(smem_raw)) + (size_t)NSTAGE * STAGE_BYTES) +
                   (size_t)quarter * 32 * EPI_LD;
-    const double c35 = 2.9103830456733704e-11 /* 2^-35 */, c56 = 1.3877787807814457e-17 /* 2^-56 */;
+    const double c35 = 2.9103830456733704e-11 /* 2^-35 */, c63 = 1.0842021724855044e-19 /* 2^-63 */;
     const int cc = lane & 15, rr = lane >> 4;
     uint32_t nt = 0;
     for (int t = first; t < last; t += step) {
@@ -338,14 +340,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
             if (d == 1) hi[j] += x << 14;
             if (d == 2) hi[j] += x << 7;
             if (d == 3) hi[j] += x;
-            if (d == 4) lo[j] = x << 14;
-            if (d == 5) lo[j] += x << 7;
-            if (d == 6) lo[j] += x;
+            if (d == 4) lo[j] = x << 21;
+            if (d == 5) lo[j] += x << 14;
+            if (d == 6) lo[j] += x << 7;
+            if (d == 7) lo[j] += x;
           }
         }
         // both conversions are exact (|hi|, |lo| < 2^53), the sum rounds once; row scale folded in (a power of two times +-1)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) val[c * 8 + j] = ra * fma((double)hi[j], c35, (double)lo[j] * c56);
+        for (int j = 0; j < 8; ++j) val[c * 8 + j] = ra * fma((double)hi[j], c35, (double)lo[j] * c63);
       }
       tc_fence_before();
       __syncwarp();
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 
 // ---------------------------------------------------------------------------------------------- slicing
 // digits of one value already scaled to |x| < 1/2:  d_t = rint(rem 2^(7 (t+1))), rem -= d_t 2^(-7 (t+1))  (every step exact)
-__device__ __forceinline__ void digits7(double x, int (&d)[S]) {
+__device__ __forceinline__ void digits8(double x, int (&d)[S]) {
   double scale = 128.0;
 #pragma unroll
   for (int t = 0; t < S; ++t) {
@@ -426,10 +429,10 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double *__restric
   for (int j = lane * 4; j < k; j += 128) {
     const double2 v0 = *reinterpret_cast<const double2 *>(a + j), v1 = *reinterpret_cast<const double2 *>(a + j + 2);
     int d0[S], d1[S], d2[S], d3[S];
-    digits7(v0.x * inv, d0);
-    digits7(v0.y * inv, d1);
-    digits7(v1.x * inv, d2);
-    digits7(v1.y * inv, d3);
+    digits8(v0.x * inv, d0);
+    digits8(v0.y * inv, d1);
+    digits8(v1.x * inv, d2);
+    digits8(v1.y * inv, d3);
     int8_t *p = drow + (long long)(j / KBLK) * (SLOTS * KBLK) + (j % KBLK);
 #pragma unroll
     for (int t = 0; t < S; ++t) {
@@ -482,10 +485,10 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double *__restric
     row_exponent(__longlong_as_double((long long)mx_in[R]), inv, sc);
     if (kb == 0 && g == 0) scale_out[R] = sc;
     int d0[S], d1[S], d2[S], d3[S];
-    digits7(tile[r][4 * g + 0] * inv, d0);
-    digits7(tile[r][4 * g + 1] * inv, d1);
-    digits7(tile[r][4 * g + 2] * inv, d2);
-    digits7(tile[r][4 * g + 3] * inv, d3);
+    digits8(tile[r][4 * g + 0] * inv, d0);
+    digits8(tile[r][4 * g + 1] * inv, d1);
+    digits8(tile[r][4 * g + 2] * inv, d2);
+    digits8(tile[r][4 * g + 3] * inv, d3);
     int8_t *p = dig + R * pitch + (long long)kb * (SLOTS * KBLK) + 4 * g;
 #pragma unroll
     for (int t = 0; t < S; ++t) {
@@ -611,7 +614,7 @@ int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &
       if (flags & GDCA_OZ_KBEG_N) kbeg = kbeg > (n0 / 128) * 128 ? kbeg : (n0 / 128) * 128;
       if (flags & GDCA_OZ_KBEG_M) kbeg = kbeg > m0 ? kbeg : m0;
       if (flags & GDCA_OZ_KEND_M) kend = kend < m0 + BM ? kend : m0 + BM;
-      if (kend > kbeg) ops += 2.0 * BM * BN * (double)(kend - kbeg) * 28.0;
+      if (kend > kbeg) ops += 2.0 * BM * BN * (double)(kend - kbeg) * (double)(S * (S + 1) / 2);
     }
   ctx->oz_int8_ops += ops * batch;
   return GDCA_OK;

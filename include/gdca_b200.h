@@ -194,8 +194,8 @@ int64_t gdca_dev_npad(gdca_ctx *ctx);
 void *gdca_dev_W_ptr(gdca_ctx *ctx);  /* f64[M] */
 int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info); /* C -> mJ on this device */
 /* Engine of the big FP64 products of the inversion (trailing updates of the Cholesky, trtri levels, lauum) for n >= 2048:
- * 1 (default; env GDCA_OZAKI overrides): INT8-sliced on the tcgen05 tensor cores -- every operand row is split exactly into seven
- * signed 7-bit digits, the 28 digit products with t + u < 7 accumulate exactly in S32 (tcgen05.mma kind::i8, TMEM) and are recombined
+ * 1 (default; env GDCA_OZAKI overrides): INT8-sliced on the tcgen05 tensor cores -- every operand row is split exactly into eight
+ * signed 7-bit digits, the 36 digit products with t + u < 8 accumulate exactly in S32 (tcgen05.mma kind::i8, TMEM) and are recombined
  * in FP64 with one rounding (csrc/ozaki.cu; mJ stays within ~1e-12 normwise of the DMMA path);  0: FP64 tensor cores (DMMA) only. */
 int32_t gdca_set_ozaki(gdca_ctx *ctx, int32_t mode);
 /* what the last inversion ran: *ozaki 0/1, the INT8 operations executed and the FP64 flop they stand for */
