@@ -304,18 +304,14 @@ class Runner:
         self.st = glib.Stats()
 
     def barrier(self):
-        self.torch.cuda.synchronize()
-        if self.dist is not None:
-            self.dist.barrier()
-        self.torch.cuda.synchronize()
+        for d in range(self.world):
+            self.torch.cuda.synchronize(d)
 
     def step_resident(self):
-        if self.world == 1:
-            self.ctx.check(self.lib.gdca_run_resident(self.ctx.h, ctypes.c_void_p(self.Zd.data_ptr()), self.L, self.M, -1.0, self.pc,
-                                                      self.glib.SCORE_CODES[self.score], MIN_SEP, None, self.n_out,
-                                                      ctypes.byref(self.st)))
-            return None
-        return self.gdist.gdca_sharded(self.Zd, self.pc, "auto", self.score, MIN_SEP, ctx=self.ctx, resident=True)
+        # one device or a device group: the same C ABI call (gdca_create_multi contexts shard the step over their GPUs)
+        self.ctx.check(self.lib.gdca_run_resident(self.ctx.h, ctypes.c_void_p(self.Zd.data_ptr()), self.L, self.M, -1.0, self.pc,
+                                                  self.glib.SCORE_CODES[self.score], MIN_SEP, None, self.n_out,
+                                                  ctypes.byref(self.st)))
 
     def timed_resident(self, W, K, flush):
         torch = self.torch
@@ -330,62 +326,39 @@ class Runner:
             a.record(self.stream)
             self.step_resident()
             b.record(self.stream)
-            if self.world == 1:
-                for k, v in self.st.asdict().items():
-                    if k.startswith("ms_"):
-                        acc[k] = acc.get(k, 0.0) + v / K
+            for k, v in self.st.asdict().items():
+                if k.startswith("ms_"):
+                    acc[k] = acc.get(k, 0.0) + v / K
         self.barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev) / K
-        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
-        if self.dist is not None:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return float(t.item()), acc
+        ms = sum(a.elapsed_time(b) for a, b in ev) / K   # events on the leader's stream: it waits for every member at each exchange
+        return ms, acc
 
     def e2e(self, K, flush, pinned=True):
         """gdca_run() on HOST buffers: H2D of Z and D2H of R inside the timed region (CUDA events of the library: before the
         H2D copy .. after the D2H copy).  Returns (seconds, R, stats)."""
         torch, np = self.torch, self.np
         L, M = self.L, self.M
-        if self.world == 1:
-            if pinned:
-                Zh = torch.empty((M, L), dtype=torch.int8).pin_memory()
-                Zh.copy_(self.Zd)
-                Rh = torch.empty(self.n_out * 24, dtype=torch.uint8).pin_memory()
-                zp, rp = Zh.data_ptr(), Rh.data_ptr()
-            else:
-                Zn = self.Zd.cpu().numpy().copy()                       # plain pageable numpy memory
-                Rn = np.empty(self.n_out, dtype=self.glib.RANK_DTYPE)
-                zp, rp = Zn.ctypes.data, Rn.ctypes.data
-            e_ms = []
-            for it in range(1 + K):
-                flush()
-                torch.cuda.synchronize()
-                self.ctx.check(self.lib.gdca_run(self.ctx.h, ctypes.c_void_p(zp), L, M, -1.0, self.pc,
-                                                 self.glib.SCORE_CODES[self.score], MIN_SEP, ctypes.c_void_p(rp), self.n_out,
-                                                 ctypes.byref(self.st)))
-                if it >= 1:
-                    e_ms.append(self.st.ms_total)
-            R = (np.frombuffer(Rh.numpy(), dtype=self.glib.RANK_DTYPE) if pinned else Rn).copy()
-            return sum(e_ms) / len(e_ms) / 1e3, R, self.st.asdict(), L * M
-        # N > 1: the public sharded API with HOST input on every rank (H2D inside), ranking copied to the host on rank 0
-        Zh = torch.empty((M, L), dtype=torch.int8).pin_memory()
-        Zh.copy_(self.Zd)
-        Zn = Zh.numpy()
-        e_ms, R, info = [], None, None
+        if pinned:
+            Zh = torch.empty((M, L), dtype=torch.int8).pin_memory()
+            Zh.copy_(self.Zd)
+            Rh = torch.empty(self.n_out * 24, dtype=torch.uint8).pin_memory()
+            zp, rp = Zh.data_ptr(), Rh.data_ptr()
+        else:
+            Zn = self.Zd.cpu().numpy().copy()                       # plain pageable numpy memory
+            Rn = np.empty(self.n_out, dtype=self.glib.RANK_DTYPE)
+            zp, rp = Zn.ctypes.data, Rn.ctypes.data
+        e_ms = []
         for it in range(1 + K):
             flush()
-            self.barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(self.stream)
-            R, info = self.gdist.gdca_sharded(Zn, self.pc, "auto", self.score, MIN_SEP, ctx=self.ctx, resident=False)
-            b.record(self.stream)
-            self.barrier()
-            tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=self.dev)
-            self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
+            self.ctx.check(self.lib.gdca_run(self.ctx.h, ctypes.c_void_p(zp), L, M, -1.0, self.pc,
+                                             self.glib.SCORE_CODES[self.score], MIN_SEP, ctypes.c_void_p(rp), self.n_out,
+                                             ctypes.byref(self.st)))
             if it >= 1:
-                e_ms.append(float(tt.item()))
-        st = {"theta": info["theta"], "thresh": info["thresh"], "meff": info["meff"]}
-        return sum(e_ms) / len(e_ms) / 1e3, R, st, L * M * self.world
+                e_ms.append(self.st.ms_total)
+        R = (np.frombuffer(Rh.numpy(), dtype=self.glib.RANK_DTYPE) if pinned else Rn).copy()
+        # a device group copies the alignment to its first GPU ONCE (the other members get it over NVLink)
+        return sum(e_ms) / len(e_ms) / 1e3, R, self.st.asdict(), L * M
 
 
 def main():
@@ -413,17 +386,28 @@ def main():
     from gaussdca_jl_b200 import _lib as glib
     from gaussdca_jl_b200 import dist as gdist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    nproc = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != max(1, args.gpus) and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local)
+    world = max(1, args.gpus)          # GPUs the step runs on
+    if nproc > 1 and nproc != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={nproc}")
     dist = None
-    if world > 1:
+    if nproc > 1:
+        # Launched as one rank per GPU (torch.distributed.run).  The library drives a device group from ONE process
+        # (gdca_create_multi: peer access, cross-device stream waits, exchanges fused into the kernels), so rank 0 leads all
+        # `world` GPUs and the other ranks only keep the launch contract: they wait at the closing barrier.  The control plane is
+        # gloo on purpose -- an NCCL barrier would park a spinning kernel on every GPU for the length of the run.
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = pkg.Context(local)   # raises loudly without the CUDA library / a B200
+        dist.init_process_group("gloo")
+        if rank != 0:
+            dist.barrier()
+            dist.destroy_process_group()
+            return
+    local = 0
+    torch.cuda.set_device(0)
+    devices = list(range(world))
+    ctx = pkg.Context(devices=devices)   # raises loudly without the CUDA library / B200s with peer access
     lib = ctx.lib
     W = max(3, args.warmup)
     K = max(1, args.steps)
@@ -456,7 +440,7 @@ def main():
     e2e = {"value": e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": run.n_out * 24,
            "host_memory": "pinned (cudaHostAlloc)"}
     e2e_pageable = None
-    if world == 1:
+    if True:
         p_s, _, _, _ = run.e2e(min(K, 3), l2_flush, pinned=False)
         e2e_pageable = {"value": p_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": run.n_out * 24,
                         "host_memory": "pageable (numpy / a Julia Matrix{Int8}): cudaMemcpyAsync stages it through the driver"}
@@ -469,27 +453,8 @@ def main():
             cb = cpu_baseline_sampled(L, M, score, pc)
         else:
             cb, o_main = cpu_baseline_full("C" if name == "Cs" else name)
-            if world == 1:
-                # the last e2e call left counts / S on the device; R and stats are the host copies
-                parity = parity_vs_oracle(np, glib, ctx, o_main, M, L, R, est, perm=run.perm)
-            else:
-                parity = {"note": "N > 1: ranking of the sharded run vs the oracle",
-                          **{k: v for k, v in _rank_only_parity(np, o_main, L, R, est).items()}}
-
-    if rank != 0:
-        # rank 0 still times its shard of the sweep below, and that kernel adds its hits into EVERY rank's counters over
-        # peer memory: keep this rank's buffers alive until rank 0 is through; then take part in the other configs
-        dist.barrier()
-        if args.configs == "all" and name == "C":
-            del run
-            torch.cuda.empty_cache()
-            for other in ["E"]:
-                try:
-                    _measure_config(args, other, torch, np, pkg, glib, gdist, ctx, world, rank, local, dist, l2_flush)
-                except Exception as e:  # noqa: BLE001
-                    print(f"rank {rank}: config {other} failed: {e!r}", file=sys.stderr)
-        dist.destroy_process_group()
-        return
+            # the last e2e call left counts / S on the (leading) device; R and stats are the host copies
+            parity = parity_vs_oracle(np, glib, ctx, o_main, M, L, R, est, perm=run.perm)
 
     # ---- per-kernel rooflines, measured live
     pk = peaks()
@@ -569,12 +534,22 @@ def main():
     else:
         sweep_entry = {**exact, "traffic": ncu_traffic("pair_sweep_kernel<5, 1>") if world == 1 and name == "C" else None, **common}
     ctx.check(lib.gdca_set_shard(ctx.h, 0, 1))
-    if dist is not None:
-        torch.cuda.synchronize()
-        dist.barrier()          # releases the other ranks (see above)
 
     n = 20 * L
     roof, roof_kernels, stages = sweep_entry, None, None
+    if world > 1:
+        t_chol = (stage_acc.get("ms_chol", 0) + stage_acc.get("ms_inv", 0)) / 1e3
+        stages = {"ms": {k: round(v, 4) for k, v in stage_acc.items()},
+                  "note": "CUDA events on the leading device's stream; it waits for every member at each exchange"}
+        inv_info = _inverse_info(ctx, lib)
+        roof = {
+            "kernel": inv_info.get("kernel", "Cholesky + inverse") + f"; factorisation on the leading GPU, trtri / lauum shared by {world} GPUs",
+            "bound": "fp64_tensor", "achieved": n ** 3 / t_chol / 1e12, "peak": dmma.value * world, "unit": "TFLOP/s",
+            "frac": (n ** 3 / t_chol / 1e12) / (dmma.value * world),
+            "peak_source": f"{world} x the FP64 tensor (DMMA) rate measured live by gdca_probe_peaks on the leading GPU",
+            "ms_per_step": t_chol * 1e3, "share_of_step": t_chol * 1e3 / ms_step,
+            "sweep_shard_on_leader": sweep_entry,
+        }
     if world == 1:
         t_cov = stage_acc.get("ms_cov", 0) / 1e3
         t_chol = (stage_acc.get("ms_chol", 0) + stage_acc.get("ms_inv", 0)) / 1e3
@@ -628,7 +603,7 @@ def main():
         configs = []
         del run
         torch.cuda.empty_cache()
-        for other in (["B", "D", "Cs", "E"] if world == 1 else ["E"]):
+        for other in (["B", "D", "Cs", "E"] if world == 1 else ["E"]):   # E is the 8-GPU config of BASELINE.json
             try:
                 configs.append(_measure_config(args, other, torch, np, pkg, glib, gdist, ctx, world, rank, local, dist, l2_flush))
             except Exception as e:  # noqa: BLE001
@@ -640,10 +615,16 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_string(name), "seed": SEED, "generator": "SURVEY 8(d) clustered SplitMix64",
                    "l2": "256 MiB flush write between steps",
-                   "sharding": ("single GPU" if world == 1 else f"pair-matrix row blocks + covariance rows over {world} ranks, "
-                                "exchange fused into the kernels over CUDA-IPC peer memory; inverse+scores on rank 0"),
-                   "data_plane": (None if world == 1 else f"cuda-ipc peer memory (peer atomics / peer stores inside the kernels), "
-                                  f"{world} ranks verified by the imported handle table; NCCL carries handles and barriers only")},
+                   "sharding": ("single GPU" if world == 1 else
+                                f"device group of {world} GPUs behind one gdca_create_multi context (one process): alignment copied to "
+                                "GPU 0 once and broadcast over NVLink; pair-matrix row blocks (peer atomics), covariance rows (peer "
+                                "stores), trtri column slices (stored to every member) and lauum row tiles (stored to GPU 0) shared; "
+                                "Cholesky chain, scores, APC, ranking on GPU 0"),
+                   "data_plane": (None if world == 1 else
+                                  f"peer memory over NVLink inside the kernels (cudaDeviceEnablePeerAccess between all {world} devices, "
+                                  f"group size reported by the library: {int(lib.gdca_group_size(ctx.h))}); no collective library on the "
+                                  "data path; cross-device ordering by CUDA events"),
+                   "launch": (None if nproc == 1 else f"{nproc} ranks launched; rank 0 drives the group, the others wait (gloo barrier)")},
         "theta": est["theta"], "thresh": est["thresh"], "meff": est["meff"], "top_pair": top,
         "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(launches2 - launches1),
         "clocks": clocks, "parity": parity, "roofline": roof, "roofline_kernels": roof_kernels, "stages": stages,
@@ -652,6 +633,7 @@ def main():
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
+        dist.barrier()           # releases the other launched ranks
         dist.destroy_process_group()
 
 
@@ -670,22 +652,6 @@ def _inverse_info(ctx, lib):
                 "int8_tops_executed": tops.value, "int8_peak_nominal_tops": 4500.0}
     except Exception:  # noqa: BLE001
         return {}
-
-
-def _rank_only_parity(np, o, L, R, est):
-    Ro = o["R"]
-    smax = float(np.max(np.abs(Ro["score"])))
-    kg, ko = R["i"] * (L + 1) + R["j"], Ro["i"] * (L + 1) + Ro["j"]
-    og, oo = np.argsort(kg, kind="stable"), np.argsort(ko, kind="stable")
-    out = {"ranking_keys_equal": bool(np.array_equal(kg[og], ko[oo])),
-           "theta_equal": bool(est["theta"] == o["theta"]), "thresh_equal": bool(est["thresh"] == o["thresh"]),
-           "meff_equal": bool(est["meff"] == o["Meff"])}
-    if out["ranking_keys_equal"]:
-        out["ranking_score_normwise_err"] = float(np.max(np.abs(R["score"][og] - Ro["score"][oo])) / smax)
-    out["top_L_identical"] = bool(np.array_equal(R["i"][:L], Ro["i"][:L]) and np.array_equal(R["j"][:L], Ro["j"][:L]))
-    out["ok"] = bool(out["ranking_keys_equal"] and out["meff_equal"] and out["thresh_equal"] and out["top_L_identical"] and
-                     out.get("ranking_score_normwise_err", 1.0) <= TOL)
-    return out
 
 
 def _measure_config(args, name, torch, np, pkg, glib, gdist, ctx, world, rank, local, dist, l2_flush):
@@ -715,8 +681,7 @@ def _measure_config(args, name, torch, np, pkg, glib, gdist, ctx, world, rank, l
         else:
             cb, o = cpu_baseline_full("C" if name == "Cs" else name)
             entry["cpu_baseline"] = cb
-            entry["parity"] = (parity_vs_oracle(np, glib, ctx, o, M, L, R, est, perm=run.perm) if world == 1
-                               else _rank_only_parity(np, o, L, R, est))
+            entry["parity"] = parity_vs_oracle(np, glib, ctx, o, M, L, R, est, perm=run.perm)
     del run
     torch.cuda.empty_cache()
     return entry

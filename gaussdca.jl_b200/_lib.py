@@ -55,6 +55,8 @@ _pi32, _pi64, _pu64, _pdbl = (ctypes.POINTER(t) for t in (_i32, _i64, _u64, _dbl
 SIGNATURES = {
     "gdca_abi_version": (_i32, []),
     "gdca_create": (_i32, [ctypes.POINTER(_p), _i32]),
+    "gdca_create_multi": (_i32, [ctypes.POINTER(_p), _pi32, _i32]),
+    "gdca_group_size": (_i32, [_p]),
     "gdca_destroy": (None, [_p]),
     "gdca_last_error": (ctypes.c_char_p, [_p]),
     "gdca_status_string": (ctypes.c_char_p, [_i32]),
@@ -151,18 +153,39 @@ def ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-class Context:
-    """Owns one gdca_ctx (one GPU, one stream, all device buffers); reusable across calls."""
+def devices_from_env(default=(0,)):
+    """GDCA_B200_DEVICES="0,1,2,3" (or a count: "4" = devices 0..3) selects the GPUs of the default context -- the knob a
+    Julia or Python user of gDCA(filename) turns to run on more than one GPU (SURVEY 5 "Config/flags", 8b-1)."""
+    v = os.environ.get("GDCA_B200_DEVICES", "").strip()
+    if not v:
+        return tuple(default)
+    if "," not in v and v.isdigit() and int(v) > 0 and len(v) <= 2 and not v.startswith("0"):
+        return tuple(range(int(v)))
+    return tuple(int(x) for x in v.split(",") if x.strip() != "")
 
-    def __init__(self, device: int = 0):
+
+class Context:
+    """Owns one gdca_ctx: one GPU, or -- devices=[...] -- a group of GPUs of one node driven from this process
+    (gdca_create_multi: the alignment is copied once and broadcast over NVLink, the sweep, the covariance and the inversion are
+    sharded with their exchanges fused into the kernels).  Reusable across calls."""
+
+    def __init__(self, device: int = 0, devices=None):
         self.lib = load()
         h = _p()
-        st = self.lib.gdca_create(ctypes.byref(h), int(device))
+        if devices is not None and len(devices) > 1:
+            arr = (ctypes.c_int32 * len(devices))(*[int(d) for d in devices])
+            st = self.lib.gdca_create_multi(ctypes.byref(h), arr, len(devices))
+            device = int(devices[0])
+        else:
+            if devices is not None and len(devices) == 1:
+                device = int(devices[0])
+            st = self.lib.gdca_create(ctypes.byref(h), int(device))
         if st != GDCA_OK:
             msg = self.lib.gdca_last_error(None).decode()
-            raise GdcaError(st, f"gdca_create(device={device}) failed: {msg}")
+            raise GdcaError(st, f"gdca_create(device={device}, devices={devices}) failed: {msg}")
         self.h = h
         self.device = int(device)
+        self.devices = tuple(int(d) for d in devices) if devices is not None else (int(device),)
 
     def close(self):
         if getattr(self, "h", None):
@@ -197,7 +220,9 @@ class Context:
 _default_ctx = {}
 
 
-def default_context(device: int = 0) -> Context:
-    if device not in _default_ctx:
-        _default_ctx[device] = Context(device)
-    return _default_ctx[device]
+def default_context(device=None) -> Context:
+    """The process-wide context: device `device`, or the GPUs named by GDCA_B200_DEVICES (default: GPU 0)."""
+    key = devices_from_env() if device is None else (int(device),)
+    if key not in _default_ctx:
+        _default_ctx[key] = Context(devices=list(key))
+    return _default_ctx[key]

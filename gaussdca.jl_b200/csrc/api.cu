@@ -245,6 +245,9 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fact, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_sliced, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_group, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_OZAKI")) ctx->ozaki_mode = atoi(env) != 0;
   if (const char *env = getenv("GDCA_OZ_TPC")) {
     const int v = atoi(env);
@@ -278,6 +281,17 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
 
 void gdca_destroy(gdca_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->group_size > 1 && ctx->group_rank == 0) {  // a leader takes its members with it
+    for (int r = 1; r < ctx->group_size; ++r) {
+      gdca_ctx *m = ctx->group[r];
+      ctx->group[r] = nullptr;
+      if (m) {
+        m->group_size = 1;
+        gdca_destroy(m);
+      }
+    }
+    ctx->group_size = 1;
+  }
   cudaSetDevice(ctx->device);
   for (void *m : ctx->peer_opened)
     if (m) cudaIpcCloseMemHandle(m);
@@ -297,6 +311,9 @@ void gdca_destroy(gdca_ctx *ctx) {
   if (ctx->ev_fact) cudaEventDestroy(ctx->ev_fact);
   if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
   if (ctx->ev_sliced) cudaEventDestroy(ctx->ev_sliced);
+  if (ctx->ev_group) cudaEventDestroy(ctx->ev_group);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+  if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
   for (cudaEvent_t e : {ctx->ev_diag, ctx->ev_p1, ctx->ev_u2a, ctx->ev_u2b})
     if (e) cudaEventDestroy(e);
   if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
@@ -304,6 +321,71 @@ void gdca_destroy(gdca_ctx *ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
+
+int32_t gdca_create_multi(gdca_ctx **out, const int32_t *devices, int32_t n) {
+  if (!out) return GDCA_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!devices || n < 1 || n > GDCA_MAX_PEERS) {
+    g_create_error = "gdca_create_multi: need 1 <= n <= 16 device ordinals";
+    return GDCA_ERR_INVALID_ARG;
+  }
+  // Test mode (env GDCA_GROUP_ALLOW_SAME_DEVICE=1): the same ordinal may be listed several times -- the members then are
+  // independent contexts that share one GPU, so every piece of the group path (broadcast, barriers, peer tables, shared levels,
+  // stores into the other members' buffers) runs on a one-GPU box.  Without it a repeated ordinal is an error.
+  const char *same_env = getenv("GDCA_GROUP_ALLOW_SAME_DEVICE");
+  const bool allow_same = same_env && atoi(same_env) != 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j] && !allow_same) {
+        g_create_error = "gdca_create_multi: a device ordinal is listed twice";
+        return GDCA_ERR_INVALID_ARG;
+      }
+  gdca_ctx *g[GDCA_MAX_PEERS] = {};
+  auto undo = [&]() {
+    for (int i = 0; i < n; ++i)
+      if (g[i]) gdca_destroy(g[i]);
+  };
+  for (int i = 0; i < n; ++i) {
+    const int32_t st = gdca_create(&g[i], devices[i]);
+    if (st != GDCA_OK) {
+      undo();
+      return st;
+    }
+  }
+  // every member reads and writes every other member's buffers inside its kernels: peer access both ways for every pair
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      if (i == j || devices[i] == devices[j]) continue;
+      int can = 0;
+      cudaSetDevice(devices[i]);
+      cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+      if (!can) {
+        char b[128];
+        snprintf(b, sizeof b, "gdca_create_multi: device %d cannot access device %d (no NVLink / P2P path)", devices[i], devices[j]);
+        g_create_error = b;
+        undo();
+        return GDCA_ERR_NO_DEVICE;
+      }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        g_create_error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        undo();
+        return GDCA_ERR_CUDA;
+      }
+      cudaGetLastError();
+    }
+  for (int i = 0; i < n; ++i) {
+    g[0]->group[i] = g[i];
+    g[i]->leader = g[0];
+    g[i]->group_rank = i;
+  }
+  g[0]->group_size = n;
+  *out = g[0];
+  return GDCA_OK;
+}
+
+int32_t gdca_group_size(const gdca_ctx *ctx) { return ctx ? ctx->group_size : 0; }
 
 int32_t gdca_set_shard(gdca_ctx *ctx, int32_t rank, int32_t world) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
@@ -662,6 +744,211 @@ int32_t gdca_dev_get_stats(gdca_ctx *ctx, gdca_stats_t *stats) {
   return GDCA_OK;
 }
 
+// ------------------------------------------------------------------ fused run on a device group (one process, N GPUs)
+namespace {
+
+// Every member's stream waits until every member's stream has reached this point: N event records + N (N-1) stream waits,
+// nothing blocks the host.  (A wait takes the record that precedes it in program order, so one event per member is reused.)
+int32_t group_barrier(gdca_ctx *lead) {
+  const int N = lead->group_size;
+  for (int r = 0; r < N; ++r) {
+    gdca_ctx *c = lead->group[r];
+    GDCA_TRY(set_device(c));
+    GDCA_CUDA(lead, cudaEventRecord(c->ev_group, c->stream));
+  }
+  for (int r = 0; r < N; ++r) {
+    gdca_ctx *c = lead->group[r];
+    GDCA_TRY(set_device(c));
+    for (int p = 0; p < N; ++p)
+      if (p != r) GDCA_CUDA(lead, cudaStreamWaitEvent(c->stream, lead->group[p]->ev_group, 0));
+  }
+  return GDCA_OK;
+}
+
+// a member's failure is reported through the leader
+int32_t member_try(gdca_ctx *lead, gdca_ctx *c, int32_t st) {
+  if (st != GDCA_OK && c != lead) lead->err = "device " + std::to_string(c->device) + ": " + c->err;
+  return st;
+}
+
+void group_peer_tables(gdca_ctx *lead, bool on) {
+  const int N = lead->group_size;
+  for (int r = 0; r < N; ++r) {
+    gdca_ctx *c = lead->group[r];
+    for (int p = 0; p < GDCA_MAX_PEERS; ++p) {
+      c->peer_counts[p] = (on && p < N) ? lead->group[p]->dCounts : nullptr;
+      c->peer_C[p] = (on && p < N) ? lead->group[p]->dC : nullptr;
+    }
+    c->peers_ready = on;
+    c->shard_rank = on ? r : 0;
+    c->shard_world = on ? N : 1;
+  }
+}
+
+}  // namespace
+
+
+// The alignment reaches the leader once (one PCIe copy, or it is already resident there) and travels to the other members over
+// NVLink along a binary tree; the pair sweep and the covariance run sharded with their exchange fused into the kernels (peer
+// atomics / peer stores into the mapped buffers of the other devices); the inversion is sharded by gdca_k_inverse_group; scores,
+// APC and ranking run on the leader.  Results are bit-identical to the single-GPU run (integer exchanges, disjoint writes).
+static int32_t run_group(gdca_ctx *lead, const int8_t *Z, bool resident, int64_t L, int64_t M, double theta, double pseudocount,
+                         int32_t score, int64_t min_separation, gdca_rank_t *R, int64_t R_len, gdca_stats_t *stats) {
+  const int N = lead->group_size;
+  gdca_ctx **g = lead->group;
+  lead->stats = gdca_stats_t{};
+  auto body = [&]() -> int32_t {
+    // ---- 1. the alignment: H2D to the leader only, then a tree broadcast over NVLink
+    GDCA_TRY(set_device(lead));
+    if (resident) {
+      if (!lead->dZ_borrowed && lead->dZ) {
+        GDCA_CUDA(lead, cudaStreamSynchronize(lead->stream));
+        GDCA_CUDA(lead, cudaFree(lead->dZ));
+      }
+      lead->dZ = const_cast<int8_t *>(Z);
+      lead->capZ = 0;
+      lead->dZ_borrowed = true;
+      GDCA_TRY(rec(lead, EV_BEGIN));
+    } else {
+      if (lead->dZ_borrowed) {
+        lead->dZ = nullptr;
+        lead->capZ = 0;
+        lead->dZ_borrowed = false;
+      }
+      GDCA_TRY(rec(lead, EV_BEGIN));
+      GDCA_TRY(gdca_reserve(lead, lead->dZ, lead->capZ, (size_t)L * M + 16));
+      GDCA_CUDA(lead, cudaMemcpyAsync(lead->dZ, Z, (size_t)L * M, cudaMemcpyHostToDevice, lead->stream));
+    }
+    GDCA_CUDA(lead, cudaEventRecord(lead->ev_group, lead->stream));  // "my copy is complete"
+    for (int r = 1; r < N; ++r) {
+      GDCA_TRY(set_device(g[r]));
+      if (g[r]->dZ_borrowed) {
+        g[r]->dZ = nullptr;
+        g[r]->capZ = 0;
+        g[r]->dZ_borrowed = false;
+      }
+      GDCA_TRY(member_try(lead, g[r], gdca_reserve(g[r], g[r]->dZ, g[r]->capZ, (size_t)L * M + 16)));
+    }
+    for (int s = 1; s < N; s <<= 1)          // round: members [0, s) send to [s, 2s)
+      for (int src = 0; src < s && src + s < N; ++src) {
+        gdca_ctx *d = g[src + s];
+        GDCA_TRY(set_device(d));
+        GDCA_CUDA(lead, cudaStreamWaitEvent(d->stream, g[src]->ev_group, 0));
+        GDCA_CUDA(lead, cudaMemcpyPeerAsync(d->dZ, d->device, g[src]->dZ, g[src]->device, (size_t)L * M, d->stream));
+        GDCA_CUDA(lead, cudaEventRecord(d->ev_group, d->stream));
+      }
+    GDCA_TRY(set_device(lead));
+    GDCA_TRY(rec(lead, EV_H2D));
+    // ---- 2. every member: q, per-site lists, bit planes (replicated: each needs all of it for its share of the pair matrix)
+    for (int r = 0; r < N; ++r) {
+      GDCA_TRY(set_device(g[r]));
+      GDCA_TRY(member_try(lead, g[r], load_common(g[r], L, M)));
+    }
+    GDCA_TRY(set_device(lead));
+    GDCA_TRY(rec(lead, EV_PACK));
+    // ---- 3. theta (leader; O(M L) histogram sum), then the sharded neighbour-count sweep
+    gdca_stats_t &st = lead->stats;
+    int64_t thresh = 0;
+    if (theta < 0) {
+      unsigned long long ident = 0;
+      GDCA_TRY(gdca_k_ident_sum(lead, &ident));
+      double th;
+      GDCA_TRY(gdca_theta_from_ident_sum(L, M, ident, &th, &thresh));
+      st.theta = th;
+      st.ident_sum = ident;
+    } else {
+      st.theta = theta;
+      thresh = (int64_t)floor(theta * (double)L);
+    }
+    st.thresh = (st.theta == 0.0) ? 0 : thresh;
+    GDCA_TRY(rec(lead, EV_THETA));
+    for (int r = 0; r < N; ++r) {  // the buffers the peers write into must exist before their addresses go into the tables
+      GDCA_TRY(set_device(g[r]));
+      GDCA_TRY(member_try(lead, g[r], gdca_reserve(g[r], g[r]->dCounts, g[r]->capCounts, (size_t)3 * g[r]->Mpad)));
+      GDCA_TRY(member_try(lead, g[r], gdca_reserve(g[r], g[r]->dC, g[r]->capC, (size_t)g[r]->npad * g[r]->npad)));
+    }
+    group_peer_tables(lead, true);
+    if (st.theta == 0.0) {
+      for (int r = 0; r < N; ++r) {
+        GDCA_TRY(set_device(g[r]));
+        GDCA_TRY(member_try(lead, g[r], gdca_k_finish_weights(g[r], -1)));
+      }
+    } else {
+      for (int r = 0; r < N; ++r) {
+        GDCA_TRY(set_device(g[r]));
+        GDCA_CUDA(lead, cudaMemsetAsync(g[r]->dCounts, 0, (size_t)3 * g[r]->Mpad * sizeof(int32_t), g[r]->stream));
+      }
+      GDCA_TRY(group_barrier(lead));  // every member's counters are zero before anyone adds
+      for (int r = 0; r < N; ++r) {
+        GDCA_TRY(set_device(g[r]));
+        GDCA_TRY(member_try(lead, g[r], gdca_k_pair_pass(g[r], 1, (int)thresh, 1)));
+      }
+      GDCA_TRY(group_barrier(lead));  // all peer atomics have landed
+      st.theta_passes = 1;
+      for (int r = 0; r < N; ++r) {
+        GDCA_TRY(set_device(g[r]));
+        GDCA_TRY(member_try(lead, g[r], gdca_k_finish_weights(g[r], 0)));
+      }
+    }
+    st.meff = lead->meff;
+    GDCA_TRY(set_device(lead));
+    GDCA_TRY(rec(lead, EV_WEIGHTS));
+    // ---- 4. covariance: rows dealt by site, every member stores its rows straight into the leader's C
+    GDCA_CUDA(lead, cudaMemsetAsync(lead->dC, 0, (size_t)lead->npad * lead->npad * sizeof(double), lead->stream));
+    GDCA_TRY(group_barrier(lead));
+    for (int r = 0; r < N; ++r) {
+      GDCA_TRY(set_device(g[r]));
+      GDCA_TRY(member_try(lead, g[r], gdca_k_covariance(g[r], pseudocount)));
+    }
+    GDCA_TRY(group_barrier(lead));
+    GDCA_TRY(set_device(lead));
+    GDCA_TRY(gdca_k_symmetrize_C(lead));
+    GDCA_TRY(rec(lead, EV_COV));
+    // ---- 5. inversion, sharded; scores, APC, ranking on the leader
+    GDCA_TRY(gdca_k_inverse_group(lead));
+    GDCA_TRY(set_device(lead));
+    GDCA_TRY(rec(lead, EV_CHOL));
+    GDCA_TRY(gdca_k_score(lead, score));
+    GDCA_TRY(rec(lead, EV_SCORE));
+    GDCA_TRY(gdca_k_apc(lead));
+    GDCA_TRY(rec(lead, EV_APC));
+    GDCA_TRY(gdca_k_rank(lead, min_separation, R_len));
+    GDCA_TRY(rec(lead, EV_RANK));
+    if (R_len > 0 && R)
+      GDCA_CUDA(lead, cudaMemcpyAsync(R, lead->dR, (size_t)R_len * sizeof(gdca_rank_t), cudaMemcpyDeviceToHost, lead->stream));
+    GDCA_TRY(rec(lead, EV_D2H));
+    GDCA_CUDA(lead, cudaStreamSynchronize(lead->stream));
+    return GDCA_OK;
+  };
+  const int32_t status = body();
+  // leave every member as a plain single-device context
+  for (int r = 0; r < N; ++r) {
+    cudaSetDevice(g[r]->device);
+    cudaStreamSynchronize(g[r]->stream);
+    cudaStreamSynchronize(g[r]->stream_copy);
+  }
+  group_peer_tables(lead, false);
+  for (int r = 0; r < N; ++r) drop_alignment_state(g[r]);
+  cudaSetDevice(lead->device);
+  gdca_stats_t &st = lead->stats;
+  if (status == GDCA_OK) {
+    st.ms_h2d = ev_ms(lead, EV_BEGIN, EV_H2D);
+    st.ms_pack = ev_ms(lead, EV_H2D, EV_PACK);
+    st.ms_theta = ev_ms(lead, EV_PACK, EV_THETA);
+    st.ms_weights = ev_ms(lead, EV_THETA, EV_WEIGHTS);
+    st.ms_cov = ev_ms(lead, EV_WEIGHTS, EV_COV);
+    st.ms_chol = ev_ms(lead, EV_COV, GDCA_EV_POTRF);
+    st.ms_inv = ev_ms(lead, GDCA_EV_POTRF, EV_CHOL);
+    st.ms_score = ev_ms(lead, EV_CHOL, EV_SCORE);
+    st.ms_apc = ev_ms(lead, EV_SCORE, EV_APC);
+    st.ms_rank = ev_ms(lead, EV_APC, EV_RANK);
+    st.ms_d2h = ev_ms(lead, EV_RANK, EV_D2H);
+    st.ms_total = ev_ms(lead, EV_BEGIN, EV_D2H);
+  }
+  if (stats) *stats = st;
+  return status;
+}
+
 // ------------------------------------------------------------------ fused run
 static int32_t run_impl(gdca_ctx *ctx, const int8_t *Z, bool resident, int64_t L, int64_t M, double theta,
                         double pseudocount, int32_t score, int64_t min_separation, gdca_rank_t *R, int64_t R_len,
@@ -679,6 +966,7 @@ static int32_t run_impl(gdca_ctx *ctx, const int8_t *Z, bool resident, int64_t L
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R_len != (L-min_separation)*(L-min_separation+1)/2");
   if (R_len > 0 && !R && !resident) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "R is NULL");
   if (M < 2 && theta < 0) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "theta = :auto needs at least 2 sequences");
+  if (ctx->group_size > 1) return run_group(ctx, Z, resident, L, M, theta, pseudocount, score, min_separation, R, R_len, stats);
   ctx->stats = gdca_stats_t{};
   const int32_t saved_rank = ctx->shard_rank, saved_world = ctx->shard_world;
   ctx->shard_rank = 0;

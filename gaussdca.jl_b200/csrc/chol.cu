@@ -378,7 +378,7 @@ __global__ void mirror_lower_kernel(double *__restrict__ A, long long n, long lo
 template <bool AT, bool BT>
 int32_t gemm(gdca_ctx *ctx, const GemmP &p_in, int batch, cudaStream_t stream = nullptr) {
   GemmP p = p_in;
-  p.info = ctx->dInfo;
+  p.info = ctx->leader ? ctx->leader->dInfo : ctx->dInfo;  // a group member watches the leader's factorisation
   if (!stream) stream = ctx->stream;
   if (p.m <= 0 || p.n <= 0 || batch <= 0) return GDCA_OK;
   const size_t smem = (size_t)GSTAGES * 2 * TILE_D * sizeof(double);
@@ -413,6 +413,37 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   constexpr int OZ_MIN_REM = 8;   // trailing updates with at least this many block rows left
   constexpr int OZ_MIN_H = 4;     // trtri levels with K >= 512
   double *A = ctx->dC, *X = ctx->dX, *T = ctx->dT, *J = ctx->dmJ;
+  // Device group: the factorisation runs on the leader (its serial chain of diagonal blocks does not shard) while every
+  // finished panel is copied to the other members beside it; the inversion of the factor and the product X'X are then shared.
+  const int N = (oz && ctx->group_size > 1) ? ctx->group_size : 1;
+  gdca_ctx **grp = ctx->group;
+  auto on_dev = [&](gdca_ctx *c) -> int32_t {
+    GDCA_CUDA(ctx, cudaSetDevice(c->device));
+    return GDCA_OK;
+  };
+  auto mtry = [&](gdca_ctx *c, int32_t st) -> int32_t {
+    if (st != GDCA_OK && c != ctx) ctx->err = "device " + std::to_string(c->device) + ": " + c->err;
+    return st;
+  };
+  for (int r = 1; r < N; ++r) {
+    gdca_ctx *c = grp[r];
+    GDCA_TRY(on_dev(c));
+    c->npad = np;
+    c->n = n;
+    GDCA_TRY(mtry(c, gdca_reserve(c, c->dC, c->capC, (size_t)np * np)));
+    GDCA_TRY(mtry(c, gdca_reserve(c, c->dX, c->capX, (size_t)np * np)));
+    GDCA_TRY(mtry(c, gdca_reserve(c, c->dT, c->capT, (size_t)np * np)));
+    GDCA_TRY(mtry(c, gdca_reserve(c, c->dDigA, c->capDigA, (size_t)np * np * 8)));
+    GDCA_TRY(mtry(c, gdca_reserve(c, c->dDigB, c->capDigB, (size_t)np * np * 8)));
+    GDCA_TRY(mtry(c, gdca_reserve(c, c->dScaleA, c->capScaleA, (size_t)np)));
+    GDCA_TRY(mtry(c, gdca_reserve(c, c->dScaleB, c->capScaleB, (size_t)np)));
+    c->oz_int8_ops = c->oz_fp64_flop = 0.0;
+    // the copy stream starts behind whatever the member's compute stream still does with these buffers
+    GDCA_CUDA(ctx, cudaEventRecord(c->ev_copy, c->stream));
+    GDCA_CUDA(ctx, cudaStreamWaitEvent(c->stream_copy, c->ev_copy, 0));
+    GDCA_CUDA(ctx, cudaMemsetAsync(c->dX, 0, (size_t)np * np * sizeof(double), c->stream_copy));
+  }
+  GDCA_TRY(on_dev(ctx));
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dInfo, 0, sizeof(int), ctx->stream));
   GDCA_CUDA(ctx, cudaMemsetAsync(X, 0, (size_t)np * np * sizeof(double), ctx->stream));
   if (np > n) {
@@ -520,6 +551,22 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
       sp_pending = true;
     }
     if (sp_pending) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_u2b, 0));
+    if (N > 1) {
+      // columns [K0, Kend) of the factor and the inverted diagonal blocks are final: every member pulls them over NVLink
+      // with its copy engine while the leader goes on factorising
+      GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_copy, sA));
+      const size_t wbytes = (size_t)(Kend - K0) * NB * sizeof(double);
+      for (int r = 1; r < N; ++r) {
+        gdca_ctx *c = grp[r];
+        GDCA_TRY(on_dev(c));
+        GDCA_CUDA(ctx, cudaStreamWaitEvent(c->stream_copy, ctx->ev_copy, 0));
+        GDCA_CUDA(ctx, cudaMemcpy2DAsync(blk(c->dC, K0, K0), (size_t)np * sizeof(double), blk(A, K0, K0), (size_t)np * sizeof(double), wbytes,
+                                         (size_t)(nb - K0) * NB, cudaMemcpyDefault, c->stream_copy));
+        GDCA_CUDA(ctx, cudaMemcpy2DAsync(blk(c->dX, K0, K0), (size_t)np * sizeof(double), blk(X, K0, K0), (size_t)np * sizeof(double), wbytes,
+                                         (size_t)(Kend - K0) * NB, cudaMemcpyDefault, c->stream_copy));
+      }
+      GDCA_TRY(on_dev(ctx));
+    }
     const int rem = nb - Kend;
     if (rem > 0) {
       // Trailing update A[I,J] -= L[I,K0:Kend] L[J,K0:Kend]' (I >= J >= Kend), split for a one-panel look-ahead:
@@ -574,6 +621,26 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   }
   if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));
   if (ctx->ev[GDCA_EV_POTRF]) GDCA_CUDA(ctx, cudaEventRecord(ctx->ev[GDCA_EV_POTRF], sA));
+  for (int r = 1; r < N; ++r) {  // the members' compute streams continue once their copy of the factor is complete
+    gdca_ctx *c = grp[r];
+    GDCA_TRY(on_dev(c));
+    GDCA_CUDA(ctx, cudaEventRecord(c->ev_copy, c->stream_copy));
+    GDCA_CUDA(ctx, cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+  }
+  GDCA_TRY(on_dev(ctx));
+  // every member's stream waits for every member's stream (event records + stream waits; the host never blocks)
+  auto barrier = [&]() -> int32_t {
+    for (int r = 0; r < N; ++r) {
+      GDCA_TRY(on_dev(grp[r]));
+      GDCA_CUDA(ctx, cudaEventRecord(grp[r]->ev_group, grp[r]->stream));
+    }
+    for (int r = 0; r < N; ++r) {
+      GDCA_TRY(on_dev(grp[r]));
+      for (int q = 0; q < N; ++q)
+        if (q != r) GDCA_CUDA(ctx, cudaStreamWaitEvent(grp[r]->stream, grp[q]->ev_group, 0));
+    }
+    return on_dev(ctx);
+  };
 
   // ---------------- trtri by recursive doubling ----------------
   for (int h = 1; h < nb; h *= 2) {
@@ -581,19 +648,35 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
     const int ngroups_full = nb / (2 * h);            // groups whose bottom part is complete
     const int rest = nb - ngroups_full * 2 * h;       // blocks left after the full groups
     const long long gstride = (long long)2 * h * NB * (np + 1);  // along the diagonal
-    auto level = [&](int g0, int mb, int batch) -> int32_t {  // mb = bottom blocks
+    // A level is SHARED in a device group when every member gets a whole number of 64-column tiles of each X21 block: member r
+    // computes the columns [r w, (r+1) w) of T and of X21 and stores its X21 columns into EVERY member's X (the all-gather is
+    // fused into the GEMM epilogue; a barrier closes the level).  Otherwise every member computes the level on its replica --
+    // same kernels, same inputs, same bits.
+    const bool shared = N > 1 && oz && h >= OZ_MIN_H && (h * NB) % (64 * N) == 0;
+    auto level = [&](gdca_ctx *c, int rnk, int g0, int mb, int batch) -> int32_t {  // mb = bottom blocks
+      double *A = c->dC, *X = c->dX, *T = c->dT;  // this member's replicas
       if (oz && h >= OZ_MIN_H) {
-        cudaStream_t st = ctx->stream;
+        cudaStream_t st = c->stream;
+        const int w = shared ? h * NB / N : h * NB, col0 = shared ? rnk * w : 0;
+        gdca_oz_shard sh{};
+        sh.n_off = col0;
+        sh.own_mod = 1;
         gdca_oz_operand oa{}, ob{};
         // T[bottom, top] = L[bottom, top] * X[top, top]: rows of L21 against the COLUMNS of the lower-triangular X11 (k >= n0)
-        GDCA_TRY(gdca_oz_slice(ctx, st, blk(A, g0 + h, g0), np, gstride, false, mb * NB, h * NB, batch, mb * NB, ctx->dDigA, ctx->dScaleA, &oa));
-        GDCA_TRY(gdca_oz_slice(ctx, st, blk(X, g0, g0), np, gstride, true, h * NB, h * NB, batch, h * NB, ctx->dDigB, ctx->dScaleB, &ob));
-        GDCA_TRY(gdca_oz_gemm(ctx, st, oa, ob, blk(T, g0 + h, g0), np, gstride, mb * NB, h * NB, h * NB, batch, GDCA_OZ_KBEG_N, 1.0, 0, 0));
+        GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(A, g0 + h, g0), np, gstride, false, mb * NB, h * NB, batch, mb * NB, c->dDigA, c->dScaleA, &oa)));
+        GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(X, g0, g0) + col0, np, gstride, true, w, h * NB, batch, w, c->dDigB, c->dScaleB, &ob)));
+        GDCA_TRY(mtry(c, gdca_oz_gemm(c, st, oa, ob, blk(T, g0 + h, g0) + col0, np, gstride, mb * NB, w, h * NB, batch, GDCA_OZ_KBEG_N, 1.0, 0, 0, &sh)));
         // X[bottom, top] = - X[bottom, bottom] * T[bottom, top]: rows of the lower-triangular X22 (k < m0 + 128) against columns of T
-        GDCA_TRY(gdca_oz_slice(ctx, st, blk(X, g0 + h, g0 + h), np, gstride, false, mb * NB, mb * NB, batch, mb * NB, ctx->dDigA, ctx->dScaleA, &oa));
-        GDCA_TRY(gdca_oz_slice(ctx, st, blk(T, g0 + h, g0), np, gstride, true, h * NB, mb * NB, batch, h * NB, ctx->dDigB, ctx->dScaleB, &ob));
-        GDCA_TRY(gdca_oz_gemm(ctx, st, oa, ob, blk(X, g0 + h, g0), np, gstride, mb * NB, h * NB, mb * NB, batch, GDCA_OZ_KEND_M, -1.0, 0, 0));
-        ctx->oz_fp64_flop += (double)batch * 2.0 * NB * NB * NB * ((double)mb * h * (h + 1) / 2 + (double)h * mb * (mb + 1) / 2);
+        GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(X, g0 + h, g0 + h), np, gstride, false, mb * NB, mb * NB, batch, mb * NB, c->dDigA, c->dScaleA, &oa)));
+        GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(T, g0 + h, g0) + col0, np, gstride, true, w, mb * NB, batch, w, c->dDigB, c->dScaleB, &ob)));
+        sh.n_off = 0;
+        if (shared) {
+          sh.npeer = N;
+          for (int q = 0; q < N; ++q) sh.peer_off[q] = (long long)(reinterpret_cast<char *>(grp[q]->dX) - reinterpret_cast<char *>(X));
+        }
+        GDCA_TRY(mtry(c, gdca_oz_gemm(c, st, oa, ob, blk(X, g0 + h, g0) + col0, np, gstride, mb * NB, w, mb * NB, batch, GDCA_OZ_KEND_M, -1.0, 0, 0, &sh)));
+        if (c == ctx)
+          ctx->oz_fp64_flop += (double)batch * 2.0 * NB * NB * NB * ((double)mb * h * (h + 1) / 2 + (double)h * mb * (mb + 1) / 2);
         return GDCA_OK;
       }
       GemmP a{};
@@ -602,26 +685,43 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
       a.B = blk(X, g0, g0);     a.ldb = np; a.strideB = gstride;
       a.C = blk(T, g0 + h, g0); a.ldc = np; a.strideC = gstride;
       a.m = mb * NB; a.n = h * NB; a.k = h * NB; a.flags = G_KBEG_N; a.alpha = 1.0; a.beta = 0.0;
-      GDCA_TRY((gemm<false, true>(ctx, a, batch)));
+      GDCA_TRY(mtry(c, (gemm<false, true>(c, a, batch))));
       GemmP b{};
       // X[bottom, top] = - X[bottom, bottom] * T[bottom, top] (A lower triangular: k < m0 + NB)
       b.A = blk(X, g0 + h, g0 + h); b.lda = np; b.strideA = gstride;
       b.B = blk(T, g0 + h, g0);     b.ldb = np; b.strideB = gstride;
       b.C = blk(X, g0 + h, g0);     b.ldc = np; b.strideC = gstride;
       b.m = mb * NB; b.n = h * NB; b.k = mb * NB; b.flags = G_KEND_M; b.alpha = -1.0; b.beta = 0.0;
-      GDCA_TRY((gemm<false, true>(ctx, b, batch)));
+      GDCA_TRY(mtry(c, (gemm<false, true>(c, b, batch))));
       return GDCA_OK;
     };
-    if (ngroups_full > 0) GDCA_TRY(level(0, h, ngroups_full));
-    if (rest > h) GDCA_TRY(level(ngroups_full * 2 * h, rest - h, 1));
+    for (int r = 0; r < N; ++r) {
+      gdca_ctx *c = N > 1 ? grp[r] : ctx;
+      GDCA_TRY(on_dev(c));
+      if (ngroups_full > 0) GDCA_TRY(level(c, r, 0, h, ngroups_full));
+      if (rest > h) GDCA_TRY(level(c, r, ngroups_full * 2 * h, rest - h, 1));
+    }
+    if (shared) GDCA_TRY(barrier());
   }
+  GDCA_TRY(on_dev(ctx));
 
   // ---------------- lauum: mJ = X' X (lower tiles), then mirror ----------------
   if (oz) {
-    // operand rows = columns of X: ONE transposed slice serves both sides; k >= m0 (X is lower triangular)
-    gdca_oz_operand ox{};
-    GDCA_TRY(gdca_oz_slice(ctx, ctx->stream, X, np, 0, true, (int)np, (int)np, 1, np, ctx->dDigA, ctx->dScaleA, &ox));
-    GDCA_TRY(gdca_oz_gemm(ctx, ctx->stream, ox, ox, J, np, 0, (int)np, (int)np, (int)np, 1, GDCA_OZ_LOWER_OUT | GDCA_OZ_KBEG_M, 1.0, 0, 0));
+    // operand rows = columns of X: ONE transposed slice serves both sides; k >= m0 (X is lower triangular).  In a device
+    // group member r computes the row tiles im = r (mod N) from its replica of X and stores them straight into the leader's mJ.
+    for (int r = 0; r < N; ++r) {
+      gdca_ctx *c = N > 1 ? grp[r] : ctx;
+      GDCA_TRY(on_dev(c));
+      gdca_oz_shard sh{};
+      sh.own_mod = N;
+      sh.own_rank = r;
+      gdca_oz_operand ox{};
+      GDCA_TRY(mtry(c, gdca_oz_slice(c, c->stream, c->dX, np, 0, true, (int)np, (int)np, 1, np, c->dDigA, c->dScaleA, &ox)));
+      GDCA_TRY(mtry(c, gdca_oz_gemm(c, c->stream, ox, ox, J, np, 0, (int)np, (int)np, (int)np, 1, GDCA_OZ_LOWER_OUT | GDCA_OZ_KBEG_M, 1.0, 0, 0, &sh)));
+    }
+    if (N > 1) GDCA_TRY(barrier());
+    GDCA_TRY(on_dev(ctx));
+    for (int r = 1; r < N; ++r) ctx->oz_int8_ops += grp[r]->oz_int8_ops;
     ctx->oz_fp64_flop += (double)np * np * np / 3.0;
     const unsigned nt = (unsigned)((np + 31) / 32);
     mirror_lower_kernel<<<dim3(nt, nt), 256, 0, ctx->stream>>>(J, np, np);
@@ -651,6 +751,8 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   ctx->have_inv = true;
   return GDCA_OK;
 }
+
+int32_t gdca_k_inverse_group(gdca_ctx *lead) { return gdca_k_inverse(lead); }
 
 // ---------------------------------------------------------------------------------------------- test hook
 // C[m x n] = beta C + alpha opA opB^T on one of the two FP64 GEMM engines, host buffers (tests/test_gpu_ozaki.py).

@@ -65,6 +65,7 @@ struct gdca_ctx {
   double oz_int8_ops = 0.0;                    // INT8 operations of the last inversion
   double oz_fp64_flop = 0.0;                   // FP64 flop those products stand for
   bool last_inverse_ozaki = false;
+  bool oz_attr_set = false;                    // dynamic shared memory size of ozaki_gemm_kernel raised on this device
   double *dS = nullptr; size_t capS = 0;       // [L][L] raw score
   double *dS2 = nullptr; size_t capS2 = 0;     // [L][L] APC-corrected
   double *dRed = nullptr; size_t capRed = 0;   // reductions for APC
@@ -97,6 +98,14 @@ struct gdca_ctx {
   void *peer_opened[2 * GDCA_MAX_PEERS] = {};  // mappings to close
   int32_t *exported_counts = nullptr;          // buffers the exported handles refer to (re-export if they moved)
   double *exported_C = nullptr;
+
+  // ---- device group (ONE process, several GPUs): gdca_run() on the leader drives every member ----
+  int group_size = 1, group_rank = 0;
+  gdca_ctx *group[GDCA_MAX_PEERS] = {};        // leader only: [0] is the leader itself
+  gdca_ctx *leader = nullptr;                  // members: their leader
+  cudaEvent_t ev_group = nullptr;              // this member's arrival at a group barrier / "my copy of the data is complete"
+  cudaStream_t stream_copy = nullptr;          // peer copies that run beside the compute stream (factor panels)
+  cudaEvent_t ev_copy = nullptr;
 
   // ---- state flags ----
   bool have_alignment = false, have_lists = false, have_weights = false, have_cov = false, have_inv = false;
@@ -159,8 +168,15 @@ struct gdca_oz_operand {
 };
 int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, long long ld, long long stride_b, bool cols, int rows,
                       int k, int batch, long long rows_b, int8_t *dig, double *scale, gdca_oz_operand *out);
+struct gdca_oz_shard {   // one member's share of a product in a device group (nullptr: the whole product, one output buffer)
+  int n_off;             // first column of this share within the full product
+  int own_mod, own_rank; // row tiles im with im % own_mod == own_rank (own_mod <= 1: all)
+  int npeer;             // output tile stored to npeer buffers at C + peer_off[p] BYTES (0 / 1: C only)
+  long long peer_off[GDCA_MAX_PEERS];
+};
 int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &A, const gdca_oz_operand &B, double *C, long long ldc,
-                     long long strideC, int m, int n, int k, int batch, int flags, double alpha, int beta, int tiles_per_cta);
+                     long long strideC, int m, int n, int k, int batch, int flags, double alpha, int beta, int tiles_per_cta,
+                     const gdca_oz_shard *sh = nullptr);
 
 // ---- stage entry points implemented across the .cu files ----
 int32_t gdca_k_maxq(gdca_ctx *ctx);                       // pack.cu: dQ <- max(Z)
@@ -183,6 +199,7 @@ int32_t gdca_k_compute_C(gdca_ctx *ctx, const double *Pi, const double *Pij, lon
 int32_t gdca_k_symmetrize_C(gdca_ctx *ctx);               // cov.cu: mirror upper site blocks, save diag blocks
 int32_t gdca_k_extract_diag(gdca_ctx *ctx);               // cov.cu: save the s x s diagonal blocks of dC
 int32_t gdca_k_inverse(gdca_ctx *ctx);                    // chol.cu
+int32_t gdca_k_inverse_group(gdca_ctx *lead);             // chol.cu: potrf on the leader, trtri / lauum shared by the device group
 int32_t gdca_k_score(gdca_ctx *ctx, int score);           // score.cu
 int32_t gdca_k_apc(gdca_ctx *ctx);                        // rank.cu
 int32_t gdca_k_rank(gdca_ctx *ctx, int64_t min_sep, int64_t R_len);  // rank.cu

@@ -61,6 +61,11 @@ struct OzGemmP {
   int total;                     // tiles in the list
   double alpha;
   const int *info;               // not-SPD flag of the factorisation: once set, the launch returns at once
+  // device group (one process, several GPUs): this launch computes a share of the product and stores it where it is needed
+  int n_off;                     // column of the full product this launch's column 0 is (k range of GDCA_OZ_KBEG_N)
+  int own_mod, own_rank;         // row tile im is computed iff im % own_mod == own_rank
+  int npeer;                     // the C tile is stored to npeer buffers: C + peer_off[p] bytes (own buffer included)
+  long long peer_off[GDCA_MAX_PEERS];
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -165,9 +170,9 @@ __device__ __forceinline__ Tile decode_tile(const OzGemmP &P, int t, int tm, int
     T.im = (P.flags & GDCA_OZ_KEND_M) ? tm - 1 - o : o;
   }
   const int m0 = T.im * BM, n0 = T.jn * BN;
-  T.valid = !((P.flags & GDCA_OZ_LOWER_OUT) && n0 >= m0 + BM);
+  T.valid = !((P.flags & GDCA_OZ_LOWER_OUT) && n0 >= m0 + BM) && (P.own_mod <= 1 || T.im % P.own_mod == P.own_rank);
   int kbeg = 0, kend = P.k;
-  if (P.flags & GDCA_OZ_KBEG_N) kbeg = max(kbeg, (n0 / 128) * 128);
+  if (P.flags & GDCA_OZ_KBEG_N) kbeg = max(kbeg, ((P.n_off + n0) / 128) * 128);
   if (P.flags & GDCA_OZ_KBEG_M) kbeg = max(kbeg, m0);
   if (P.flags & GDCA_OZ_KEND_M) kend = min(kend, m0 + BM);
   T.kb0 = kbeg / KBLK;
@@ -370,8 +375,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 16; ++i) old[i] = Ct[(long long)(2 * i + rr) * P.ldc + (c + 1) * EPI_COLS + cc];
         }
+        if (P.npeer <= 1) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) Ct[(long long)(2 * i + rr) * P.ldc + c * EPI_COLS + cc] = out[i];
+          for (int i = 0; i < 16; ++i) Ct[(long long)(2 * i + rr) * P.ldc + c * EPI_COLS + cc] = out[i];
+        } else {
+          // fused all-gather: the tile goes to every member of the device group (own HBM and, over NVLink, the peers')
+          for (int pp = 0; pp < P.npeer; ++pp) {
+            double *Cp = reinterpret_cast<double *>(reinterpret_cast<char *>(Ct) + P.peer_off[pp]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Cp[(long long)(2 * i + rr) * P.ldc + c * EPI_COLS + cc] = out[i];
+          }
+        }
         __syncwarp();
       }
     }
@@ -566,11 +580,12 @@ int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, lon
 
 // C[b] (+)= alpha A[b] B[b]^T on the INT8 tensor cores.  m % 128 == 0, n % 64 == 0, k % 128 == 0.
 int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &A, const gdca_oz_operand &B, double *C, long long ldc,
-                     long long strideC, int m, int n, int k, int batch, int flags, double alpha, int beta, int tiles_per_cta) {
+                     long long strideC, int m, int n, int k, int batch, int flags, double alpha, int beta, int tiles_per_cta,
+                     const gdca_oz_shard *sh) {
   if (m <= 0 || n <= 0 || batch <= 0) return GDCA_OK;
   if (m % BM || n % BN || k % 128 || (long long)(k / KBLK) * SLOTS * KBLK > A.pitch || A.pitch != B.pitch)
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "oz_gemm: shape / pitch mismatch (m % 128, n % 64, k % 128, same k padding)");
-  if (((flags & GDCA_OZ_KBEG_M) && m > k) || ((flags & GDCA_OZ_KBEG_N) && n > k))
+  if (((flags & GDCA_OZ_KBEG_M) && m > k) || ((flags & GDCA_OZ_KBEG_N) && (sh ? sh->n_off : 0) + n > k))
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "oz_gemm: triangular k range would be empty");
   CUtensorMap mapA, mapB;
   GDCA_TRY(make_digit_map(ctx, &mapA, A.dig, A.rows_total, A.pitch, BM));
@@ -591,15 +606,20 @@ int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &
   P.beta = beta;
   P.tiles_per_cta = tiles_per_cta;
   P.alpha = alpha;
-  P.info = ctx->dInfo;
+  P.info = ctx->leader ? ctx->leader->dInfo : ctx->dInfo;  // a group member watches the leader's factorisation
+  P.n_off = sh ? sh->n_off : 0;
+  P.own_mod = sh ? sh->own_mod : 1;
+  P.own_rank = sh ? sh->own_rank : 0;
+  P.npeer = sh ? sh->npeer : 0;
+  for (int i = 0; i < GDCA_MAX_PEERS; ++i) P.peer_off[i] = (sh && i < sh->npeer) ? sh->peer_off[i] : 0;
+  if (P.npeer > 1 && beta) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "oz_gemm: replicated stores need beta == 0");
   P.tri = ((flags & GDCA_OZ_LOWER_OUT) && batch == 1 && m == n && !(flags & GDCA_OZ_KBEG_N)) ? 1 : 0;
   const long long total = P.tri ? (long long)(m / BM) * (m / BM + 1) : (long long)batch * (m / BM) * (n / BN);
   P.total = (int)total;
   long long grid = tiles_per_cta > 0 ? (total + tiles_per_cta - 1) / tiles_per_cta : (total < ctx->num_sms ? total : ctx->num_sms);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->oz_attr_set) {  // per device
     GDCA_CUDA(ctx, cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-    attr_set = true;
+    ctx->oz_attr_set = true;
   }
   ozaki_gemm_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, stream>>>(mapA, mapB, P);
   GDCA_LAUNCH_CHECK(ctx);
@@ -610,8 +630,9 @@ int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &
     for (int jn = 0; jn < tn; ++jn) {
       const int m0 = im * BM, n0 = jn * BN;
       if ((flags & GDCA_OZ_LOWER_OUT) && n0 >= m0 + BM) continue;
+      if (P.own_mod > 1 && im % P.own_mod != P.own_rank) continue;
       int kbeg = 0, kend = k;
-      if (flags & GDCA_OZ_KBEG_N) kbeg = kbeg > (n0 / 128) * 128 ? kbeg : (n0 / 128) * 128;
+      if (flags & GDCA_OZ_KBEG_N) kbeg = kbeg > ((P.n_off + n0) / 128) * 128 ? kbeg : ((P.n_off + n0) / 128) * 128;
       if (flags & GDCA_OZ_KBEG_M) kbeg = kbeg > m0 ? kbeg : m0;
       if (flags & GDCA_OZ_KEND_M) kend = kend < m0 + BM ? kend : m0 + BM;
       if (kend > kbeg) ops += 2.0 * BM * BN * (double)(kend - kbeg) * (double)(S * (S + 1) / 2);

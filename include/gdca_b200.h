@@ -82,6 +82,14 @@ typedef struct gdca_ctx gdca_ctx;
 int32_t gdca_abi_version(void);
 /* device: CUDA ordinal.  Owns one stream, all device memory, reusable across calls. */
 int32_t gdca_create(gdca_ctx **out, int32_t device);
+/* Several GPUs of one node behind ONE context ("create(n_gpus or device list)"): the returned context leads a group
+ * of n devices with peer access enabled between all pairs.  gdca_run() / gdca_run_resident() on it copy the alignment to devices[0]
+ * once, broadcast it over NVLink, shard the pair sweep (peer atomics), the covariance (peer stores) and the inversion (trtri by
+ * column slices with the result stored to every member, lauum by row tiles stored to devices[0]) and return the same bits as a
+ * single-GPU run.  Every other entry point acts on devices[0] alone.  n == 1 is gdca_create().  The host wrapper picks the
+ * devices (env GDCA_B200_DEVICES in julia/GaussDCA.jl and api.py).  gdca_destroy() releases the whole group. */
+int32_t gdca_create_multi(gdca_ctx **out, const int32_t *devices, int32_t n);
+int32_t gdca_group_size(const gdca_ctx *ctx);
 void gdca_destroy(gdca_ctx *ctx);
 const char *gdca_last_error(const gdca_ctx *ctx); /* ctx may be NULL: error of a failed gdca_create */
 const char *gdca_status_string(int32_t status);
