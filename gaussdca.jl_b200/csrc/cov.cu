@@ -164,15 +164,17 @@ template <> struct ZLoad<4> { typedef unsigned int type; };
 
 // CTA (row r = (i,a), chunk c): sites [start + c*CH, start + (c+1)*CH), CH = JT*SPT, start = i rounded down to a
 // warp's worth of sites (32*SPT).  Thread t owns the SPT adjacent sites start + c*CH + SPT*t + u.
-template <int SPT, bool RAW>
+// GRID2D: (chunks, rows) grid (rows <= 65535); otherwise a 1-D grid, row-major over (row, chunk), for L > 3276 at q = 21.
+// (A compile-time switch on purpose: the common instantiation keeps the exact code -- 48 registers, 19.3 ms at config C -- that a
+// run-time selection of the two index computations lost to a 40-register schedule, 21.4 ms.)
+template <int SPT, bool RAW, bool GRID2D>
 __global__ void __launch_bounds__(JT) cov_rows_kernel(CovParams P) {
   constexpr int CH = JT * SPT;
   extern __shared__ double acc[];      // [q][SPT][JT]; slot s is the dump for the gap state / padding
   __shared__ unsigned stage_off[STG];  // row offset k*Lq of the staged sequences
   __shared__ double stage_w[STG];      // W[k]
-  // (chunks, rows) grid; beyond its 65535-row limit (L > 3276 at q = 21) a 1-D grid, row-major over (row, chunk)
-  const int r = gridDim.y > 1 ? (int)blockIdx.y : (int)(blockIdx.x / (unsigned)P.nchunks);  // output row (i, a)
-  const int chunk = gridDim.y > 1 ? (int)blockIdx.x : (int)(blockIdx.x - (unsigned)r * (unsigned)P.nchunks);
+  const int r = GRID2D ? (int)blockIdx.y : (int)(blockIdx.x / (unsigned)P.nchunks);  // output row (i, a)
+  const int chunk = GRID2D ? (int)blockIdx.x : (int)(blockIdx.x - (unsigned)r * (unsigned)P.nchunks);
   const int i = r / P.s, a = r - i * P.s + 1;
   if (P.world > 1 && (i % P.world) != P.rank) return;  // rows are dealt to ranks by site
   const int start = (i / (32 * SPT)) * (32 * SPT) + chunk * CH;
@@ -403,14 +405,18 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw) {
   P.pc = pc;
   const size_t smem = (size_t)ctx->q * SPT * JT * sizeof(double);
   // RAW (compile time): write Pij_true (no pseudocount, no - Pi Pi') for DCAUtils compute_weighted_frequencies
-  GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_rows_kernel<SPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov0, ctx->stream));
-  const dim3 cgrid = (n <= 65535 && n > 1) ? dim3((unsigned)P.nchunks, (unsigned)n) : dim3((unsigned)((long long)P.nchunks * n));
+  const bool g2 = n <= 65535;
+  const dim3 cgrid = g2 ? dim3((unsigned)P.nchunks, (unsigned)n) : dim3((unsigned)((long long)P.nchunks * n));
+  auto launch = [&](auto kern) -> int32_t {
+    GDCA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov0, ctx->stream));
+    kern<<<cgrid, JT, smem, ctx->stream>>>(P);
+    return GDCA_OK;
+  };
   if (raw)
-    cov_rows_kernel<SPT, true><<<cgrid, JT, smem, ctx->stream>>>(P);
+    GDCA_TRY(g2 ? launch(cov_rows_kernel<SPT, true, true>) : launch(cov_rows_kernel<SPT, true, false>));
   else
-    cov_rows_kernel<SPT, false><<<cgrid, JT, smem, ctx->stream>>>(P);
+    GDCA_TRY(g2 ? launch(cov_rows_kernel<SPT, false, true>) : launch(cov_rows_kernel<SPT, false, false>));
   GDCA_LAUNCH_CHECK(ctx);
   GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov1, ctx->stream));
   ctx->pseudocount = pc;
