@@ -265,7 +265,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaEventCreate(&ctx->ev_sweep1)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreate(&ctx->ev_cov0)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreate(&ctx->ev_cov1)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc((void **)&ctx->dNItems, sizeof(int))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dNItems, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_TC_FILTER")) {
     const int m = atoi(env);
     if (m >= 0 && m <= 2) ctx->tc_filter_mode = m;
@@ -274,6 +274,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
     const int b = atoi(env);
     if (b == 4 || b == 8 || b == 80) ctx->tc_filter_bits = b;
   }
+  if (const char *env = getenv("GDCA_CELL_SWEEP")) ctx->cell_sweep = atoi(env) != 0;
   if (const char *env = getenv("GDCA_TC_MULTICAST")) ctx->tc_filter_want_multicast = atoi(env) != 0;
   *out = ctx;
   return GDCA_OK;
@@ -301,7 +302,7 @@ void gdca_destroy(gdca_ctx *ctx) {
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
                   ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask,
-                  ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax};
+                  ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax, ctx->dCellBase};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)
@@ -532,7 +533,7 @@ int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_ti
   int64_t blocks = T * (T + 1) / 2 / ctx->shard_world;
   if (f) {
     int nit = 0;
-    GDCA_CUDA(ctx, cudaMemcpy(&nit, ctx->dNItems, sizeof(int), cudaMemcpyDeviceToHost));
+    GDCA_CUDA(ctx, cudaMemcpy(&nit, ctx->dNItems, sizeof(int), cudaMemcpyDeviceToHost));  // low word of the packed counter
     blocks = nit;
   }
   if (swept_blocks) *swept_blocks = blocks;

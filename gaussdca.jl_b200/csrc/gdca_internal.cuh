@@ -78,8 +78,10 @@ struct gdca_ctx {
   uint32_t *dFlags = nullptr; size_t capFlags = 0; // [T][T] 16-bit masks of the 32x32 cells the filter could not clear
   int2 *dItems = nullptr; size_t capItems = 0;     // compacted (bi, bj) list of blocks with a non-empty mask
   uint32_t *dItemMask = nullptr; size_t capItemMask = 0;  // their masks
-  int *dNItems = nullptr;                          // [1] its length
+  unsigned long long *dNItems = nullptr;           // [1] low word: its length; high word: flagged 32 x 32 cells in it
+  uint32_t *dCellBase = nullptr; size_t capCellBase = 0;  // flagged cells in front of every listed block
   int have_V = 0;                                  // 0: dV stale; 8 / 4 / 80: dV holds the FP8 / FP4 / INT8 encoding of the loaded alignment
+  int cell_sweep = 1;                              // behind the prefilter: sweep flagged CELLS, one warp each (env GDCA_CELL_SWEEP=0: blocks)
   int tc_filter_mode = 1;                          // 0 off, 1 auto (large M), 2 always (tests)
   int tc_filter_bits = 4;                          // operands of the filter: 4 = e2m1 (kind::mxf4), 8 = e4m3 (kind::f8f6f4), 80 = int8 (kind::i8)
   bool tc_filter_want_multicast = true;            // 2-CTA clusters + TMA multicast of the B tile (env GDCA_TC_MULTICAST=0: off)

@@ -389,6 +389,158 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_sweep_kernel(PairParams P) {
   }
 }
 
+// ---- exact sweep of the flagged 32 x 32 CELLS (production path behind the tensor-core prefilter) -------------------------
+// The prefilter leaves a list of blocks with a 16-bit mask of the cells it could not clear.  On a favourable sequence order few
+// blocks are listed; on a random order almost every block holds a few flagged cells (~22 % of all cells at config C), and a
+// block-per-CTA sweep then costs as much as no filter at all.  Here the unit of work is the flagged cell: ONE WARP per cell,
+// no shared memory, no CTA barrier -- lane (ry, cx) owns the 4 x 8 pairs of rows 4 ry.. and columns 8 cx.. and reads its
+// operands (16-byte words of the bit planes) straight through L1 from the L2-resident planes; the per-warp early exit is the
+// one of the block kernel.  Every warp walks a contiguous range of the cell list (cells of one block are adjacent), found by
+// one binary search on the running cell counts of the blocks.
+struct CellParams {
+  const uint32_t *planes;
+  long long Mpad, M;
+  int nwords, thresh;
+  const int2 *items;
+  const uint32_t *item_mask, *cellbase;
+  const unsigned long long *n_packed;  // low word: listed blocks, high word: flagged cells
+  int32_t *counts[GDCA_MAX_PEERS];
+  int npeers;
+  unsigned long long *ham_sum;
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(128, 3) cell_sweep_kernel(CellParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned long long np = *P.n_packed;
+  const int n_items = (int)(np & 0xffffffffull);
+  const long long n_cells = (long long)(np >> 32);
+  const int ry = lane >> 2, cx = lane & 3;
+  const unsigned one = (unsigned)(P.nwords > 0);  // == 1 at run time, unknown at compile time
+  const long long c_beg = n_cells * gw / nw, c_end = n_cells * (gw + 1) / nw;
+  if (c_beg >= c_end) return;
+  // block that holds cell c_beg: the last slot with cellbase <= c_beg
+  int slot = 0;
+  {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((long long)P.cellbase[mid] <= c_beg) lo = mid; else hi = mid - 1;
+    }
+    slot = lo;
+  }
+  int2 it = P.items[slot];
+  uint32_t mask = P.item_mask[slot];
+  // drop the cells of this block that belong to the warp in front
+  for (long long skip = c_beg - (long long)P.cellbase[slot]; skip > 0; --skip) mask &= mask - 1;
+  unsigned long long words_done = 0;
+  const int n_free = min((P.thresh + 31) / 32, P.nwords);  // no pair can reach thresh before this many words
+  for (long long c = c_beg; c < c_end; ++c) {
+    while (mask == 0) {  // next listed block
+      ++slot;
+      it = P.items[slot];
+      mask = P.item_mask[slot];
+    }
+    const int bit = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int cr = bit >> 2, cc = bit & 3;
+    const long long row0 = (long long)it.x * TILE + 32 * cr, col0 = (long long)it.y * TILE + 32 * cc;
+    const uint32_t *pa = P.planes + row0 + 4 * ry, *pb = P.planes + col0 + 8 * cx;
+    unsigned acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0;
+    auto process_word = [&](int w) {
+      unsigned x[4][8];
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) {
+        const long long o = (long long)(w * NPL + p) * P.Mpad;
+        const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(pa + o));
+        const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(pb + o));
+        const uint4 b1 = __ldg(reinterpret_cast<const uint4 *>(pb + o + 4));
+        const unsigned a[4] = {a0.x, a0.y, a0.z, a0.w};
+        const unsigned b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[i][j] = (p == 0) ? (a[i] ^ b[j]) : (x[i][j] | (a[i] ^ b[j]));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) add_on_fma_pipe(acc[i][j], (unsigned)__popc(x[i][j]), one);
+    };
+    // exact early exit: hamming only grows with more sites; once all 1024 pairs of the cell have reached thresh none of them
+    // can be a neighbour.  The first ceil(thresh/32) words run without votes.  (Measured: 12 warps per SM with the loads issued
+    // where they are used beat 8 warps per SM with the operands of the next word prefetched into registers, 27.1 vs 28.7 ms on
+    // the shuffled config C.)
+    bool done = false;
+    auto vote = [&]() {
+      unsigned dmin = acc[0][0];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmin = min(dmin, acc[i][j]);
+      done = __all_sync(0xffffffffu, (int)dmin >= P.thresh) != 0;
+    };
+#pragma unroll 2
+    for (int w = 0; w < n_free; ++w) process_word(w);
+    vote();
+    int w = n_free;
+    for (; w < P.nwords && !done; ++w) {
+      process_word(w);
+      vote();
+    }
+    words_done += (unsigned long long)w;
+    if (done) continue;  // every pair is at or beyond thresh
+    // ---- hits: a pair credits both sequences; diagonal cells of diagonal blocks count each unordered pair once ----
+    const bool diag_cell = (it.x == it.y) && (cr == cc);
+    int rh[4] = {0, 0, 0, 0}, ch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned any = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = row0 + 4 * ry + i;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long cl = col0 + 8 * cx + j;
+        const bool valid = r < P.M && cl < P.M && (!diag_cell || r < cl);
+        const int h = (valid && (int)acc[i][j] < P.thresh) ? 1 : 0;
+        rh[i] += h;
+        ch[j] += h;
+        any |= (unsigned)h;
+      }
+    }
+    if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // rows: the 4 lanes that share ry
+      int v = rh[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (cx == 0 && v)
+        for (int pr = 0; pr < P.npeers; ++pr) atomicAdd(P.counts[pr] + row0 + 4 * ry + i, v);  // own buffer and, over NVLink, the peers'
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // columns: the 8 lanes that share cx
+      int v = ch[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (ry == 0 && v)
+        for (int pr = 0; pr < P.npeers; ++pr) atomicAdd(P.counts[pr] + col0 + 8 * cx + j, v);
+    }
+  }
+  if (lane == 0 && words_done) atomicAdd(P.ham_sum + 1, words_done * 1024ull);  // executed pair-words (roofline evidence)
+}
+
+template <int NPL>
+int32_t launch_cells(gdca_ctx *ctx, const CellParams &P) {
+  cell_sweep_kernel<NPL><<<ctx->num_sms * 3, 128, 0, ctx->stream>>>(P);
+  GDCA_LAUNCH_CHECK(ctx);
+  return GDCA_OK;
+}
+
 template <int NPL>
 int32_t launch_pairs(gdca_ctx *ctx, int mode, const PairParams &P) {
   const size_t smem = (size_t)STAGES * 2 * WC * NPL * TILE * sizeof(uint32_t);
@@ -446,7 +598,7 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
   P.item_mask = nullptr;
   if (filtered) {  // the list is already this rank's share
     P.items = ctx->dItems;
-    P.n_items_dev = ctx->dNItems;
+    P.n_items_dev = reinterpret_cast<const int *>(ctx->dNItems);  // low word of the packed counter
     P.item_mask = ctx->dItemMask;
     P.rank = 0;
     P.world = 1;
@@ -462,6 +614,31 @@ int32_t gdca_k_pair_pass(gdca_ctx *ctx, int mode, int thresh, int sample_stride)
   }
   P.ham_sum = ctx->dHam;
   int32_t st;
+  if (filtered && ctx->cell_sweep) {
+    // behind the prefilter the unit of work is the flagged 32 x 32 cell (one warp each), not the 128 x 128 block
+    CellParams Q;
+    Q.planes = ctx->dPlanes;
+    Q.Mpad = ctx->Mpad;
+    Q.M = ctx->M;
+    Q.nwords = (int)ctx->nwords;
+    Q.thresh = thresh;
+    Q.items = ctx->dItems;
+    Q.item_mask = ctx->dItemMask;
+    Q.cellbase = ctx->dCellBase;
+    Q.n_packed = ctx->dNItems;
+    Q.npeers = P.npeers;
+    for (int r = 0; r < GDCA_MAX_PEERS; ++r) Q.counts[r] = r < P.npeers ? P.counts[r] : nullptr;
+    Q.ham_sum = ctx->dHam;
+    switch (ctx->nplanes) {
+      case 1: st = launch_cells<1>(ctx, Q); break;
+      case 2: st = launch_cells<2>(ctx, Q); break;
+      case 3: st = launch_cells<3>(ctx, Q); break;
+      case 4: st = launch_cells<4>(ctx, Q); break;
+      default: st = launch_cells<5>(ctx, Q); break;
+    }
+    if (st == GDCA_OK) GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_sweep1, ctx->stream));
+    return st;
+  }
   switch (ctx->nplanes) {
     case 1: st = launch_pairs<1>(ctx, mode, P); break;
     case 2: st = launch_pairs<2>(ctx, mode, P); break;

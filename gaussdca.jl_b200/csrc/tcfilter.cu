@@ -496,18 +496,26 @@ __global__ void encode_simplex4_kernel(const int8_t *__restrict__ Z, long long L
   }
 }
 
-// cell masks [T][T] -> list of blocks (bi <= bj) with their masks for the exact sweep
+// cell masks [T][T] -> list of blocks (bi <= bj) with their masks for the exact sweep, plus the running number of flagged
+// cells in front of every block (cellbase), so the sweep can deal CELLS, not blocks, to its warps.  One 64-bit atomic hands out
+// the block slot (low word) and the cell offset (high word) together: cellbase grows with the slot.
 __global__ void compact_flags_kernel(const uint32_t *__restrict__ flags, int T, int2 *__restrict__ items,
-                                     uint32_t *__restrict__ masks, int *__restrict__ n_items) {
+                                     uint32_t *__restrict__ masks, uint32_t *__restrict__ cellbase,
+                                     unsigned long long *__restrict__ n_packed) {
   const long long total = (long long)T * T;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const uint32_t m = flags[t];
+    uint32_t m = flags[t];
     if (m) {
       const int bi = (int)(t / T), bj = (int)(t - (long long)bi * T);
       if (bj >= bi) {
-        const int slot = atomicAdd(n_items, 1);
+        // diagonal blocks: cell (r, c) with r > c only repeats the pairs of cell (c, r)
+        if (bi == bj) m &= 0x8CEFu;  // bits 4r + c with c >= r
+        if (!m) continue;
+        const unsigned long long old = atomicAdd(n_packed, ((unsigned long long)__popc(m) << 32) | 1ull);
+        const uint32_t slot = (uint32_t)old;
         items[slot] = make_int2(bi, bj);
         masks[slot] = m;
+        cellbase[slot] = (uint32_t)(old >> 32);
       }
     }
   }
@@ -559,6 +567,7 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   GDCA_TRY(gdca_reserve(ctx, ctx->dFlags, ctx->capFlags, (size_t)(T * T)));
   GDCA_TRY(gdca_reserve(ctx, ctx->dItems, ctx->capItems, (size_t)(T * (T + 1) / 2)));
   GDCA_TRY(gdca_reserve(ctx, ctx->dItemMask, ctx->capItemMask, (size_t)(T * (T + 1) / 2)));
+  GDCA_TRY(gdca_reserve(ctx, ctx->dCellBase, ctx->capCellBase, (size_t)(T * (T + 1) / 2)));
 
   if (ctx->have_V != TAG) {
     const long long words = VM * Kbytes / 4;
@@ -578,7 +587,7 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   GDCA_TRY(make_tensor_map(ctx, &mapB, ctx->dV, VM, Kbytes, mc ? C::BN / 2 : C::BN));
 
   GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dFlags, 0, (size_t)(T * T) * sizeof(uint32_t), ctx->stream));
-  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dNItems, 0, sizeof(int), ctx->stream));
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dNItems, 0, sizeof(unsigned long long), ctx->stream));
 
   FilterParams P;
   P.T = (int)T;
@@ -617,7 +626,7 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
 
   const long long tt = T * T;
   const int cgrid = (int)((tt + 255) / 256 < (long long)ctx->num_sms * 8 ? (tt + 255) / 256 : (long long)ctx->num_sms * 8);
-  compact_flags_kernel<<<cgrid, 256, 0, ctx->stream>>>(ctx->dFlags, (int)T, ctx->dItems, ctx->dItemMask, ctx->dNItems);
+  compact_flags_kernel<<<cgrid, 256, 0, ctx->stream>>>(ctx->dFlags, (int)T, ctx->dItems, ctx->dItemMask, ctx->dCellBase, ctx->dNItems);
   GDCA_LAUNCH_CHECK(ctx);
   // tiles this rank visits (host arithmetic, same rule as TileIter::valid)
   long long tiles = 0;

@@ -59,14 +59,26 @@ struct GdcaStats
 end
 GdcaStats() = GdcaStats(0, 0, 0, 0, 0, 0.0, 0, 0.0, 0, 0, 0, ntuple(_ -> 0.0f0, 12)...)
 
+# GDCA_B200_DEVICES="0,1,2,3" (or a count, "4" = devices 0..3) selects the GPUs; default: GDCA_B200_DEVICE (one ordinal) or GPU 0.
+# With more than one device the context leads a device group (gdca_create_multi): gDCA(filename) then runs on all of them --
+# one host-to-device copy of Z, NVLink broadcast, sharded sweep / covariance / inversion -- and returns the same bits.
+function devices_from_env()
+    v = strip(get(ENV, "GDCA_B200_DEVICES", ""))
+    isempty(v) && return Int32[parse(Int32, get(ENV, "GDCA_B200_DEVICE", "0"))]
+    occursin(",", v) || return Int32.(0:parse(Int, v)-1)
+    return Int32[parse(Int32, x) for x in split(v, ",") if !isempty(strip(x))]
+end
+
 mutable struct Context
     handle::Ptr{Cvoid}
-    function Context(device::Integer = parse(Int, get(ENV, "GDCA_B200_DEVICE", "0")))
+    function Context(devices::Vector{Int32} = devices_from_env())
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        st = ccall((:gdca_create, libgdca), Int32, (Ref{Ptr{Cvoid}}, Int32), h, device)
+        st = length(devices) == 1 ?
+            ccall((:gdca_create, libgdca), Int32, (Ref{Ptr{Cvoid}}, Int32), h, devices[1]) :
+            ccall((:gdca_create_multi, libgdca), Int32, (Ref{Ptr{Cvoid}}, Ptr{Int32}, Int32), h, devices, length(devices))
         if st != GDCA_OK
             msg = unsafe_string(ccall((:gdca_last_error, libgdca), Cstring, (Ptr{Cvoid},), C_NULL))
-            error("gdca_create(device=$device) failed: $msg")     # no CPU fallback by design
+            error("gdca_create(devices=$devices) failed: $msg")     # no CPU fallback by design
         end
         ctx = new(h[])
         finalizer(c -> (c.handle != C_NULL && ccall((:gdca_destroy, libgdca), Cvoid, (Ptr{Cvoid},), c.handle); c.handle = C_NULL), ctx)
