@@ -638,18 +638,19 @@ def main():
 
 
 def _inverse_info(ctx, lib):
-    """What the last inversion ran on (DMMA only, or the INT8-sliced tcgen05 GEMMs), if the library reports it."""
-    fn = getattr(lib, "gdca_dev_inverse_info", None)
-    if fn is None:
-        return {}
+    """What the last inversion ran on (DMMA only, or the INT8-sliced tcgen05 GEMMs): gdca_dev_inverse_info."""
     try:
-        mode, ms_oz, tops = ctypes.c_int32(), ctypes.c_float(), ctypes.c_double()
-        ctx.check(fn(ctx.h, ctypes.byref(mode), ctypes.byref(ms_oz), ctypes.byref(tops)))
+        mode, ops, flop = ctypes.c_int32(), ctypes.c_double(), ctypes.c_double()
+        ctx.check(lib.gdca_dev_inverse_info(ctx.h, ctypes.byref(mode), ctypes.byref(ops), ctypes.byref(flop)))
         if not mode.value:
             return {}
         return {"kernel": "ozaki_gemm_kernel (FP64 GEMMs of potrf / trtri / lauum as 36 INT8 tcgen05 kind::i8 digit products, S32 in "
-                          "TMEM, FP64 recombination) + dgemm_kernel<*> / diag_block_kernel (DMMA) for panels and diagonal blocks",
-                "int8_tops_executed": tops.value, "int8_peak_nominal_tops": 4500.0}
+                          "TMEM, one-rounding FP64 recombination) + dgemm_kernel<*> / diag_block_kernel (DMMA) for panels and diagonal blocks",
+                "int8_ops_per_step": ops.value, "fp64_flop_carried_by_int8": flop.value,
+                "int8_peak_nominal_tops": 4500.0,
+                "note": ("frac is against the FP64 tensor (DMMA) peak, the roofline of a plain FP64 implementation: > 1 means the "
+                         "sliced engine is past that wall; the INT8 kernels themselves run at ~0.57 of the nominal dense INT8 rate "
+                         "(profiles/r2_top_kernels.md: tensor pipe 61 % active, bound by the shared-memory operand reads of N = 64 MMAs)")}
     except Exception:  # noqa: BLE001
         return {}
 

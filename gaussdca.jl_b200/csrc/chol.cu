@@ -185,6 +185,66 @@ __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(GemmP p) {
   }
 }
 
+// ---- the two 128 x 128 x 128 products on the critical chain of the factorisation (panel tile, diagonal update) ----
+// C[128 x 128] = beta C + alpha A B', A and B as [row][k].  The big kernel above gives such a product ONE CTA whose 4-slot ring
+// never fills (8 k-steps): ~26 us.  Here 8 CTAs of 4 warps take a strip of 16 output rows each: the strip's 16 operand rows of A
+// and all 128 rows of B arrive in one cp.async burst, then 256 DMMAs per warp.  In-place use (C == A, the panel tile) is safe:
+// a CTA is the only reader of its A rows and has them in shared memory before its first store.
+constexpr int SG_M = 16;          // output rows per CTA
+constexpr int SG_LD = NB + 4;     // operand row stride (doubles): conflict-free 64-bit fragment loads
+__global__ void __launch_bounds__(128) dgemm_small_kernel(GemmP p) {
+  extern __shared__ __align__(16) double sm[];
+  double *As = sm, *Bs = sm + SG_M * SG_LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  const int m0 = blockIdx.x * SG_M;
+  int failed = (p.info && tid == 0) ? *reinterpret_cast<const volatile int *>(p.info) : 0;
+  for (int ch = tid; ch < (SG_M + NB) * (NB / 2); ch += 128) {  // 16-byte chunks: row = ch / 64, two doubles at 2 (ch % 64)
+    const int row = ch >> 6, cc = ch & 63;
+    if (row < SG_M)
+      cp16(As + row * SG_LD + cc * 2, p.A + (long long)(m0 + row) * p.lda + cc * 2);
+    else
+      cp16(Bs + (row - SG_M) * SG_LD + cc * 2, p.B + (long long)(row - SG_M) * p.ldb + cc * 2);
+  }
+  cp_commit();
+  failed = __syncthreads_or(failed);
+  cp_wait<0>();
+  if (failed) return;
+  __syncthreads();
+  const int wn = warp * 32;  // warp tile 16 x 32 = 2 x 4 atoms of 8 x 8
+  double acc[2][4][2] = {};
+#pragma unroll 4
+  for (int kk = 0; kk < NB / 4; ++kk) {
+    double a[2], b[4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) a[mi] = As[(mi * 8 + g) * SG_LD + kk * 4 + c];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(wn + ni * 8 + g) * SG_LD + kk * 4 + c];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    const long long row = m0 + mi * 8 + g;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const long long col = wn + ni * 8 + 2 * c;
+      double2 *dst = reinterpret_cast<double2 *>(p.C + row * p.ldc + col);
+      double2 v;
+      v.x = p.alpha * acc[mi][ni][0];
+      v.y = p.alpha * acc[mi][ni][1];
+      if (p.beta != 0.0) {
+        const double2 old = *dst;
+        v.x += p.beta * old.x;
+        v.y += p.beta * old.y;
+      }
+      *dst = v;
+    }
+  }
+}
+
 // ---- diagonal block: A[k,k] (lower) -> inv(chol(A[k,k])) written to X[k,k] (lower, zeros above) ----
 // One CTA of 16 warps, the 128 x 128 block lives in REGISTERS (32 doubles per thread), both phases are
 // right-looking rank-1 sweeps with ONE barrier per step and a one-step look-ahead:
@@ -389,6 +449,17 @@ int32_t gemm(gdca_ctx *ctx, const GemmP &p_in, int batch, cudaStream_t stream = 
   return GDCA_OK;
 }
 
+// 128 x 128 x 128, both operands [row][k], on the critical chain: 8 strip CTAs instead of one ring-pipelined CTA
+int32_t gemm_small(gdca_ctx *ctx, const GemmP &p_in, cudaStream_t stream) {
+  GemmP p = p_in;
+  p.info = ctx->leader ? ctx->leader->dInfo : ctx->dInfo;
+  const size_t smem = (size_t)(SG_M + NB) * SG_LD * sizeof(double);
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(dgemm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dgemm_small_kernel<<<NB / SG_M, 128, smem, stream>>>(p);
+  GDCA_LAUNCH_CHECK(ctx);
+  return GDCA_OK;
+}
+
 }  // namespace
 
 int32_t gdca_k_inverse(gdca_ctx *ctx) {
@@ -507,7 +578,7 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
         p.B = blk(X, k, k);     p.ldb = np;
         p.C = blk(A, k + 1, k); p.ldc = np;
         p.m = NB; p.n = NB; p.k = NB; p.flags = 0; p.alpha = 1.0; p.beta = 0.0;
-        GDCA_TRY((gemm<false, false>(ctx, p, 1, sA)));
+        GDCA_TRY(gemm_small(ctx, p, sA));
       }
       GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_p1, sA));
       if (sp_pending) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_u2b, 0));
@@ -517,7 +588,7 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
         u.B = blk(A, k + 1, k); u.ldb = np;
         u.C = blk(A, k + 1, k + 1); u.ldc = np;
         u.m = NB; u.n = NB; u.k = NB; u.flags = 0; u.alpha = -1.0; u.beta = 1.0;
-        GDCA_TRY((gemm<false, false>(ctx, u, 1, sA)));
+        GDCA_TRY(gemm_small(ctx, u, sA));
       }
       // panel stream
       GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, ctx->ev_diag, 0));

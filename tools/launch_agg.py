@@ -6,6 +6,9 @@ up to the next one, without the L2-flush fill between steps."""
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
 hdr = rows[0]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+if "Metric Name" in hdr:  # lists captured with more than one metric: keep the durations
+    mi = hdr.index("Metric Name")
+    rows = [hdr] + [r for r in rows[1:] if "gpu__time_duration" in r[mi]]
 if "--step" in sys.argv:
     n = int(sys.argv[sys.argv.index("--step") + 1])
     starts = [i for i, r in enumerate(rows) if i and "maxq_kernel" in r[ki]]

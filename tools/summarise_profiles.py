@@ -6,17 +6,23 @@ OUT = "profiles"
 os.makedirs(OUT, exist_ok=True)
 
 # ---- 1. launch list
-agg = subprocess.run([sys.executable, "tools/launch_agg.py", "gpurun_out/launches_bench.csv", "--step", "4"], capture_output=True, text=True).stdout
+if ROUND == "r1":
+    agg = subprocess.run([sys.executable, "tools/launch_agg.py", "gpurun_out/launches_bench.csv", "--step", "4"], capture_output=True, text=True).stdout
+    how = ("Command (on the GPU box): `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv "
+           "--log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline`; the list below is the "
+           "timed step = the 4th hot-path pass (after 3 warm-up passes), cut out with `tools/launch_agg.py --step 4`\n")
+else:
+    agg = subprocess.run([sys.executable, "tools/launch_agg.py", f"gpurun_out/{ROUND}_launches.csv"], capture_output=True, text=True).stdout
+    how = ("Command (on the GPU box, tools/make_profiles_r2.sh): `ncu --profile-from-start off --metrics gpu__time_duration.sum,"
+           "launch__grid_size --clock-control none --csv --log-file gpurun_out/r2_launches.csv python tools/profile_step.py C`: ONE "
+           "gdca_run_resident step of config C (L=500, M=200k) inside a cudaProfiler range, after two unprofiled warm-up steps\n")
 open(f"{OUT}/{ROUND}_launches.md", "w").write(
-    f"# {ROUND}: ncu launch list of one bench step\n\n"
-    "Command (on the GPU box): `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv "
-    "--log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline`; the list below is the "
-    "timed step = the 4th hot-path pass (after 3 warm-up passes), cut out with `tools/launch_agg.py --step 4`\n"
+    f"# {ROUND}: ncu launch list of one hot-path step\n\n" + how +
     "(cold-cache, serialised launches: compare SHARES, not absolutes; the bench value itself is never taken under ncu).\n\n```\n" + agg + "```\n")
 
 # ---- 2. full-set metrics of the top kernels
 import glob
-reports = sorted(glob.glob("gpurun_out/top_*.ncu-rep"))
+reports = sorted(glob.glob("gpurun_out/top_*.ncu-rep" if ROUND == "r1" else f"gpurun_out/{ROUND}_top_*.ncu-rep"))
 KEYS = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
     "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
@@ -28,6 +34,9 @@ KEYS = [
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__warps_eligible.avg.per_cycle_active",
 ]
 seen = set()
@@ -77,8 +86,8 @@ with open(f"{OUT}/{ROUND}_top_kernels.md", "w") as f:
 json.dump(traffic, open(f"{OUT}/{ROUND}_traffic.json", "w"), indent=1)
 
 # ---- 3. the bench line of the same build
-if os.path.exists("gpurun_out/bench_r1.json"):
-    line = open("gpurun_out/bench_r1.json").read().strip().splitlines()[-1]
+if os.path.exists(f"gpurun_out/bench_{ROUND}.json"):
+    line = open(f"gpurun_out/bench_{ROUND}.json").read().strip().splitlines()[-1]
     d = json.loads(line)
     open(f"{OUT}/{ROUND}_bench.json", "w").write(json.dumps(d, indent=1) + "\n")
 print(open(f"{OUT}/{ROUND}_top_kernels.md").read()[:3000])
