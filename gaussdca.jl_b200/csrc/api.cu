@@ -246,6 +246,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_sliced, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_group, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_p1b, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_OZAKI")) ctx->ozaki_mode = atoi(env) != 0;
@@ -302,7 +303,7 @@ void gdca_destroy(gdca_ctx *ctx) {
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
                   ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask,
-                  ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax, ctx->dCellBase};
+                  ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax, ctx->dCellBase, ctx->dDigP, ctx->dScaleP};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)
@@ -313,6 +314,7 @@ void gdca_destroy(gdca_ctx *ctx) {
   if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
   if (ctx->ev_sliced) cudaEventDestroy(ctx->ev_sliced);
   if (ctx->ev_group) cudaEventDestroy(ctx->ev_group);
+  if (ctx->ev_p1b) cudaEventDestroy(ctx->ev_p1b);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
   for (cudaEvent_t e : {ctx->ev_diag, ctx->ev_p1, ctx->ev_u2a, ctx->ev_u2b})

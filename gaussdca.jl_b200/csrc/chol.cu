@@ -480,6 +480,8 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
                                                                                    // is up to (nb - 1) blocks wide), potrf panels
     GDCA_TRY(gdca_reserve(ctx, ctx->dScaleA, ctx->capScaleA, (size_t)np));
     GDCA_TRY(gdca_reserve(ctx, ctx->dScaleB, ctx->capScaleB, (size_t)np));
+    GDCA_TRY(gdca_reserve(ctx, ctx->dDigP, ctx->capDigP, (size_t)NB * 8 * 1024));  // 128 rows x (K <= 1024) x 8 digit slots
+    GDCA_TRY(gdca_reserve(ctx, ctx->dScaleP, ctx->capScaleP, (size_t)NB));
   }
   constexpr int OZ_MIN_REM = 8;   // trailing updates with at least this many block rows left
   constexpr int OZ_MIN_H = 4;     // trtri levels with K >= 512
@@ -531,6 +533,7 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   constexpr int OB = 4;
   cudaStream_t sA = ctx->stream, sB = ctx->stream2, sP = ctx->stream3;
   bool pending_trail = false;
+  bool p1b_pending = false;  // the panel stream still updates this outer block's columns below its first diagonal tile
   for (int K0 = 0; K0 < nb; K0 += OB) {
     const int Kend = (K0 + OB < nb) ? K0 + OB : nb;
     bool sp_pending = false;  // work of this outer block is still queued on the panel stream
@@ -539,6 +542,10 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
       GDCA_LAUNCH_CHECK(ctx);
       const int rem = nb - k - 1;
       if (rem == 0) break;
+      if (p1b_pending) {  // the first panel product of the block reads columns the panel stream has just updated
+        GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_p1b, 0));
+        p1b_pending = false;
+      }
       const int inner_cols = Kend - k - 1;
       if (!ctx->chol_inner_lookahead || inner_cols == 0 || rem < 2) {
         // last step of the outer block (or look-ahead off): the whole panel on the main stream, then the inner update
@@ -647,13 +654,33 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
       GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_fact, sA));          // panel [K0,Kend) is final
       if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));  // columns >= Kend carry update K0-OB
       if (oz && rem >= OZ_MIN_REM) {
-        // the panel rows L[Kend.., K0:Kend) are sliced ONCE into int8 digits (after the previous bulk update has finished
-        // reading the digit buffer: the wait above); both parts of the update read them
+        // The chain only needs the NEXT DIAGONAL TILE before it can go on: the 128 panel rows that produce it are sliced and
+        // multiplied on the main stream (2 tiles), the next diagonal block starts factorising right behind them.  Everything
+        // else -- slicing the whole panel once, the other columns of the next panel, the bulk -- runs beside it: the panel
+        // stream updates the next panel's columns below that tile (the first panel product of the next block waits for it),
+        // the low-priority stream the bulk.  (The waits on the previous bulk update come first: it wrote all of this.)
         const int kk = (Kend - K0) * NB;
+        gdca_oz_operand Pd{};
+        GDCA_TRY(gdca_oz_slice(ctx, sA, blk(A, Kend, K0), np, 0, false, NB, kk, 1, NB, ctx->dDigP, ctx->dScaleP, &Pd));
+        GDCA_TRY(gdca_oz_gemm(ctx, sA, Pd, Pd, blk(A, Kend, Kend), np, 0, NB, NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1, 0));
+        GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, ctx->ev_fact, 0));
+        if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, ctx->ev_trail, 0));
         gdca_oz_operand P{};
-        GDCA_TRY(gdca_oz_slice(ctx, sA, blk(A, Kend, K0), np, 0, false, rem * NB, kk, 1, rem * NB, ctx->dDigB, ctx->dScaleB, &P));
-        GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_sliced, sA));
-        GDCA_TRY(gdca_oz_gemm(ctx, sA, P, P, blk(A, Kend, Kend), np, 0, rem * NB, (Kn - Kend) * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1, 0));
+        GDCA_TRY(gdca_oz_slice(ctx, sP, blk(A, Kend, K0), np, 0, false, rem * NB, kk, 1, rem * NB, ctx->dDigB, ctx->dScaleB, &P));
+        GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_sliced, sP));
+        if (rem > 1) {
+          gdca_oz_operand P1 = P;   // rows from block Kend + 1 on
+          P1.dig += (long long)NB * P.pitch;
+          P1.scale += NB;
+          P1.rows_total = P1.rows_b = (long long)(rem - 1) * NB;
+          gdca_oz_shard sh{};
+          sh.own_mod = 1;
+          sh.m_off = NB;  // lower-triangular test against the panel's own origin
+          GDCA_TRY(gdca_oz_gemm(ctx, sP, P1, P, blk(A, Kend + 1, Kend), np, 0, (rem - 1) * NB, (Kn - Kend) * NB, kk, 1, GDCA_OZ_LOWER_OUT,
+                                -1.0, 1, 0, &sh));
+        }
+        GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_p1b, sP));
+        p1b_pending = true;
         ctx->oz_fp64_flop += 2.0 * (double)kk * NB * NB * ((double)(Kn - Kend) * rem - 0.5 * (Kn - Kend) * (Kn - Kend - 1));
         const int rem2 = nb - Kn;
         if (rem2 > 0) {
@@ -691,6 +718,7 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
     }
   }
   if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));
+  if (p1b_pending) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_p1b, 0));
   if (ctx->ev[GDCA_EV_POTRF]) GDCA_CUDA(ctx, cudaEventRecord(ctx->ev[GDCA_EV_POTRF], sA));
   for (int r = 1; r < N; ++r) {  // the members' compute streams continue once their copy of the factor is complete
     gdca_ctx *c = grp[r];

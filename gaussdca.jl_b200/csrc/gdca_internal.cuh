@@ -62,6 +62,9 @@ struct gdca_ctx {
   double *dScaleB = nullptr; size_t capScaleB = 0;
   unsigned long long *dOzMax = nullptr; size_t capOzMax = 0;  // column maxima of a transposed slice
   cudaEvent_t ev_sliced = nullptr;             // panel digits ready (potrf trailing update on two streams)
+  cudaEvent_t ev_p1b = nullptr;                // next panel's columns updated (all but the diagonal tile, which the chain does itself)
+  int8_t *dDigP = nullptr; size_t capDigP = 0; // digits of the 128 panel rows the chain needs first
+  double *dScaleP = nullptr; size_t capScaleP = 0;
   double oz_int8_ops = 0.0;                    // INT8 operations of the last inversion
   double oz_fp64_flop = 0.0;                   // FP64 flop those products stand for
   bool last_inverse_ozaki = false;
@@ -172,6 +175,7 @@ int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, lon
                       int k, int batch, long long rows_b, int8_t *dig, double *scale, gdca_oz_operand *out);
 struct gdca_oz_shard {   // one member's share of a product in a device group (nullptr: the whole product, one output buffer)
   int n_off;             // first column of this share within the full product
+  int m_off;             // first row of this share within the full product (lower-triangular output test)
   int own_mod, own_rank; // row tiles im with im % own_mod == own_rank (own_mod <= 1: all)
   int npeer;             // output tile stored to npeer buffers at C + peer_off[p] BYTES (0 / 1: C only)
   long long peer_off[GDCA_MAX_PEERS];
