@@ -102,6 +102,7 @@ SIGNATURES = {
     "gdca_dev_mJ_ptr": (_p, [_p]),
     "gdca_set_ozaki": (_i32, [_p, _i32]),
     "gdca_dev_inverse_info": (_i32, [_p, _pi32, _pdbl, _pdbl]),
+    "gdca_dev_inverse_shared": (_i32, [_p]),
     "gdca_test_fp64_gemm": (_i32, [_p, _i32, _p, _i32, _p, _i32, _p, _i64, _i64, _i64, _i32, _dbl, _dbl]),
     "gdca_dev_score_rank": (_i32, [_p, _i32, _i64, _p, _i64]),
     "gdca_dev_S_ptr": (_p, [_p]),

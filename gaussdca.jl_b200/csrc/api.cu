@@ -247,6 +247,12 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_sliced, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_group, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_p1b, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_sent, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_upd, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if (const char *env = getenv("GDCA_SHARE_MIN_NB")) {
+    const int v = atoi(env);
+    if (v >= 16) ctx->share_min_nb = v;
+  }
   if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_OZAKI")) ctx->ozaki_mode = atoi(env) != 0;
@@ -315,6 +321,8 @@ void gdca_destroy(gdca_ctx *ctx) {
   if (ctx->ev_sliced) cudaEventDestroy(ctx->ev_sliced);
   if (ctx->ev_group) cudaEventDestroy(ctx->ev_group);
   if (ctx->ev_p1b) cudaEventDestroy(ctx->ev_p1b);
+  if (ctx->ev_sent) cudaEventDestroy(ctx->ev_sent);
+  if (ctx->ev_upd) cudaEventDestroy(ctx->ev_upd);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
   for (cudaEvent_t e : {ctx->ev_diag, ctx->ev_p1, ctx->ev_u2a, ctx->ev_u2b})
@@ -635,6 +643,8 @@ int32_t gdca_dev_inverse_info(gdca_ctx *ctx, int32_t *ozaki, double *int8_ops, d
   if (fp64_flop_on_int8) *fp64_flop_on_int8 = ctx->oz_fp64_flop;
   return GDCA_OK;
 }
+
+int32_t gdca_dev_inverse_shared(gdca_ctx *ctx) { return (ctx && ctx->last_inverse_shared) ? 1 : 0; }
 
 int32_t gdca_dev_score_rank(gdca_ctx *ctx, int32_t score, int64_t min_separation, gdca_rank_t *R_host, int64_t R_len) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;

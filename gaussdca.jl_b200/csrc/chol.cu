@@ -13,6 +13,8 @@
 // The matrix is padded to a multiple of 128 with an identity block, so no kernel here has edge
 // cases: inv([[C,0],[0,I]]) = [[inv(C),0],[0,I]].  All matrices are row-major with ld = npad.
 // A non-positive pivot records the 1-based order of the failing leading minor (PosDefException.info).
+#include <algorithm>
+
 #include "gdca_internal.cuh"
 
 namespace {
@@ -472,6 +474,7 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   // INT8-sliced tcgen05 GEMMs (ozaki.cu) for the big products; DMMA for diagonal blocks, K = 128 panels and small shapes
   const bool oz = ctx->ozaki_mode != 0 && nb >= 16;
   ctx->last_inverse_ozaki = oz;
+  ctx->last_inverse_shared = false;
   ctx->oz_int8_ops = 0.0;
   ctx->oz_fp64_flop = 0.0;
   if (oz) {
@@ -526,11 +529,38 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   const size_t dsmem = (size_t)NB * DLD * sizeof(double);
   GDCA_CUDA(ctx, cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
   auto blk = [&](double *base, int I, int Jb) { return base + ((long long)I * NB) * np + (long long)Jb * NB; };
+  constexpr int OB = 4;  // 128-blocks per outer block of the factorisation
+  // SHARED FACTORISATION (device group, n >= share_min_nb * 128: the bulk trailing updates outweigh the serial chain).
+  // Outer block column ob (512 columns) of the trailing matrix belongs to member ob % N: the owner applies every broadcast
+  // panel to it and ships it to the leader one step before the leader factorises it.  The chain itself stays on the leader.
+  bool share = N > 1 && nb >= ctx->share_min_nb;
+  const bool shared_factorisation = share;
+  ctx->last_inverse_shared = shared_factorisation;
+  auto owner = [&](int ob) { return ob % N; };
+  auto copy_cols = [&](gdca_ctx *on, cudaStream_t st, double *dst, const double *src, int K, int wblocks) -> int32_t {
+    // rows [K, nb) of the block columns [K, K + wblocks)
+    GDCA_CUDA(ctx, cudaSetDevice(on->device));
+    GDCA_CUDA(ctx, cudaMemcpy2DAsync(dst + ((long long)K * NB) * np + (long long)K * NB, (size_t)np * sizeof(double),
+                                     src + ((long long)K * NB) * np + (long long)K * NB, (size_t)np * sizeof(double),
+                                     (size_t)wblocks * NB * sizeof(double), (size_t)(nb - K) * NB, cudaMemcpyDefault, st));
+    return GDCA_OK;
+  };
+  if (share) {
+    GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));  // C (+ identity padding) is complete on the leader
+    for (int r = 1; r < N; ++r) {
+      gdca_ctx *c = grp[r];
+      GDCA_TRY(on_dev(c));
+      GDCA_CUDA(ctx, cudaStreamWaitEvent(c->stream_copy, ctx->ev_copy, 0));
+      for (int ob = r; ob * OB < nb; ob += N) GDCA_TRY(copy_cols(c, c->stream_copy, c->dC, A, ob * OB, std::min(OB, nb - ob * OB)));
+      GDCA_CUDA(ctx, cudaEventRecord(c->ev_copy, c->stream_copy));
+      GDCA_CUDA(ctx, cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    }
+    GDCA_TRY(on_dev(ctx));
+  }
 
   // ---------------- potrf: two-level right-looking ----------------
   // inner step (128 columns): diagonal block, panel, update of the remaining columns of the OUTER block only;
   // after OB inner steps one trailing update with K = OB*128 (C tiles read/written n/512 times, not n/128).
-  constexpr int OB = 4;
   cudaStream_t sA = ctx->stream, sB = ctx->stream2, sP = ctx->stream3;
   bool pending_trail = false;
   bool p1b_pending = false;  // the panel stream still updates this outer block's columns below its first diagonal tile
@@ -642,6 +672,10 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
                                          (size_t)(nb - K0) * NB, cudaMemcpyDefault, c->stream_copy));
         GDCA_CUDA(ctx, cudaMemcpy2DAsync(blk(c->dX, K0, K0), (size_t)np * sizeof(double), blk(X, K0, K0), (size_t)np * sizeof(double), wbytes,
                                          (size_t)(Kend - K0) * NB, cudaMemcpyDefault, c->stream_copy));
+        if (share) {  // the member's compute stream applies this panel to its own block columns
+          GDCA_CUDA(ctx, cudaEventRecord(c->ev_copy, c->stream_copy));
+          GDCA_CUDA(ctx, cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+        }
       }
       GDCA_TRY(on_dev(ctx));
     }
@@ -653,7 +687,30 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
       const int Kn = (Kend + OB < nb) ? Kend + OB : nb;
       GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_fact, sA));          // panel [K0,Kend) is final
       if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));  // columns >= Kend carry update K0-OB
+      if (share && rem < OZ_MIN_REM) {
+        // The last few block columns: every owner hands its columns back and the leader finishes alone, on the same engines
+        // as a single-GPU run (bit-identical results for every group size).
+        for (int r = 1; r < N; ++r) {
+          gdca_ctx *c = grp[r];
+          GDCA_TRY(on_dev(c));
+          GDCA_CUDA(ctx, cudaEventRecord(c->ev_upd, c->stream));
+          GDCA_CUDA(ctx, cudaStreamWaitEvent(c->stream_copy, c->ev_upd, 0));
+          for (int ob = r; ob * OB < nb; ob += N)
+            if (ob * OB >= Kend) GDCA_TRY(copy_cols(c, c->stream_copy, A, c->dC, ob * OB, std::min(OB, nb - ob * OB)));
+          GDCA_CUDA(ctx, cudaEventRecord(c->ev_sent, c->stream_copy));
+        }
+        GDCA_TRY(on_dev(ctx));
+        for (int r = 1; r < N; ++r)
+          for (cudaStream_t st : {sA, sB, sP}) GDCA_CUDA(ctx, cudaStreamWaitEvent(st, grp[r]->ev_sent, 0));
+        share = false;
+      }
       if (oz && rem >= OZ_MIN_REM) {
+        const int sidx = K0 / OB;  // this step's outer block; the chain goes on with block sidx + 1
+        if (share && sidx >= 1 && owner(sidx + 1) != 0) {
+          // block column sidx + 1 carries the updates of all earlier panels on its owner: it has been shipped one step ahead
+          GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, grp[owner(sidx + 1)]->ev_sent, 0));
+          GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, grp[owner(sidx + 1)]->ev_sent, 0));
+        }
         // The chain only needs the NEXT DIAGONAL TILE before it can go on: the 128 panel rows that produce it are sliced and
         // multiplied on the main stream (2 tiles), the next diagonal block starts factorising right behind them.  Everything
         // else -- slicing the whole panel once, the other columns of the next panel, the bulk -- runs beside it: the panel
@@ -689,11 +746,48 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
           P2.dig += (long long)(Kn - Kend) * NB * P.pitch;
           P2.scale += (long long)(Kn - Kend) * NB;
           P2.rows_total = P2.rows_b = (long long)rem2 * NB;
+          gdca_oz_shard cf{};  // shared factorisation: only the block columns this member owns
+          cf.own_mod = 1;
+          cf.col_mod = share ? N : 1;
+          cf.col_rank = 0;
+          cf.col_unit0 = Kn * (NB / 64);
+          cf.col_per = OB * (NB / 64);
           GDCA_TRY(gdca_oz_gemm(ctx, sB, P2, P2, blk(A, Kn, Kn), np, 0, rem2 * NB, rem2 * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1,
-                                ctx->ozaki_tpc));
+                                ctx->ozaki_tpc, share ? &cf : nullptr));
           ctx->oz_fp64_flop += 2.0 * (double)kk * NB * NB * (0.5 * (double)rem2 * (rem2 + 1));
           GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_trail, sB));
           pending_trail = true;
+          if (share) {
+            // every other member: slice the panel rows it received, update the block column the leader needs next FIRST and
+            // ship it (copy engine, NVLink), then the rest of its columns
+            const int wu = std::min(OB, nb - Kn);   // blocks of outer block sidx + 2
+            for (int r = 1; r < N; ++r) {
+              gdca_ctx *c = grp[r];
+              GDCA_TRY(on_dev(c));
+              gdca_oz_operand Pm{};
+              GDCA_TRY(mtry(c, gdca_oz_slice(c, c->stream, blk(c->dC, Kn, K0), np, 0, false, rem2 * NB, kk, 1, rem2 * NB, c->dDigB, c->dScaleB, &Pm)));
+              if (owner(sidx + 2) == r) {
+                GDCA_TRY(mtry(c, gdca_oz_gemm(c, c->stream, Pm, Pm, blk(c->dC, Kn, Kn), np, 0, rem2 * NB, wu * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1, 0)));
+                GDCA_CUDA(ctx, cudaEventRecord(c->ev_upd, c->stream));
+                GDCA_CUDA(ctx, cudaStreamWaitEvent(c->stream_copy, c->ev_upd, 0));
+                GDCA_TRY(copy_cols(c, c->stream_copy, A, c->dC, Kn, wu));
+                GDCA_CUDA(ctx, cudaEventRecord(c->ev_sent, c->stream_copy));
+              }
+              const int Kr = Kn + OB;  // the columns behind that block
+              if (Kr < nb) {
+                gdca_oz_operand Pr = Pm;
+                Pr.dig += (long long)(Kr - Kn) * NB * Pm.pitch;
+                Pr.scale += (long long)(Kr - Kn) * NB;
+                Pr.rows_total = Pr.rows_b = (long long)(nb - Kr) * NB;
+                gdca_oz_shard cm = cf;
+                cm.col_rank = r;
+                cm.col_unit0 = Kr * (NB / 64);
+                GDCA_TRY(mtry(c, gdca_oz_gemm(c, c->stream, Pr, Pr, blk(c->dC, Kr, Kr), np, 0, (nb - Kr) * NB, (nb - Kr) * NB, kk, 1,
+                                              GDCA_OZ_LOWER_OUT, -1.0, 1, 0, &cm)));
+              }
+            }
+            GDCA_TRY(on_dev(ctx));
+          }
         }
         continue;
       }

@@ -68,6 +68,7 @@ struct gdca_ctx {
   double oz_int8_ops = 0.0;                    // INT8 operations of the last inversion
   double oz_fp64_flop = 0.0;                   // FP64 flop those products stand for
   bool last_inverse_ozaki = false;
+  bool last_inverse_shared = false;            // the trailing update of the last factorisation was shared by the device group
   bool oz_attr_set = false;                    // dynamic shared memory size of ozaki_gemm_kernel raised on this device
   double *dS = nullptr; size_t capS = 0;       // [L][L] raw score
   double *dS2 = nullptr; size_t capS2 = 0;     // [L][L] APC-corrected
@@ -111,6 +112,9 @@ struct gdca_ctx {
   cudaEvent_t ev_group = nullptr;              // this member's arrival at a group barrier / "my copy of the data is complete"
   cudaStream_t stream_copy = nullptr;          // peer copies that run beside the compute stream (factor panels)
   cudaEvent_t ev_copy = nullptr;
+  cudaEvent_t ev_sent = nullptr;               // this member's block columns have arrived at the leader (shared factorisation)
+  cudaEvent_t ev_upd = nullptr;                // this member's compute stream has finished the columns it is about to send
+  int share_min_nb = 128;                      // the trailing update of the factorisation is shared by the group from this many 128-blocks on (env GDCA_SHARE_MIN_NB)
 
   // ---- state flags ----
   bool have_alignment = false, have_lists = false, have_weights = false, have_cov = false, have_inv = false;
@@ -177,6 +181,7 @@ struct gdca_oz_shard {   // one member's share of a product in a device group (n
   int n_off;             // first column of this share within the full product
   int m_off;             // first row of this share within the full product (lower-triangular output test)
   int own_mod, own_rank; // row tiles im with im % own_mod == own_rank (own_mod <= 1: all)
+  int col_mod, col_rank, col_unit0, col_per;  // 64-column tiles jn with ((col_unit0 + jn) / col_per) % col_mod == col_rank (col_mod <= 1: all)
   int npeer;             // output tile stored to npeer buffers at C + peer_off[p] BYTES (0 / 1: C only)
   long long peer_off[GDCA_MAX_PEERS];
 };

@@ -65,6 +65,7 @@ struct OzGemmP {
   int n_off;                     // column of the full product this launch's column 0 is (k range of GDCA_OZ_KBEG_N)
   int m_off;                     // row of the full product this launch's row 0 is (GDCA_OZ_LOWER_OUT test)
   int own_mod, own_rank;         // row tile im is computed iff im % own_mod == own_rank
+  int col_mod, col_rank, col_unit0, col_per;  // column tile jn is computed iff ((col_unit0 + jn) / col_per) % col_mod == col_rank
   int npeer;                     // the C tile is stored to npeer buffers: C + peer_off[p] bytes (own buffer included)
   long long peer_off[GDCA_MAX_PEERS];
 };
@@ -171,7 +172,8 @@ __device__ __forceinline__ Tile decode_tile(const OzGemmP &P, int t, int tm, int
     T.im = (P.flags & GDCA_OZ_KEND_M) ? tm - 1 - o : o;
   }
   const int m0 = T.im * BM, n0 = T.jn * BN;
-  T.valid = !((P.flags & GDCA_OZ_LOWER_OUT) && n0 >= m0 + P.m_off + BM) && (P.own_mod <= 1 || T.im % P.own_mod == P.own_rank);
+  T.valid = !((P.flags & GDCA_OZ_LOWER_OUT) && n0 >= m0 + P.m_off + BM) && (P.own_mod <= 1 || T.im % P.own_mod == P.own_rank) &&
+            (P.col_mod <= 1 || ((P.col_unit0 + T.jn) / P.col_per) % P.col_mod == P.col_rank);
   int kbeg = 0, kend = P.k;
   if (P.flags & GDCA_OZ_KBEG_N) kbeg = max(kbeg, ((P.n_off + n0) / 128) * 128);
   if (P.flags & GDCA_OZ_KBEG_M) kbeg = max(kbeg, m0);
@@ -612,10 +614,14 @@ int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &
   P.m_off = sh ? sh->m_off : 0;
   P.own_mod = sh ? sh->own_mod : 1;
   P.own_rank = sh ? sh->own_rank : 0;
+  P.col_mod = sh ? sh->col_mod : 1;
+  P.col_rank = sh ? sh->col_rank : 0;
+  P.col_unit0 = sh ? sh->col_unit0 : 0;
+  P.col_per = (sh && sh->col_per > 0) ? sh->col_per : 1;
   P.npeer = sh ? sh->npeer : 0;
   for (int i = 0; i < GDCA_MAX_PEERS; ++i) P.peer_off[i] = (sh && i < sh->npeer) ? sh->peer_off[i] : 0;
   if (P.npeer > 1 && beta) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "oz_gemm: replicated stores need beta == 0");
-  P.tri = ((flags & GDCA_OZ_LOWER_OUT) && batch == 1 && m == n && !(flags & GDCA_OZ_KBEG_N) && P.m_off == 0) ? 1 : 0;
+  P.tri = ((flags & GDCA_OZ_LOWER_OUT) && batch == 1 && m == n && !(flags & GDCA_OZ_KBEG_N) && P.m_off == 0 && P.col_mod <= 1) ? 1 : 0;
   const long long total = P.tri ? (long long)(m / BM) * (m / BM + 1) : (long long)batch * (m / BM) * (n / BN);
   P.total = (int)total;
   long long grid = tiles_per_cta > 0 ? (total + tiles_per_cta - 1) / tiles_per_cta : (total < ctx->num_sms ? total : ctx->num_sms);
@@ -633,6 +639,7 @@ int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &
       const int m0 = im * BM, n0 = jn * BN;
       if ((flags & GDCA_OZ_LOWER_OUT) && n0 >= m0 + P.m_off + BM) continue;
       if (P.own_mod > 1 && im % P.own_mod != P.own_rank) continue;
+      if (P.col_mod > 1 && ((P.col_unit0 + jn) / P.col_per) % P.col_mod != P.col_rank) continue;
       int kbeg = 0, kend = k;
       if (flags & GDCA_OZ_KBEG_N) kbeg = kbeg > ((P.n_off + n0) / 128) * 128 ? kbeg : ((P.n_off + n0) / 128) * 128;
       if (flags & GDCA_OZ_KBEG_M) kbeg = kbeg > m0 ? kbeg : m0;

@@ -208,6 +208,10 @@ int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info); /* C -> mJ on this devic
 int32_t gdca_set_ozaki(gdca_ctx *ctx, int32_t mode);
 /* what the last inversion ran: *ozaki 0/1, the INT8 operations executed and the FP64 flop they stand for */
 int32_t gdca_dev_inverse_info(gdca_ctx *ctx, int32_t *ozaki, double *int8_ops, double *fp64_flop_on_int8);
+/* 1 if the last factorisation on a device group shared its trailing update by block columns: every member owns the 512-column
+ * outer blocks ob = rank (mod n), applies each broadcast panel to them and ships the next panel's columns to the leader one step
+ * ahead (automatic for n >= 16 384, where the bulk updates outweigh the serial chain; env GDCA_SHARE_MIN_NB, in 128-blocks). */
+int32_t gdca_dev_inverse_shared(gdca_ctx *ctx);
 /* Test hook (tests/test_gpu_ozaki.py): C[m x n] = beta C + alpha opA opB^T on one FP64 GEMM engine, host buffers, contiguous
  * matrices.  engine 0: dgemm_kernel (DMMA), 1: INT8-sliced tcgen05 kernel (beta 0 or 1).  A is [m][k] (a_cols = 0) or [k][m]
  * (a_cols = 1), B is [n][k] (b_cols = 0) or [k][n] (b_cols = 1).  flags: 1 skip output tiles above the diagonal, 2 k starts at

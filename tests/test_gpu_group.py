@@ -47,6 +47,27 @@ def test_group_of_members_on_one_gpu_is_bit_identical_to_single(pkg, orc, ctx, m
         ctxg.close()
 
 
+@pytest.mark.parametrize("members", [2, 3, 4])
+def test_shared_factorisation_is_bit_identical_to_single(pkg, orc, ctx, monkeypatch, members):
+    """The trailing update of the Cholesky shared by block columns (owners apply the broadcast panels and ship the next panel's
+    columns back one step ahead).  It switches on by itself at n >= 16 384; GDCA_SHARE_MIN_NB=16 forces it at test sizes."""
+    import ctypes
+    monkeypatch.setenv("GDCA_GROUP_ALLOW_SAME_DEVICE", "1")
+    monkeypatch.setenv("GDCA_SHARE_MIN_NB", "16")
+    ctxg = pkg.Context(devices=[0] * members)
+    try:
+        # n = 2560 (20 blocks), 4000 (32 blocks, padded), 4100 (33 blocks: partial last outer block)
+        for (L, M, theta, score, pc) in [(128, 6000, "auto", "frob", 0.8), (200, 3000, 0.3, "DI", 0.2), (205, 2500, "auto", "frob", 0.5)]:
+            Z = orc.synth_alignment(L, M, seed=3 * L + M)
+            R1 = pkg.gdca_from_alignment(Z, pc, theta, score, 5, ctx=ctx, as_array=True)
+            Rg = pkg.gdca_from_alignment(Z, pc, theta, score, 5, ctx=ctxg, as_array=True)
+            assert np.array_equal(Rg["i"], R1["i"]) and np.array_equal(Rg["j"], R1["j"]), (L, M)
+            assert np.array_equal(Rg["score"], R1["score"]), (L, M, float(np.max(np.abs(Rg["score"] - R1["score"]))))
+            assert ctxg.lib.gdca_dev_inverse_shared(ctxg.h) == 1 and ctx.lib.gdca_dev_inverse_shared(ctx.h) == 0
+    finally:
+        ctxg.close()
+
+
 def test_repeated_device_is_rejected_outside_test_mode(pkg, monkeypatch):
     monkeypatch.delenv("GDCA_GROUP_ALLOW_SAME_DEVICE", raising=False)
     with pytest.raises(pkg.GdcaError, match="listed twice"):
