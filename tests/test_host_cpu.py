@@ -281,3 +281,34 @@ def test_fasta_reader_fuzz_against_oracle(pkg, orc, tmp_path):
         assert np.array_equal(d_got, orc.remove_duplicate_sequences(want)) and np.array_equal(d_got, got[keep])
 
     run()
+
+
+def test_bench_arms_describe_the_same_workload_and_probe_julia():
+    """Both arms of bench.py build config.workload from one function (the driver compares the strings), every BASELINE.json config
+    has an entry, and the julia probe reports an outcome instead of assuming one."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.workload_string("C") == "synthetic L=500 M=200000 theta=auto score=frob pseudocount=0.8 min_separation=5 (BASELINE.json configs[2])"
+    assert {"B", "C", "D", "Cs", "E"} <= set(b.WORKLOADS)
+    assert b.WORKLOADS["D"][:4] == (500, 200000, "DI", 0.2) and b.WORKLOADS["E"][:2] == (1500, 1000000)
+    p = b.julia_probe()
+    assert set(p) == {"julia", "outcome"} and isinstance(p["outcome"], str)
+
+
+def test_fullsize_oracle_cache_round_trip(orc, tmp_path, monkeypatch):
+    """oracle/fullsize.py at a small shape: the staged run equals gdca_from_Z, and a cache hit returns the same results."""
+    import importlib
+    monkeypatch.setenv("GDCA_ORACLE_CACHE", str(tmp_path))
+    from oracle import fullsize
+    importlib.reload(fullsize)
+    d = fullsize.pipeline_full(40, 1500, "DI", 0.2, seed=5, keep_big=True)
+    st = {}
+    Ro = orc.gdca_from_Z(orc.synth_alignment(40, 1500, 5), 0.2, "auto", "DI", 5, stages=st)
+    assert np.array_equal(d["counts"], st["counts"]) and d["Meff"] == st["Meff"] and d["thresh"] == st["thresh"]
+    assert [(int(i), int(j)) for i, j, _ in d["R"].tolist()] == [(i, j) for i, j, _ in Ro]
+    assert np.array_equal(d["C"], st["C"]) and not d["cached"]
+    d2 = fullsize.pipeline_full(40, 1500, "DI", 0.2, seed=5)
+    assert d2["cached"] and d2["weights_cached"] and np.array_equal(d2["R"], d["R"]) and np.array_equal(d2["S"], d["S"])
+    assert fullsize.set_all_threads() == (os.cpu_count() or 1) == orc.lib().oracle_max_threads()
