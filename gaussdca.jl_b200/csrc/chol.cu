@@ -23,7 +23,9 @@ constexpr int NB = GDCA_NB;  // 128
 constexpr int BK = 16;
 constexpr int GSTAGES = 4;      // 4-slot ring: stage kt+1 is already visible while kt is computed (fragment prefetch)
 constexpr int LDS_N = BK + 4;    // [row][k] tile stride (doubles): conflict-free 64-bit fragment loads
-constexpr int LDS_T = NB + 8;    // [k][row] tile stride
+constexpr int LDS_T = NB + 8;    // [k][row] tile stride: the transposed orientations (AT / BT) keep 2-way conflicts on their fragment
+                                 // loads (ncu r1: 24 % / 49 % of the wavefronts of <0,1> / <1,1>); since round 2 those instantiations
+                                 // only serve n < 2048 and the small trtri levels -- the big transposed products run in ozaki.cu
 constexpr int TILE_D = NB * LDS_N;  // 2560 doubles >= BK*LDS_T = 2176
 constexpr int GTHREADS = 256;
 

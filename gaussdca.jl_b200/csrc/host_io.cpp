@@ -16,6 +16,7 @@
 //     ("inconsistent inputs");
 //   * a sequence is kept when (#'-' in match columns) / L <= max_gap_fraction;
 //   * A C D E F G H I K L M N P Q R S T V W Y -> 1..20, everything else (B J O U X Z '-' ...) -> 21.
+#include <cmath>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -310,10 +311,17 @@ int32_t gdca_remove_duplicate_sequences(const int8_t *Z, int64_t L, int64_t M, i
 // chunks are written in order: the bytes are exactly those of the serial loop of printrank (src/GaussDCA.jl:67-74).  At
 // L = 1500 the ranking has 1.1 M rows: 0.38 s with a serial fprintf loop (5x the whole GPU path at L = 500), 0.08 - 0.17 s here
 // on 8 warm cores.
+// one row, Julia's @printf spelling of the non-finite values: "NaN", "Inf", "-Inf" (C's %e prints nan / inf / -inf)
+static int format_row(char *out, const gdca_rank_t &r) {
+  if (std::isfinite(r.score)) return snprintf(out, 64, "%lld %lld %e\n", (long long)r.i, (long long)r.j, r.score);
+  const char *v = std::isnan(r.score) ? "NaN" : (r.score > 0 ? "Inf" : "-Inf");
+  return snprintf(out, 64, "%lld %lld %s\n", (long long)r.i, (long long)r.j, v);
+}
+
 static int64_t format_rows(const gdca_rank_t *R, int64_t lo, int64_t hi, char *out) {
   int64_t off = 0;
   for (int64_t k = lo; k < hi; ++k)
-    off += snprintf(out + off, 64, "%lld %lld %e\n", (long long)R[k].i, (long long)R[k].j, R[k].score);
+    off += format_row(out + off, R[k]);
   return off;
 }
 
@@ -359,7 +367,7 @@ int32_t gdca_format_rank(const gdca_rank_t *R, int64_t n, char *buf, int64_t cap
     char tmp[96];
     int64_t len = 0;
     for (int64_t k = lo; k < hi; ++k)
-      len += snprintf(tmp, sizeof tmp, "%lld %lld %e\n", (long long)R[k].i, (long long)R[k].j, R[k].score);
+      len += format_row(tmp, R[k]);
     off[(size_t)c + 1] = len;
   }
   for (int64_t c = 0; c < nchunks; ++c) off[(size_t)c + 1] += off[(size_t)c];

@@ -392,7 +392,9 @@ def gDCA(filename, pseudocount=0.8, theta="auto", max_gap_fraction=0.9, score="f
 
 def format_rank(R) -> str:
     """printrank, src/GaussDCA.jl:67-70: '%i %i %e\\n'"""
-    return "".join("%i %i %e\n" % (i, j, x) for i, j, x in R)
+    def e(x):  # Julia's @printf spells the non-finite values NaN / Inf / -Inf
+        return "%e" % x if math.isfinite(x) else ("NaN" if math.isnan(x) else ("Inf" if x > 0 else "-Inf"))
+    return "".join("%i %i %s\n" % (i, j, e(x)) for i, j, x in R)
 
 
 def synth_alignment(L: int, M: int, seed: int = 20140321) -> np.ndarray:

@@ -213,7 +213,9 @@ def test_rank_writer_is_byte_identical_across_chunk_boundaries(pkg, tmp_path):
     R["score"][:5] = [0.0, -0.0, np.inf, -np.inf, np.nan]
     path = str(tmp_path / "rank.txt")
     for m in (0, 1, 4095, 4096, 4097, 8192, n):
-        want = "".join("%d %d %e\n" % t for t in zip(R["i"][:m].tolist(), R["j"][:m].tolist(), R["score"][:m].tolist()))
+        def jl(x):   # Julia's @printf("%e") spells the non-finite values NaN / Inf / -Inf
+            return "%e" % x if np.isfinite(x) else ("NaN" if np.isnan(x) else ("Inf" if x > 0 else "-Inf"))
+        want = "".join("%d %d %s\n" % (i, j, jl(x)) for i, j, x in zip(R["i"][:m].tolist(), R["j"][:m].tolist(), R["score"][:m].tolist()))
         assert lib.gdca_write_rank(path.encode(), _lib.ptr(R), m) == 0
         assert open(path).read() == want, m
         used = ctypes.c_int64()
