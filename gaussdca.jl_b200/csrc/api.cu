@@ -281,6 +281,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
     const int b = atoi(env);
     if (b == 4 || b == 8 || b == 80) ctx->tc_filter_bits = b;
   }
+  if (const char *env = getenv("GDCA_STAGED_H2D")) ctx->staged_h2d = atoi(env) != 0;
   if (const char *env = getenv("GDCA_CELL_SWEEP")) ctx->cell_sweep = atoi(env) != 0;
   if (const char *env = getenv("GDCA_TC_MULTICAST")) ctx->tc_filter_want_multicast = atoi(env) != 0;
   *out = ctx;
@@ -304,6 +305,7 @@ void gdca_destroy(gdca_ctx *ctx) {
   for (void *m : ctx->peer_opened)
     if (m) cudaIpcCloseMemHandle(m);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  gdca_h2d_release(ctx);
   if (!ctx->dZ_borrowed) cudaFree(ctx->dZ);
   void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPerm, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
@@ -450,7 +452,7 @@ int32_t gdca_dev_load(gdca_ctx *ctx, const int8_t *Z_host, int64_t L, int64_t M)
   }
   GDCA_TRY(rec(ctx, EV_BEGIN));
   GDCA_TRY(gdca_reserve(ctx, ctx->dZ, ctx->capZ, (size_t)L * M + 16));
-  GDCA_CUDA(ctx, cudaMemcpyAsync(ctx->dZ, Z_host, (size_t)L * M, cudaMemcpyHostToDevice, ctx->stream));
+  GDCA_TRY(gdca_h2d(ctx, ctx->dZ, Z_host, (size_t)L * M, ctx->stream));  // pinned: one async copy; pageable: pipelined through a pinned ring
   GDCA_TRY(rec(ctx, EV_H2D));
   GDCA_TRY(load_common(ctx, L, M));
   GDCA_TRY(rec(ctx, EV_PACK));
@@ -830,7 +832,7 @@ static int32_t run_group(gdca_ctx *lead, const int8_t *Z, bool resident, int64_t
       }
       GDCA_TRY(rec(lead, EV_BEGIN));
       GDCA_TRY(gdca_reserve(lead, lead->dZ, lead->capZ, (size_t)L * M + 16));
-      GDCA_CUDA(lead, cudaMemcpyAsync(lead->dZ, Z, (size_t)L * M, cudaMemcpyHostToDevice, lead->stream));
+      GDCA_TRY(gdca_h2d(lead, lead->dZ, Z, (size_t)L * M, lead->stream));
     }
     GDCA_CUDA(lead, cudaEventRecord(lead->ev_group, lead->stream));  // "my copy is complete"
     for (int r = 1; r < N; ++r) {

@@ -12,6 +12,7 @@
 #define GDCA_MAX_PLANES 5      // q <= 31  ->  5 bit planes
 #define GDCA_NB 128            // Cholesky / GEMM block
 #define GDCA_MAX_PEERS 16
+#define GDCA_STAGE_SLOTS 4       // pinned ring of the pageable host-to-device copy (stage_copy.cpp)
 #define GDCA_EV_POTRF 15        // ctx->ev[15]: recorded by chol.cu between the factorisation and the inversion
 
 struct gdca_ctx {
@@ -116,6 +117,11 @@ struct gdca_ctx {
   cudaEvent_t ev_upd = nullptr;                // this member's compute stream has finished the columns it is about to send
   int share_min_nb = 128;                      // the trailing update of the factorisation is shared by the group from this many 128-blocks on (env GDCA_SHARE_MIN_NB)
 
+  // ---- pageable host memory: pipelined H2D through a pinned ring (stage_copy.cpp) ----
+  void *stage_buf[GDCA_STAGE_SLOTS] = {};
+  cudaEvent_t stage_ev[GDCA_STAGE_SLOTS] = {};
+  int staged_h2d = 1;                          // env GDCA_STAGED_H2D=0: plain cudaMemcpyAsync from pageable memory
+
   // ---- state flags ----
   bool have_alignment = false, have_lists = false, have_weights = false, have_cov = false, have_inv = false;
   double meff = 0.0, pseudocount = 0.0;
@@ -188,6 +194,9 @@ struct gdca_oz_shard {   // one member's share of a product in a device group (n
 int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &A, const gdca_oz_operand &B, double *C, long long ldc,
                      long long strideC, int m, int n, int k, int batch, int flags, double alpha, int beta, int tiles_per_cta,
                      const gdca_oz_shard *sh = nullptr);
+
+int32_t gdca_h2d(gdca_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t stream);  // stage_copy.cpp
+void gdca_h2d_release(gdca_ctx *ctx);
 
 // ---- stage entry points implemented across the .cu files ----
 int32_t gdca_k_maxq(gdca_ctx *ctx);                       // pack.cu: dQ <- max(Z)
