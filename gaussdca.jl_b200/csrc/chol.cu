@@ -911,7 +911,7 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
       sh.own_mod = N;
       sh.own_rank = r;
       gdca_oz_operand ox{};
-      GDCA_TRY(mtry(c, gdca_oz_slice(c, c->stream, c->dX, np, 0, true, (int)np, (int)np, 1, np, c->dDigA, c->dScaleA, &ox)));
+      GDCA_TRY(mtry(c, gdca_oz_slice(c, c->stream, c->dX, np, 0, true, (int)np, (int)np, 1, np, c->dDigA, c->dScaleA, &ox, /*lower_only=*/true)));
       GDCA_TRY(mtry(c, gdca_oz_gemm(c, c->stream, ox, ox, J, np, 0, (int)np, (int)np, (int)np, 1, GDCA_OZ_LOWER_OUT | GDCA_OZ_KBEG_M, 1.0, 0, 0, &sh)));
     }
     if (N > 1) GDCA_TRY(barrier());

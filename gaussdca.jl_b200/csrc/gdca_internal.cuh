@@ -182,7 +182,7 @@ struct gdca_oz_operand {
   long long rows_b;       // rows between consecutive batch members
 };
 int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, long long ld, long long stride_b, bool cols, int rows,
-                      int k, int batch, long long rows_b, int8_t *dig, double *scale, gdca_oz_operand *out);
+                      int k, int batch, long long rows_b, int8_t *dig, double *scale, gdca_oz_operand *out, bool lower_only = false);
 struct gdca_oz_shard {   // one member's share of a product in a device group (nullptr: the whole product, one output buffer)
   int n_off;             // first column of this share within the full product
   int m_off;             // first row of this share within the full product (lower-triangular output test)

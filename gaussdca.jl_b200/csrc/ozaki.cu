@@ -462,14 +462,19 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double *__restric
 
 // operand element (r, kk) = src[kk * ld + r] (operand rows = columns of a row-major matrix)
 // pass 1: column maxima (|x| as ordered 64-bit patterns, atomicMax)
+// lower_only: the source is lower triangular in 128-blocks (X = inv(L)): column r is zero above k = 128 floor(r / 128), and the
+// product that consumes the digits never reads them there -- neither scanned nor sliced
 __global__ void __launch_bounds__(256) col_absmax_kernel(const double *__restrict__ src, long long ld, long long stride_b, int rows,
-                                                         int k, long long rows_b, unsigned long long *__restrict__ mx_out) {
+                                                         int k, long long rows_b, unsigned long long *__restrict__ mx_out,
+                                                         int lower_only) {
   __shared__ double sh[8][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int b = blockIdx.z;
   const int r = blockIdx.x * 32 + x;
   const int kchunk = (k + gridDim.y - 1) / gridDim.y;
-  const int k0 = blockIdx.y * kchunk, k1 = min(k, k0 + kchunk);
+  int k0 = blockIdx.y * kchunk;
+  const int k1 = min(k, k0 + kchunk);
+  if (lower_only) k0 = max(k0, (blockIdx.x * 32 / 128) * 128);
   const double *a = src + b * stride_b + r;
   double mx = 0.0;
   if (r < rows)
@@ -485,10 +490,19 @@ __global__ void __launch_bounds__(256) col_absmax_kernel(const double *__restric
 // pass 2: 64 (k) x 64 (r) tiles through shared memory, digits written 64 bytes per (row, digit)
 __global__ void __launch_bounds__(256) slice_cols_kernel(const double *__restrict__ src, long long ld, long long stride_b, int rows,
                                                          int k, long long rows_b, const unsigned long long *__restrict__ mx_in,
-                                                         int8_t *__restrict__ dig, long long pitch, double *__restrict__ scale_out) {
+                                                         int8_t *__restrict__ dig, long long pitch, double *__restrict__ scale_out,
+                                                         int lower_only) {
   __shared__ double tile[64][65];  // [r][kk]
   const int b = blockIdx.z;
   const int r0 = blockIdx.x * 64, kb = blockIdx.y;
+  if (lower_only && kb * KBLK + KBLK <= (r0 / 128) * 128) {  // all zeros, never read: only the row scales are due
+    if (kb == 0 && threadIdx.x < 64) {
+      double inv, sc;
+      row_exponent(__longlong_as_double((long long)mx_in[b * rows_b + r0 + threadIdx.x]), inv, sc);
+      scale_out[b * rows_b + r0 + threadIdx.x] = sc;
+    }
+    return;
+  }
   const double *a = src + b * stride_b + (long long)kb * KBLK * ld + r0;
   for (int e = threadIdx.x; e < 64 * 64; e += 256) {
     const int kk = e >> 6, r = e & 63;
@@ -551,7 +565,7 @@ int32_t make_digit_map(gdca_ctx *ctx, CUtensorMap *map, const void *dig, long lo
 // Slice `batch` operands of `rows` x `k` (rows stacked rows_b apart in the digit matrix) into `out`.
 //   cols == false: element (r, kk) = src[b * stride_b + r * ld + kk];  cols == true: element (r, kk) = src[b * stride_b + kk * ld + r]
 int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, long long ld, long long stride_b, bool cols, int rows,
-                      int k, int batch, long long rows_b, int8_t *dig, double *scale, gdca_oz_operand *out) {
+                      int k, int batch, long long rows_b, int8_t *dig, double *scale, gdca_oz_operand *out, bool lower_only) {
   if (rows % 64 || k % 128 || rows <= 0 || k <= 0 || batch <= 0)
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "oz_slice: rows must be a multiple of 64 and k a multiple of 128");
   const long long pitch = (long long)(k / KBLK) * SLOTS * KBLK;
@@ -567,10 +581,10 @@ int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, lon
     if (ksplit < 1) ksplit = 1;
     if (ksplit > 32) ksplit = 32;
     col_absmax_kernel<<<dim3((unsigned)((rows + 31) / 32), (unsigned)ksplit, (unsigned)batch), 256, 0, stream>>>(
-        src, ld, stride_b, rows, k, rows_b, ctx->dOzMax);
+        src, ld, stride_b, rows, k, rows_b, ctx->dOzMax, lower_only ? 1 : 0);
     GDCA_LAUNCH_CHECK(ctx);
     slice_cols_kernel<<<dim3((unsigned)(rows / 64), (unsigned)(k / KBLK), (unsigned)batch), 256, 0, stream>>>(
-        src, ld, stride_b, rows, k, rows_b, ctx->dOzMax, dig, pitch, scale);
+        src, ld, stride_b, rows, k, rows_b, ctx->dOzMax, dig, pitch, scale, lower_only ? 1 : 0);
     GDCA_LAUNCH_CHECK(ctx);
   }
   out->dig = dig;
