@@ -81,6 +81,8 @@ SIGNATURES = {
     "gdca_set_tc_filter": (_i32, [_p, _i32]),
     "gdca_dev_tc_filter": (_i32, [_p, _i64, _p, _p, _i64]),
     "gdca_dev_cov_kernel_ms": (_i32, [_p, ctypes.POINTER(ctypes.c_float)]),
+    "gdca_set_cov_engine": (_i32, [_p, _i32]),
+    "gdca_dev_cov_info": (_i32, [_p, _pi32, _pi32, _pi32, _pi64, _pi32, _pdbl, _pdbl]),
     "gdca_set_tc_filter_bits": (_i32, [_p, _i32]),
     "gdca_set_tc_filter_multicast": (_i32, [_p, _i32]),
     "gdca_tc_filter_tile_order": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _pi64]),
@@ -211,6 +213,20 @@ class Context:
             self.lib.gdca_dev_get_stats(self.h, ctypes.byref(s))
             raise PosDefException(s.posdef_info)
         raise GdcaError(st, f"{self.lib.gdca_status_string(st).decode()}: {msg}")
+
+    def set_cov_engine(self, mode: int):
+        """0 auto, 1 scatter-add engine, 2 co-occurrence counts per weight class on the FP4 tensor cores (gdca_set_cov_engine)."""
+        self.check(self.lib.gdca_set_cov_engine(self.h, int(mode)))
+
+    def cov_info(self) -> dict:
+        """What the last covariance stage ran on (gdca_dev_cov_info)."""
+        eng, cls, seg, clu = _i32(), _i32(), _i32(), _i32()
+        kb = _i64()
+        tf, l2 = _dbl(), _dbl()
+        self.check(self.lib.gdca_dev_cov_info(self.h, ctypes.byref(eng), ctypes.byref(cls), ctypes.byref(seg), ctypes.byref(kb),
+                                              ctypes.byref(clu), ctypes.byref(tf), ctypes.byref(l2)))
+        return dict(engine=eng.value, classes=cls.value, segments=seg.value, kblocks=kb.value, clusters=clu.value,
+                    tflop=tf.value, l2_bytes=l2.value)
 
     def stats(self) -> dict:
         s = Stats()

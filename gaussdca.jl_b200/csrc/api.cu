@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include <stdlib.h>
 
@@ -86,6 +87,7 @@ int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
   if (ctx->peers_ready && ((size_t)3 * ctx->Mpad > ctx->capCounts || (size_t)ctx->npad * ctx->npad > ctx->capC)) peer_close_all(ctx);
   ctx->have_alignment = true;
   ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  ctx->weights_from_counts = false;
   ctx->have_V = 0;
   GDCA_TRY(gdca_k_pack(ctx));  // builds the per-site lists first (site order), then the bit planes
   return GDCA_OK;
@@ -144,6 +146,7 @@ int32_t weights_stage(gdca_ctx *ctx, double theta) {
 // gdca_dev_* call reports GDCA_ERR_STATE instead of mixing the new shape with the old buffers.
 void drop_alignment_state(gdca_ctx *ctx) {
   ctx->have_alignment = ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  ctx->weights_from_counts = false;
   ctx->have_V = 0;
   if (ctx->dZ_borrowed) {
     ctx->dZ = nullptr;
@@ -284,6 +287,10 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if (const char *env = getenv("GDCA_STAGED_H2D")) ctx->staged_h2d = atoi(env) != 0;
   if (const char *env = getenv("GDCA_CELL_SWEEP")) ctx->cell_sweep = atoi(env) != 0;
   if (const char *env = getenv("GDCA_TC_MULTICAST")) ctx->tc_filter_want_multicast = atoi(env) != 0;
+  if (const char *env = getenv("GDCA_COV_ENGINE")) {
+    const int m = atoi(env);
+    if (m >= 0 && m <= 2) ctx->cov_engine = m;
+  }
   *out = ctx;
   return GDCA_OK;
 }
@@ -311,7 +318,8 @@ void gdca_destroy(gdca_ctx *ctx) {
                   ctx->dListOff, ctx->dPi, ctx->dC,   ctx->dX,    ctx->dmJ,  ctx->dCdiag, ctx->dT,   ctx->dInfo,
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
                   ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask,
-                  ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax, ctx->dCellBase, ctx->dDigP, ctx->dScaleP};
+                  ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax, ctx->dCellBase, ctx->dDigP, ctx->dScaleP,
+                  ctx->dClsHist, ctx->dClsPerm, ctx->dClsTab, ctx->dXt, ctx->dCovTiles};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)
@@ -610,6 +618,7 @@ int32_t gdca_dev_set_weights(gdca_ctx *ctx, const double *W_host, double meff) {
   ctx->meff = meff;
   ctx->stats.meff = meff;
   ctx->have_weights = true;
+  ctx->weights_from_counts = false;  // arbitrary weights: the scatter-add covariance engine
   return GDCA_OK;
 }
 
@@ -619,6 +628,29 @@ int32_t gdca_dev_covariance(gdca_ctx *ctx, double pseudocount) {
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "invalid pseudocount value (must be between 0 and 1)");
   GDCA_TRY(set_device(ctx));
   return gdca_k_covariance(ctx, pseudocount);
+}
+
+int32_t gdca_set_cov_engine(gdca_ctx *ctx, int32_t mode) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (mode < 0 || mode > 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_cov_engine: mode must be 0 (auto), 1 (scatter-add) or 2 (tensor cores)");
+  ctx->cov_engine = mode;
+  for (int r = 1; r < ctx->group_size; ++r)
+    if (ctx->group[r]) ctx->group[r]->cov_engine = mode;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_cov_info(gdca_ctx *ctx, int32_t *engine, int32_t *classes, int32_t *segments, int64_t *kblocks, int32_t *clusters,
+                          double *tflop, double *l2_bytes) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  const bool tc = ctx->last_cov_engine == 2;
+  if (engine) *engine = ctx->last_cov_engine;
+  if (classes) *classes = ctx->cov_tc_classes;
+  if (segments) *segments = tc ? ctx->cov_tc_segments : 0;
+  if (kblocks) *kblocks = tc ? ctx->cov_tc_kblocks : 0;
+  if (clusters) *clusters = tc ? ctx->cov_tc_clusters : 0;
+  if (tflop) *tflop = tc ? ctx->cov_tc_tflop : 0.0;
+  if (l2_bytes) *l2_bytes = tc ? ctx->cov_tc_l2_bytes : 0.0;
+  return GDCA_OK;
 }
 
 int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info) {
@@ -911,9 +943,17 @@ static int32_t run_group(gdca_ctx *lead, const int8_t *Z, bool resident, int64_t
     // ---- 4. covariance: rows dealt by site, every member stores its rows straight into the leader's C
     GDCA_CUDA(lead, cudaMemsetAsync(lead->dC, 0, (size_t)lead->npad * lead->npad * sizeof(double), lead->stream));
     GDCA_TRY(group_barrier(lead));
+    // the weight classes of the tensor-core engine are the same on every member (every member holds all counts): one device
+    // round trip on the leader, the members plan from its copy
+    std::vector<int32_t> cls(1 + 2 * GDCA_COV_MAXCLS);
+    const bool share_cls = lead->cov_engine != 1 && lead->weights_from_counts;
+    if (share_cls) GDCA_TRY(gdca_k_cov_classes(lead, cls.data()));
     for (int r = 0; r < N; ++r) {
       GDCA_TRY(set_device(g[r]));
-      GDCA_TRY(member_try(lead, g[r], gdca_k_covariance(g[r], pseudocount)));
+      g[r]->cov_cls_host = share_cls ? cls.data() : nullptr;
+      const int32_t cst = member_try(lead, g[r], gdca_k_covariance(g[r], pseudocount));
+      g[r]->cov_cls_host = nullptr;
+      GDCA_TRY(cst);
     }
     GDCA_TRY(group_barrier(lead));
     GDCA_TRY(set_device(lead));

@@ -316,9 +316,11 @@ int32_t gdca_k_compute_C(gdca_ctx *ctx, const double *Pi, const double *Pij, lon
 
 int32_t gdca_k_symmetrize_C(gdca_ctx *ctx) {
   const long long n = ctx->n;
-  const unsigned nt = (unsigned)((n + 31) / 32);
-  symmetrize_kernel<<<dim3(nt, nt), 256, 0, ctx->stream>>>(ctx->dC, n, ctx->npad, ctx->s);
-  GDCA_LAUNCH_CHECK(ctx);
+  if (!ctx->cov_full) {  // the tensor-core engine writes every tile together with its mirror image
+    const unsigned nt = (unsigned)((n + 31) / 32);
+    symmetrize_kernel<<<dim3(nt, nt), 256, 0, ctx->stream>>>(ctx->dC, n, ctx->npad, ctx->s);
+    GDCA_LAUNCH_CHECK(ctx);
+  }
   return gdca_k_extract_diag(ctx);
 }
 
@@ -366,6 +368,24 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw) {
   GDCA_TRY(gdca_reserve(ctx, ctx->dPi, ctx->capPi, (size_t)n));
   const long long npad = ctx->npad;
   GDCA_TRY(gdca_reserve(ctx, ctx->dC, ctx->capC, (size_t)npad * npad));
+  ctx->cov_full = false;
+  ctx->last_cov_engine = 1;
+  pi_kernel<<<(unsigned)L, 256, 0, ctx->stream>>>(ctx->dList, ctx->dListOff, ctx->dW, ctx->dMeff, M, ctx->q, pc, ctx->dPi);
+  GDCA_LAUNCH_CHECK(ctx);
+  if (ctx->cov_engine != 1 && ctx->weights_from_counts) {
+    // weights that are 1/(integer count): exact co-occurrence counts per weight class on the tensor cores (covtc.cu) when the
+    // classes are few and large enough to pay; otherwise, and for arbitrary weights, the scatter-add engine below
+    bool done = false;
+    GDCA_TRY(gdca_k_covariance_tc(ctx, pc, raw, &done));
+    if (done) {
+      ctx->pseudocount = pc;
+      ctx->have_cov = true;
+      ctx->have_inv = false;
+      ctx->cov_full = true;
+      ctx->last_cov_engine = 2;
+      return GDCA_OK;
+    }
+  }
   const long long Lq = (L + 127) / 128 * 128;
   if ((unsigned long long)M * (unsigned long long)Lq >= (1ull << 32))
     return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "covariance: M * roundup(L,128) must be < 2^32");
@@ -373,8 +393,6 @@ int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw) {
   build_zq_kernel<<<(unsigned)(((size_t)M * Lq + 255) / 256), 256, 0, ctx->stream>>>(ctx->dZ, L, M, Lq, ctx->s, ctx->dZq);
   GDCA_LAUNCH_CHECK(ctx);
 
-  pi_kernel<<<(unsigned)L, 256, 0, ctx->stream>>>(ctx->dList, ctx->dListOff, ctx->dW, ctx->dMeff, M, ctx->q, pc, ctx->dPi);
-  GDCA_LAUNCH_CHECK(ctx);
   // zero everything: padding rows/cols, the not-yet-mirrored lower part, and other shards' rows.  In peer mode the
   // host zeroes rank 0's buffer (gdca_dev_zero_C) and barriers BEFORE any rank launches this stage.
   if (!(ctx->peers_ready && ctx->shard_world > 1))

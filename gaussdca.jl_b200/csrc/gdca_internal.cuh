@@ -13,6 +13,7 @@
 #define GDCA_NB 128            // Cholesky / GEMM block
 #define GDCA_MAX_PEERS 16
 #define GDCA_STAGE_SLOTS 4       // pinned ring of the pageable host-to-device copy (stage_copy.cpp)
+#define GDCA_COV_MAXCLS 512      // weight classes / class segments the tensor-core covariance handles
 #define GDCA_EV_POTRF 15        // ctx->ev[15]: recorded by chol.cu between the factorisation and the inversion
 
 struct gdca_ctx {
@@ -96,7 +97,22 @@ struct gdca_ctx {
   double tc_filter_l2_bytes = 0.0;                 // operand bytes its TMA loads moved
   long long tc_filter_tiles = 0;
   cudaEvent_t ev_sweep0 = nullptr, ev_filter = nullptr, ev_sweep1 = nullptr;  // filter / exact sweep split
-  cudaEvent_t ev_cov0 = nullptr, ev_cov1 = nullptr;                            // around cov_rows_kernel alone
+  cudaEvent_t ev_cov0 = nullptr, ev_cov1 = nullptr;                            // around cov_rows_kernel / cov_tc_kernel alone
+
+  // ---- covariance on the tensor cores: co-occurrence counts per weight class (covtc.cu) ----
+  int cov_engine = 0;                              // 0 auto (cost model), 1 scatter-add engine (cov.cu), 2 tensor cores whenever the weights are count classes (env GDCA_COV_ENGINE)
+  int32_t *dClsHist = nullptr; size_t capClsHist = 0;  // [M] histogram of the counts + compacted (value, size) pairs
+  int32_t *dClsPerm = nullptr; size_t capClsPerm = 0;  // [Mk] sequences in class order (-1: padding) + cursors + class values + segment ends
+  double *dClsTab = nullptr; size_t capClsTab = 0;     // class bases (int64) and segment weights
+  uint8_t *dXt = nullptr; size_t capXt = 0;        // [n][Mk/2] one-hot operand, packed e2m1, K-major
+  int2 *dCovTiles = nullptr; size_t capCovTiles = 0;   // super-tiles of this rank
+  bool weights_from_counts = false;                // W = 1/(count+1) of dCounts[counts_row] (or all 1): the classes are the distinct counts
+  bool cov_full = false;                           // the last covariance wrote both triangles (nothing to mirror)
+  int last_cov_engine = 0;                         // 1 scatter-add, 2 tensor cores
+  int cov_tc_classes = 0, cov_tc_segments = 0, cov_tc_clusters = 0;
+  long long cov_tc_kblocks = 0;
+  double cov_tc_tflop = 0.0, cov_tc_l2_bytes = 0.0;
+  int32_t *cov_cls_host = nullptr;                 // device groups: the leader's compacted classes, so the members plan without a device round trip
 
   // ---- peer memory (one process per GPU): IPC-mapped counts / C buffers of the other ranks ----
   bool peers_ready = false;
@@ -213,6 +229,10 @@ int32_t gdca_k_finish_weights(gdca_ctx *ctx, int which);  // weights.cu
 int32_t gdca_k_build_lists(gdca_ctx *ctx);                // cov.cu: per-site lists of sequence ids grouped by state
 int32_t gdca_k_ident_sum(gdca_ctx *ctx, unsigned long long *ident_out);  // cov.cu: sum_{k<l} ident from site histograms
 int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw = false);  // cov.cu (raw: Pij_true instead of C)
+int32_t gdca_k_covariance_tc(gdca_ctx *ctx, double pc, bool raw, bool *done);  // covtc.cu: tensor-core engine; *done = false: not applicable
+int32_t gdca_k_cov_classes(gdca_ctx *ctx, int32_t *host_out /*[1 + 2 * GDCA_COV_MAXCLS]*/);  // covtc.cu: distinct counts and their sizes
+struct CUtensorMap_st;
+int32_t gdca_make_tensor_map_2d(gdca_ctx *ctx, CUtensorMap_st *map, void *base, long long rows, long long row_bytes, int box_rows);  // tcfilter.cu: 128-byte boxes, SWIZZLE_128B
 int32_t gdca_k_add_pseudocount(gdca_ctx *ctx, const double *Pi_true, const double *Pij_true, long long n, int q, double pc,
                                double *Pi, double *Pij);  // cov.cu, contiguous device buffers
 int32_t gdca_k_compute_C(gdca_ctx *ctx, const double *Pi, const double *Pij, long long n, double *C);  // cov.cu

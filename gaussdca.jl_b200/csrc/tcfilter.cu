@@ -641,6 +641,10 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
 
 }  // namespace
 
+int32_t gdca_make_tensor_map_2d(gdca_ctx *ctx, CUtensorMap_st *map, void *base, long long rows, long long row_bytes, int box_rows) {
+  return make_tensor_map(ctx, map, base, rows, row_bytes, box_rows);
+}
+
 // Host-side replay of the kernel's tile order for one CTA (the same TileIter code, compiled for the host): rows of
 // {bi, cj, valid, peer_valid} in visiting order.  Lets CPU tests check coverage, disjointness across ranks and the
 // lock-step of cluster pairs without a GPU.

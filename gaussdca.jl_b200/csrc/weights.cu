@@ -92,5 +92,6 @@ int32_t gdca_k_finish_weights(gdca_ctx *ctx, int which) {
   GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->have_weights = true;
   ctx->counts_row = which;
+  ctx->weights_from_counts = true;
   return GDCA_OK;
 }

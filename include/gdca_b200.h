@@ -175,8 +175,18 @@ int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t rank, int32_t
  * flop (1e12) and TMA operand bytes; 128x128 blocks that went through the exact sweep; device ms of the two parts. */
 int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
                             int64_t *swept_blocks, float *ms_filter, float *ms_exact, double *filter_l2_bytes);
-/* device ms of the last cov_rows_kernel launch alone (the covariance stage also runs small preparation kernels) */
+/* device ms of the last cov_rows_kernel / cov_tc_kernel launch alone (the covariance stage also runs small preparation kernels) */
 int32_t gdca_dev_cov_kernel_ms(gdca_ctx *ctx, float *ms);
+/* Engine of the frequency / covariance stage (DCAUtils compute_weighted_frequencies, call site src/GaussDCA.jl:28):
+ *   1 = scatter-add (cov.cu; any weights), 2 = exact co-occurrence counts per weight class on the FP4 tensor cores (covtc.cu;
+ *   needs W = 1/count, i.e. weights computed by this library), 0 = auto: the tensor cores when a cost model of the class sizes
+ *   says they win (default; env GDCA_COV_ENGINE).  With mode 2 the scatter-add engine still runs when the weights were supplied
+ *   by the caller (gdca_dev_set_weights / gdca_compute_covariance) or there are more than 512 distinct counts. */
+int32_t gdca_set_cov_engine(gdca_ctx *ctx, int32_t mode);
+/* what the last covariance ran on: engine (1 / 2), distinct counts found, class segments, 256-sequence k-blocks of the operand,
+ * 4-CTA clusters launched, FP4 tensor work in 1e12 flop, TMA operand bytes requested from L2.  Any pointer may be NULL. */
+int32_t gdca_dev_cov_info(gdca_ctx *ctx, int32_t *engine, int32_t *classes, int32_t *segments, int64_t *kblocks, int32_t *clusters,
+                          double *tflop, double *l2_bytes);
 /* mode-0 sweep over every stride-th tile of this shard (cheap estimate of the mean identity). */
 int32_t gdca_dev_pair_sample(gdca_ctx *ctx, int32_t stride);
 /* partial results of this shard, device pointers: u64[2] {hamming sum, pairs visited} (after a mode-1 sweep
