@@ -92,24 +92,33 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
-    def start(self):
+    def start(self, wait_s=5.0):
+        """Launch nvidia-smi and wait for its first row: the sampler must already be running when the timed region begins
+        (a step is ~45 ms: a sampler started at the region's first step would deliver nothing before the last)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < wait_s:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Row index now: rows [mark() at region start, mark() at region end) were sampled during the region."""
+        return len(self.rows)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, lo=0, hi=None):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[lo:hi]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -422,15 +431,17 @@ def main():
             flushbuf.zero_()
 
     # ---- value: device-resident, per-step CUDA events on the library stream, L2 flushed between steps
+    sampler = ClockSampler(local)
+    sampler.start()
     launches0 = lib.gdca_dev_kernel_launches(ctx.h)
     for _ in range(W):
         run.step_resident()
     launches1 = lib.gdca_dev_kernel_launches(ctx.h)
-    sampler = ClockSampler(local)
-    sampler.start()
+    m0 = sampler.mark()
     ms_step, stage_acc = run.timed_resident(0, K, l2_flush)
     launches2 = lib.gdca_dev_kernel_launches(ctx.h)
-    clocks = sampler.stop()
+    time.sleep(0.03)             # the sample taken during the last step reaches the pipe
+    m1 = sampler.mark()
     cov_ms = ctypes.c_float()
     ctx.check(lib.gdca_dev_cov_kernel_ms(ctx.h, ctypes.byref(cov_ms)))   # cov_rows_kernel of the last timed step
     stats = run.st.asdict()
@@ -445,6 +456,12 @@ def main():
         e2e_pageable = {"value": p_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": run.n_out * 24,
                         "host_memory": "pageable (numpy / a Julia Matrix{Int8}): cudaMemcpyAsync stages it through the driver"}
     top = [int(R["i"][0]), int(R["j"][0]), float(R["score"][0])] if R is not None else None
+    m2 = sampler.mark()
+    # clocks DURING the timed region of `value`; if nvidia-smi delivered fewer than 3 rows in it, the e2e timed regions that
+    # follow it back to back are included (and the window says so)
+    few = (m1 - m0) < 3
+    clocks = sampler.stop(m0, m2 if few else m1)
+    clocks["window"] = "timed resident steps + timed e2e steps" if few else "timed resident steps"
 
     # ---- parity of THIS run (the e2e call's results) against the oracle run for real on the same alignment; cpu_baseline
     cb, parity, o_main = None, None, None
@@ -558,9 +575,11 @@ def main():
             "theta_passes": stats["theta_passes"],
             "weights_pairs_per_s": npairs / ((stage_acc.get("ms_theta", 0) + stage_acc.get("ms_weights", 0)) / 1e3 + 1e-30),
             "cov_fp64_equiv_tflops": M * n * (n + 1) / t_cov / 1e12 if t_cov else None,
-            "cov_fp64_equiv_note": ("SURVEY 8(d) counts the DENSE contraction M n (n+1); the kernel does the M L(L+1)/2 non-zero "
-                                    "additions of the one-hot product instead (1/400 of the dense flop), so this figure exceeds the "
-                                    "DMMA peak by construction: it describes the algorithm, not a tensor-pipe utilisation"),
+            "cov_fp64_equiv_note": ("SURVEY 8(d) counts the DENSE contraction M n (n+1) against the FP64 tensor peak.  The tensor-core "
+                                    "engine executes that contraction as exact 0/1 products on the FP4 tensor cores (one class of equal "
+                                    "weights at a time, FP64 combination), the scatter-add engine only its M L(L+1)/2 non-zero terms: "
+                                    "either way the figure exceeds the DMMA peak by construction -- see roofline_kernels for the pipe "
+                                    "each engine is really bound by"),
             "chol_inv_tflops": n ** 3 / t_chol / 1e12 if t_chol else None,
             "cov_plus_inv_fp64_equiv_tflops": (M * n * (n + 1) + n ** 3) / (t_cov + t_chol) / 1e12 if t_cov else None,
             "dmma_peak_tflops_measured": dmma.value, "dfma_peak_tflops_measured": dfma.value,
@@ -570,17 +589,49 @@ def main():
         smem_peak = 148 * 128 * sm_clk / 1e12                       # TB/s: 128 B/clk/SM shared-memory crossbar
         t_cv = cov_ms.value / 1e3
         rmw = M * L * (L + 1) // 2                                   # FP64 additions = 8-byte smem read + 8-byte write each
-        cov_entry = {
-            "kernel": "cov_rows_kernel<2> (weighted one-hot covariance as M*L(L+1)/2 private shared-memory FP64 adds)",
-            "bound": "shared_memory", "achieved": 16 * rmw / t_cv / 1e12, "peak": smem_peak, "unit": "TB/s",
-            "frac": 16 * rmw / t_cv / 1e12 / smem_peak,
-            "peak_source": "148 SMs x 128 B/clk (B300_MICROARCH.md shared-memory crossbar) x SM clock under load (nominal; "
-                           "MEASURED_PEAKS.json has no shared-memory figure)",
-            "ms_per_launch": cov_ms.value, "adds_per_launch": rmw,
-            "traffic": ncu_traffic("cov_rows_kernel<2, 0>") or ncu_traffic("cov_rows_kernel<2>") if name == "C" else None,
-            "hbm": {"achieved": (L * M + 8 * n * n / 2) / t_cv / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
-                    "note": "compulsory bytes (recoded alignment once + upper half of C once); not the limiter"},
-        }
+        cinfo = ctx.cov_info()
+        if cinfo["engine"] == 2:
+            # exact co-occurrence counts per weight class on the FP4 tensor cores (csrc/covtc.cu): the SURVEY 8(d) convention --
+            # the dense contraction M n (n+1) -- now IS what the kernel executes (lower triangle + mirror image)
+            bf16 = pk.get("bf16_tflops")
+            alg = float(M) * n * (n + 1)
+            cov_entry = {
+                "kernel": ("cov_tc_kernel (X'WX as integer co-occurrence counts per weight class: tcgen05 kind::mxf4 128x128x64, 2x2 "
+                           "clusters with TMA multicast of the operand halves, FP64 combination sum_c w_c N_c in the epilogue registers)"),
+                "bound": "tensor", "achieved": alg / t_cv / 1e12, "peak": 9000.0, "unit": "TFLOP/s",
+                "frac": alg / t_cv / 1e12 / 9000.0,
+                "peak_source": "nominal dense FP4 tensor rate of the B200_PROFILING.md table: MEASURED_PEAKS.json measures bf16 only",
+                "frac_of_measured_bf16_scaled": (alg / t_cv / 1e12 / (4.0 * bf16)) if bf16 else None,
+                "algorithmic_flop_per_launch": alg,
+                "algorithmic_note": "SURVEY 8(d): M n (n+1) flop of the dense one-hot contraction (FP64-equivalent)",
+                "executed_tflop_per_launch": cinfo["tflop"], "executed_tflops": cinfo["tflop"] / t_cv,
+                "executed_note": "every 128x128x256 MMA block issued, incl. the padding of the classes to whole k-blocks and the "
+                                 "unused quarter of the diagonal super-tiles",
+                "weight_classes": cinfo["classes"], "class_segments": cinfo["segments"], "kblocks_of_256_sequences": cinfo["kblocks"],
+                "clusters_of_4_ctas": cinfo["clusters"],
+                "operand_bytes_into_sms_per_launch": 2.0 * cinfo["l2_bytes"],
+                "sm_ingest_bytes_per_clk_per_sm": 2.0 * cinfo["l2_bytes"] / t_cv / (4 * cinfo["clusters"]) / sm_clk,
+                "sm_ingest_note": "32 KB of operands per 128x128x256 block arrive in every SM (half fetched, half multicast by the "
+                                  "neighbour): the L2->SM path delivers 64 B/clk/SM (ncu: l1tex__m_xbar2l1tex_read_bytes), which "
+                                  "caps a 128x128 FP4 tile at 0.53 of the tensor rate",
+                "l2_read_bytes_per_launch": cinfo["l2_bytes"],
+                "ms_per_launch": cov_ms.value,
+                "traffic": ncu_traffic("cov_tc_kernel") if name == "C" else None,
+                "hbm": {"achieved": (float(n) * cinfo["kblocks"] * 128 + 8.0 * n * n) / t_cv / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                        "note": "compulsory bytes (one-hot operand once + C once); not the limiter"},
+            }
+        else:
+            cov_entry = {
+                "kernel": "cov_rows_kernel<2> (weighted one-hot covariance as M*L(L+1)/2 private shared-memory FP64 adds)",
+                "bound": "shared_memory", "achieved": 16 * rmw / t_cv / 1e12, "peak": smem_peak, "unit": "TB/s",
+                "frac": 16 * rmw / t_cv / 1e12 / smem_peak,
+                "peak_source": "148 SMs x 128 B/clk (B300_MICROARCH.md shared-memory crossbar) x SM clock under load (nominal; "
+                               "MEASURED_PEAKS.json has no shared-memory figure)",
+                "ms_per_launch": cov_ms.value, "adds_per_launch": rmw,
+                "traffic": ncu_traffic("cov_rows_kernel<2, 0, 1>") or ncu_traffic("cov_rows_kernel<2, 0>") if name == "C" else None,
+                "hbm": {"achieved": (L * M + 8 * n * n / 2) / t_cv / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                        "note": "compulsory bytes (recoded alignment once + upper half of C once); not the limiter"},
+            }
         inv_info = _inverse_info(ctx, lib)
         inv_entry = {
             "kernel": inv_info.get("kernel", "dgemm_kernel<*> + diag_block_kernel (blocked Cholesky, trtri by recursive doubling, lauum)"),
