@@ -245,6 +245,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   for (cudaEvent_t *ev : {&ctx->ev_diag, &ctx->ev_p1, &ctx->ev_u2a, &ctx->ev_u2b})
     if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_CHOL_LOOKAHEAD")) ctx->chol_inner_lookahead = atoi(env) != 0;
+  if (const char *env = getenv("GDCA_DIAG_BLOCKED")) ctx->diag_blocked = atoi(env) != 0;
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fact, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_sliced, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
@@ -261,7 +262,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if (const char *env = getenv("GDCA_OZAKI")) ctx->ozaki_mode = atoi(env) != 0;
   if (const char *env = getenv("GDCA_OZ_TPC")) {
     const int v = atoi(env);
-    if (v >= 0 && v <= 1024) ctx->ozaki_tpc = v;
+    if (v >= -1024 && v <= 1024) ctx->ozaki_tpc = v;
   }
   if ((e = cudaMalloc((void **)&ctx->dHam, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dQ, 2 * sizeof(int))) != cudaSuccess) return fail(e);

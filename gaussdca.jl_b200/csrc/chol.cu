@@ -417,6 +417,218 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel(const double *__restr
   DIAG_STAMP(4);
 }
 
+// ---- diagonal block, blocked (round 2; the chain of the factorisation waits for this kernel 79 times at n = 10 000) ----
+// Same contract as diag_block_kernel: A[k,k] (lower) -> inv(chol(A[k,k])) written to X[k,k] (lower, zeros above); a non-positive
+// pivot records the order of the failing leading minor.  Same arithmetic per element (rs = rsqrt(pivot), L_jj = pivot * rs,
+// L_ij = a_ij * rs, right-looking updates), different schedule: instead of 128 + 128 barrier-separated rank-1 steps of the whole
+// CTA (70 us), the block is factorised in four 32-column panels held in shared memory:
+//   (a) the 32 x 32 diagonal block: ONE warp, a row per lane in registers, pivots and multipliers by shuffle, no barrier;
+//       its inverse right behind it (a column per lane, forward substitution with broadcast reads of the factor);
+//   (b) the rows below: L = A * inv(L_D)' as DMMA strips of 8 rows (a warp owns its strip: in place);
+//   (c) the trailing block: A -= L L' on the 8 x 8 lower tiles, DMMA;
+// and X = L^-1 by recursive doubling on the 32-blocks (X21 = -X22 (L21 X11), two levels, four DMMA stages) with the unused upper
+// triangle of the block as workspace.  12 + 4 CTA barriers instead of 256.
+constexpr int D2_LD = NB + 4;   // == 4 (mod 16): conflict-free 64-bit DMMA fragment loads in both orientations
+constexpr int D2_ID = 36;       // leading dimension of the inverted 32 x 32 diagonal blocks (same residue)
+constexpr size_t D2_SMEM = (size_t)(NB * D2_LD + 4 * 32 * D2_ID) * sizeof(double);
+
+__global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__restrict__ Akk, long long lda, double *__restrict__ Xkk,
+                                                            long long ldx, int col0, int n_true, int *__restrict__ info) {
+  extern __shared__ __align__(16) double sm2[];
+  double *Ls = sm2;                  // [128][D2_LD]: the block, then its factor (lower); upper blocks: workspace of the inversion
+  double *Dv = sm2 + NB * D2_LD;     // [4][32][D2_ID]: inverses of the diagonal 32 x 32 blocks of the factor
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const int g = l >> 2, c = l & 3;
+  constexpr unsigned FULL = 0xffffffffu;
+  if (*reinterpret_cast<const volatile int *>(info) != 0) return;  // an earlier block already failed: nothing left to factor
+  DIAG_STAMP(0);
+
+  for (int e = tid; e < NB * NB / 2; e += DT) {  // 16-byte chunks; the strict upper triangle is never read from memory
+    const int r = e >> 6, cc = (e & 63) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (cc <= r) {
+      v = *reinterpret_cast<const double2 *>(Akk + (long long)r * lda + cc);
+      if (cc + 1 > r) v.y = 0.0;
+    }
+    *reinterpret_cast<double2 *>(Ls + r * D2_LD + cc) = v;
+  }
+  __syncthreads();
+  DIAG_STAMP(1);
+
+  // ---------------- phase 1: Cholesky, four panels of 32 columns ----------------
+#pragma unroll 1
+  for (int p = 0; p < 4; ++p) {
+    const int r0 = 32 * p;
+    double *Dp = Dv + p * 32 * D2_ID;
+    if (w == 0) {
+      // (a) lane l owns row l of the diagonal block
+      double v[32];
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) v[cc] = Ls[(r0 + l) * D2_LD + r0 + cc];
+      double myrs = 0.0;
+      double d = __shfl_sync(FULL, v[0], 0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (!(d > 0.0)) {  // also catches NaN
+          if (l == 0 && col0 + r0 + j < n_true) atomicCAS(info, 0, col0 + r0 + j + 1);
+        }
+        const double rs = rsqrt(d);
+        double lij = (l == j) ? d * rs : v[j] * rs;  // final L[l][j]
+        if (l < j) lij = 0.0;
+        v[j] = lij;
+        if (l == j) myrs = rs;
+        if (j < 31) {
+          // the next pivot first: its own lane needs no shuffle for the update of its diagonal element
+          const double dn = fma(-lij, lij, v[j + 1]);
+          d = __shfl_sync(FULL, dn, j + 1);
+        }
+#pragma unroll
+        for (int cc = j + 1; cc < 32; ++cc) v[cc] = fma(-lij, __shfl_sync(FULL, lij, cc), v[cc]);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) Ls[(r0 + l) * D2_LD + r0 + cc] = (cc <= l) ? v[cc] : 0.0;
+      __syncwarp();
+      // inverse of the diagonal block: lane l owns column l, forward substitution (rows above l stay zero)
+      double x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = (i == l) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        x[k] *= __shfl_sync(FULL, myrs, k);
+#pragma unroll
+        for (int i = k + 1; i < 32; ++i) x[i] = fma(-Ls[(r0 + i) * D2_LD + r0 + k], x[k], x[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) Dp[i * D2_ID + l] = x[i];
+    }
+    __syncthreads();
+    if (p == 0) DIAG_STAMP(5);
+    const int m = NB - r0 - 32;  // rows below the diagonal block
+    if (m > 0) {
+      // (b) panel: rows i0 .. i0+7 of  A[:, r0:r0+32] * inv(L_D)'   (inv(L_D)[n][k] = 0 for k > n)
+      for (int s = w; s < m / 8; s += DT / 32) {
+        const int i0 = r0 + 32 + 8 * s;
+        double acc[4][2] = {};
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const double a = Ls[(i0 + g) * D2_LD + r0 + kk * 4 + c];
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni)
+            if (kk <= 2 * ni + 1) dmma(acc[ni][0], acc[ni][1], a, Dp[(ni * 8 + g) * D2_ID + kk * 4 + c]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          *reinterpret_cast<double2 *>(Ls + (i0 + g) * D2_LD + r0 + ni * 8 + 2 * c) = make_double2(acc[ni][0], acc[ni][1]);
+      }
+      __syncthreads();
+      // (c) trailing update on the lower 8 x 8 tiles of the m x m block
+      const int T = m / 8, ntile = T * (T + 1) / 2;
+      for (int t = w; t < ntile; t += DT / 32) {
+        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while (ti * (ti + 1) / 2 > t) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        const int i0 = r0 + 32 + 8 * ti, j0 = r0 + 32 + 8 * tj;
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          dmma(d0, d1, Ls[(i0 + g) * D2_LD + r0 + kk * 4 + c], Ls[(j0 + g) * D2_LD + r0 + kk * 4 + c]);
+        double2 *dst = reinterpret_cast<double2 *>(Ls + (i0 + g) * D2_LD + j0 + 2 * c);
+        double2 old = *dst;
+        old.x -= d0;
+        old.y -= d1;
+        *dst = old;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---------------- phase 2: X = L^-1 by recursive doubling on the 32-blocks ----------------
+  DIAG_STAMP(2);
+  // level A: X[1][0] = -D1 (L[1][0] D0),  X[3][2] = -D3 (L[3][2] D2)   (D_b = inverse of diagonal block b)
+  {
+    const int q = w >> 3;                    // pair 0: blocks (0,1), pair 1: blocks (2,3)
+    const int lo = 2 * q, hi = 2 * q + 1;
+    const double *Dlo = Dv + lo * 32 * D2_ID, *Dhi = Dv + hi * 32 * D2_ID;
+    double *Wq = Ls + (32 * q) * D2_LD + 64;           // T of this pair: rows 32q.., columns 64..95 (upper workspace)
+    double *Xq = Ls + (64 * q) * D2_LD + 64 * q + 32;  // X[hi][lo]: block (0,1) resp. (2,3) of the upper workspace
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {            // T = L[hi][lo] * Dlo, Dlo[k][j] = 0 for k < j
+      const int t = (w & 7) * 2 + u, ti = t >> 2, tj = t & 3;
+      double d0 = 0.0, d1 = 0.0;
+      for (int kk = 2 * tj; kk < 8; ++kk)
+        dmma(d0, d1, Ls[(32 * hi + 8 * ti + g) * D2_LD + 32 * lo + kk * 4 + c], Dlo[(kk * 4 + c) * D2_ID + 8 * tj + g]);
+      *reinterpret_cast<double2 *>(Wq + (8 * ti + g) * D2_LD + 8 * tj + 2 * c) = make_double2(d0, d1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {            // X[hi][lo] = -Dhi * T, Dhi[i][k] = 0 for k > i
+      const int t = (w & 7) * 2 + u, ti = t >> 2, tj = t & 3;
+      double d0 = 0.0, d1 = 0.0;
+      for (int kk = 0; kk <= 2 * ti + 1; ++kk)
+        dmma(d0, d1, Dhi[(8 * ti + g) * D2_ID + kk * 4 + c], Wq[(kk * 4 + c) * D2_LD + 8 * tj + g]);
+      *reinterpret_cast<double2 *>(Xq + (8 * ti + g) * D2_LD + 8 * tj + 2 * c) = make_double2(-d0, -d1);
+    }
+    __syncthreads();
+  }
+  // level B: X21 = -X22 (L21 X11) on the 64-blocks; X11 = [[D0, 0], [X10, D1]], X22 = [[D2, 0], [X32, D3]]
+  double *Wb = Ls + 64;                      // T: rows 0..63, columns 64..127 of the upper workspace
+  {
+    const int a4 = w & 3, tib = (w >> 2) * 2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {            // T = L21 * X11: column tiles a4 and 7 - a4 (balanced k ranges), two row tiles
+      const int ti = tib + (u & 1), tj = (u & 2) ? 7 - a4 : a4;
+      double d0 = 0.0, d1 = 0.0;
+      for (int kk = 2 * tj; kk < 16; ++kk) {
+        const double *bp;
+        if (kk < 8)
+          bp = Dv + (kk * 4 + c) * D2_ID + 8 * tj + g;                                   // D0 (tj < 4 here)
+        else if (tj < 4)
+          bp = Ls + (kk * 4 - 32 + c) * D2_LD + 32 + 8 * tj + g;                         // X10
+        else
+          bp = Dv + 32 * D2_ID + (kk * 4 - 32 + c) * D2_ID + 8 * tj - 32 + g;            // D1
+        dmma(d0, d1, Ls[(64 + 8 * ti + g) * D2_LD + kk * 4 + c], *bp);
+      }
+      *reinterpret_cast<double2 *>(Wb + (8 * ti + g) * D2_LD + 8 * tj + 2 * c) = make_double2(d0, d1);
+    }
+  }
+  __syncthreads();
+  {
+    const int a4 = w & 3, tjb = (w >> 2) * 2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {            // X21 = -X22 * T: row tiles a4 and 7 - a4, two column tiles; straight to global memory
+      const int tj = tjb + (u & 1), ti = (u & 2) ? 7 - a4 : a4;
+      double d0 = 0.0, d1 = 0.0;
+      for (int kk = 0; kk <= 2 * ti + 1; ++kk) {
+        const double *ap;
+        if (ti < 4)
+          ap = Dv + 2 * 32 * D2_ID + (8 * ti + g) * D2_ID + kk * 4 + c;                  // D2 (kk < 8 here)
+        else if (kk < 8)
+          ap = Ls + (64 + 8 * ti - 32 + g) * D2_LD + 96 + kk * 4 + c;                    // X32
+        else
+          ap = Dv + 3 * 32 * D2_ID + (8 * ti - 32 + g) * D2_ID + kk * 4 - 32 + c;        // D3
+        dmma(d0, d1, *ap, Wb[(kk * 4 + c) * D2_LD + 8 * tj + g]);
+      }
+      *reinterpret_cast<double2 *>(Xkk + (long long)(64 + 8 * ti + g) * ldx + 8 * tj + 2 * c) = make_double2(-d0, -d1);
+    }
+  }
+  // the rest of X: the four inverted diagonal blocks, X10, X32, zeros elsewhere (rows 64.., columns 0..63 were written above)
+  DIAG_STAMP(3);
+  for (int e = tid; e < NB * NB / 2; e += DT) {
+    const int r = e >> 6, cc = (e & 63) * 2;
+    if (r >= 64 && cc < 64) continue;
+    const int rb = r >> 5, cb = cc >> 5;
+    double2 v = make_double2(0.0, 0.0);
+    if (rb == cb)
+      v = *reinterpret_cast<const double2 *>(Dv + rb * 32 * D2_ID + (r & 31) * D2_ID + (cc & 31));
+    else if (rb == cb + 1 && (rb & 1))
+      v = *reinterpret_cast<const double2 *>(Ls + (r - 32) * D2_LD + 32 + cc);
+    *reinterpret_cast<double2 *>(Xkk + (long long)r * ldx + cc) = v;
+  }
+  DIAG_STAMP(4);
+}
+
 __global__ void pad_identity_kernel(double *__restrict__ C, long long n, long long npad) {
   const long long r = n + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < npad) C[r * npad + r] = 1.0;
@@ -530,6 +742,8 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   }
   const size_t dsmem = (size_t)NB * DLD * sizeof(double);
   GDCA_CUDA(ctx, cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+  GDCA_CUDA(ctx, cudaFuncSetAttribute(diag_block_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D2_SMEM));
+  const bool diag2 = ctx->diag_blocked != 0;
   auto blk = [&](double *base, int I, int Jb) { return base + ((long long)I * NB) * np + (long long)Jb * NB; };
   constexpr int OB = 4;  // 128-blocks per outer block of the factorisation
   // SHARED FACTORISATION (device group, n >= share_min_nb * 128: the bulk trailing updates outweigh the serial chain).
@@ -570,7 +784,10 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
     const int Kend = (K0 + OB < nb) ? K0 + OB : nb;
     bool sp_pending = false;  // work of this outer block is still queued on the panel stream
     for (int k = K0; k < Kend; ++k) {
-      diag_block_kernel<<<1, DT, dsmem, sA>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
+      if (diag2)
+        diag_block_kernel2<<<1, DT, D2_SMEM, sA>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
+      else
+        diag_block_kernel<<<1, DT, dsmem, sA>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
       GDCA_LAUNCH_CHECK(ctx);
       const int rem = nb - k - 1;
       if (rem == 0) break;

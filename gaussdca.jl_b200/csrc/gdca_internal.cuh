@@ -24,6 +24,7 @@ struct gdca_ctx {
   cudaStream_t stream3 = nullptr;  // panel stream of the Cholesky: rest of the panel + inner updates, beside the diagonal chain
   cudaEvent_t ev_fact = nullptr, ev_trail = nullptr;  // look-ahead hand-shakes
   cudaEvent_t ev_diag = nullptr, ev_p1 = nullptr, ev_u2a = nullptr, ev_u2b = nullptr;  // inner look-ahead hand-shakes
+  int diag_blocked = 1;            // env GDCA_DIAG_BLOCKED=0: the rank-1 diagonal-block kernel of round 1 (256 CTA barriers per block)
   int chol_inner_lookahead = 1;    // env GDCA_CHOL_LOOKAHEAD=0: serial inner steps (round-1 first version)
   std::string err;
   int32_t shard_rank = 0, shard_world = 1;

@@ -621,7 +621,7 @@ int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &
   P.batch = batch;
   P.flags = flags;
   P.beta = beta;
-  P.tiles_per_cta = tiles_per_cta;
+  P.tiles_per_cta = tiles_per_cta > 0 ? tiles_per_cta : 0;
   P.alpha = alpha;
   P.info = ctx->leader ? ctx->leader->dInfo : ctx->dInfo;  // a group member watches the leader's factorisation
   P.n_off = sh ? sh->n_off : 0;
@@ -638,7 +638,10 @@ int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &
   P.tri = ((flags & GDCA_OZ_LOWER_OUT) && batch == 1 && m == n && !(flags & GDCA_OZ_KBEG_N) && P.m_off == 0 && P.col_mod <= 1) ? 1 : 0;
   const long long total = P.tri ? (long long)(m / BM) * (m / BM + 1) : (long long)batch * (m / BM) * (n / BN);
   P.total = (int)total;
-  long long grid = tiles_per_cta > 0 ? (total + tiles_per_cta - 1) / tiles_per_cta : (total < ctx->num_sms ? total : ctx->num_sms);
+  // tiles_per_cta > 0: short CTAs of that many tiles; 0: one persistent CTA per SM; < 0: a persistent grid of only -tiles_per_cta
+  // CTAs -- the other SMs stay free for whatever runs beside this launch (the chain of the factorisation beside its bulk update)
+  const long long pers = tiles_per_cta < 0 ? (long long)-tiles_per_cta : (long long)ctx->num_sms;
+  long long grid = tiles_per_cta > 0 ? (total + tiles_per_cta - 1) / tiles_per_cta : (total < pers ? total : pers);
   if (!ctx->oz_attr_set) {  // per device
     GDCA_CUDA(ctx, cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
     ctx->oz_attr_set = true;

@@ -23,7 +23,18 @@ int main() {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("diag_block_kernel: %.1f us per launch (100 back-to-back)\n", ms * 10);
   }
+  cudaFuncSetAttribute(diag_block_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D2_SMEM);
   long long clk[8]; cudaMemcpyFromSymbol(clk, g_diag_clk, sizeof clk);
+  printf("v1 cycles: load %lld  phase1 %lld  phase2 %lld  store %lld\n", clk[1]-clk[0], clk[2]-clk[1], clk[3]-clk[2], clk[4]-clk[3]);
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    for (int i = 0; i < 100; ++i) diag_block_kernel2<<<1, DT, D2_SMEM>>>(dA, n, dX, n, 0, n, dInfo);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("diag_block_kernel2: %.1f us per launch (100 back-to-back)\n", ms * 10);
+  }
+  cudaMemcpyFromSymbol(clk, g_diag_clk, sizeof clk);
+  printf("v2 first 32x32 block (factor + inverse): %lld cycles\n", clk[5]-clk[1]);
   printf("cycles: load %lld  phase1 %lld  phase2 %lld  store %lld\n", clk[1]-clk[0], clk[2]-clk[1], clk[3]-clk[2], clk[4]-clk[3]);
   cudaMemcpy(X.data(), dX, n*n*8, cudaMemcpyDeviceToHost);
   // check: X * A * X' == I  (X = L^-1)
