@@ -246,8 +246,10 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
     if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_CHOL_LOOKAHEAD")) ctx->chol_inner_lookahead = atoi(env) != 0;
   if (const char *env = getenv("GDCA_DIAG_BLOCKED")) ctx->diag_blocked = atoi(env) != 0;
+  if (const char *env = getenv("GDCA_INV_GRAPH")) ctx->inv_graph_mode = atoi(env) != 0;
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fact, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_trail_a, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_sliced, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_group, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_p1b, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
@@ -313,6 +315,7 @@ void gdca_destroy(gdca_ctx *ctx) {
   for (void *m : ctx->peer_opened)
     if (m) cudaIpcCloseMemHandle(m);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  gdca_k_inverse_release(ctx);
   gdca_h2d_release(ctx);
   if (!ctx->dZ_borrowed) cudaFree(ctx->dZ);
   void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPerm, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
@@ -329,6 +332,7 @@ void gdca_destroy(gdca_ctx *ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->ev_fact) cudaEventDestroy(ctx->ev_fact);
   if (ctx->ev_trail) cudaEventDestroy(ctx->ev_trail);
+  if (ctx->ev_trail_a) cudaEventDestroy(ctx->ev_trail_a);
   if (ctx->ev_sliced) cudaEventDestroy(ctx->ev_sliced);
   if (ctx->ev_group) cudaEventDestroy(ctx->ev_group);
   if (ctx->ev_p1b) cudaEventDestroy(ctx->ev_p1b);

@@ -14,6 +14,7 @@
 // cases: inv([[C,0],[0,I]]) = [[inv(C),0],[0,I]].  All matrices are row-major with ld = npad.
 // A non-positive pivot records the 1-based order of the failing leading minor (PosDefException.info).
 #include <algorithm>
+#include <string.h>
 
 #include "gdca_internal.cuh"
 
@@ -421,37 +422,57 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel(const double *__restr
 // Same contract as diag_block_kernel: A[k,k] (lower) -> inv(chol(A[k,k])) written to X[k,k] (lower, zeros above); a non-positive
 // pivot records the order of the failing leading minor.  Same arithmetic per element (rs = rsqrt(pivot), L_jj = pivot * rs,
 // L_ij = a_ij * rs, right-looking updates), different schedule: instead of 128 + 128 barrier-separated rank-1 steps of the whole
-// CTA (70 us), the block is factorised in four 32-column panels held in shared memory:
-//   (a) the 32 x 32 diagonal block: ONE warp, a row per lane in registers, pivots and multipliers by shuffle, no barrier;
-//       its inverse right behind it (a column per lane, forward substitution with broadcast reads of the factor);
+// CTA (68 us), the block is factorised in four 32-column panels held in shared memory:
+//   (a) the 32 x 32 diagonal block: warp 0 owns it, a row per lane in registers.  The serial chain per column is
+//       pivot -> rsqrt -> multiplier -> next pivot (one shuffle); the finished column goes to shared memory, the rank-1 update
+//       reads it back as broadcast words.  Warp 1 follows one column behind (a flag in shared memory, no barrier) and builds the
+//       INVERSE of the block by forward substitution, a column per lane, off the chain;
 //   (b) the rows below: L = A * inv(L_D)' as DMMA strips of 8 rows (a warp owns its strip: in place);
-//   (c) the trailing block: A -= L L' on the 8 x 8 lower tiles, DMMA;
-// and X = L^-1 by recursive doubling on the 32-blocks (X21 = -X22 (L21 X11), two levels, four DMMA stages) with the unused upper
-// triangle of the block as workspace.  12 + 4 CTA barriers instead of 256.
+//   (c) the trailing block: A -= L L' on the 8 x 8 lower tiles, DMMA, three tiles in flight per warp;
+// and X = L^-1 by recursive doubling on the 32-blocks (X21 = -X22 (L21 X11), two levels, four DMMA stages, independent
+// accumulator chains interleaved) with the unused upper triangle of the block as workspace.  The first 32 rows are loaded
+// first: the other warps fetch the rest of the block while warps 0 and 1 already factorise.  16 CTA barriers instead of 256.
 constexpr int D2_LD = NB + 4;   // == 4 (mod 16): conflict-free 64-bit DMMA fragment loads in both orientations
 constexpr int D2_ID = 36;       // leading dimension of the inverted 32 x 32 diagonal blocks (same residue)
-constexpr size_t D2_SMEM = (size_t)(NB * D2_LD + 4 * 32 * D2_ID) * sizeof(double);
+constexpr size_t D2_SMEM = (size_t)(NB * D2_LD + 4 * 32 * D2_ID + 32 * 32 + 32) * sizeof(double);
 
 __global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__restrict__ Akk, long long lda, double *__restrict__ Xkk,
                                                             long long ldx, int col0, int n_true, int *__restrict__ info) {
   extern __shared__ __align__(16) double sm2[];
-  double *Ls = sm2;                  // [128][D2_LD]: the block, then its factor (lower); upper blocks: workspace of the inversion
-  double *Dv = sm2 + NB * D2_LD;     // [4][32][D2_ID]: inverses of the diagonal 32 x 32 blocks of the factor
+  double *Ls = sm2;                       // [128][D2_LD]: the block, then its factor (lower); upper blocks: workspace of the inversion
+  double *Dv = sm2 + NB * D2_LD;          // [4][32][D2_ID]: inverses of the diagonal 32 x 32 blocks of the factor
+  double *Lc = Dv + 4 * 32 * D2_ID;       // [32 columns][32 rows]: the diagonal block's factor, column by column as it is finished
+  double *rsd = Lc + 32 * 32;             // [32] 1 / L[j][j]
+  __shared__ int s_ready;                 // columns of Lc published by warp 0
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   const int g = l >> 2, c = l & 3;
   constexpr unsigned FULL = 0xffffffffu;
   if (*reinterpret_cast<const volatile int *>(info) != 0) return;  // an earlier block already failed: nothing left to factor
   DIAG_STAMP(0);
 
-  for (int e = tid; e < NB * NB / 2; e += DT) {  // 16-byte chunks; the strict upper triangle is never read from memory
-    const int r = e >> 6, cc = (e & 63) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (cc <= r) {
-      v = *reinterpret_cast<const double2 *>(Akk + (long long)r * lda + cc);
-      if (cc + 1 > r) v.y = 0.0;
+  // rows r0 .. r1-1 of the block into shared memory: 16-byte chunks, all loads of a thread in flight before its first store;
+  // the strict upper triangle is never read from memory
+  auto load_rows = [&](int rbeg, int rend, int t0, int nthr) {
+    for (int e0 = rbeg * 64 + t0; e0 < rend * 64; e0 += 4 * nthr) {
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nthr, r = e >> 6, cc = (e & 63) * 2;
+        v[u] = make_double2(0.0, 0.0);
+        if (e < rend * 64 && cc <= r) v[u] = *reinterpret_cast<const double2 *>(Akk + (long long)r * lda + cc);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nthr, r = e >> 6, cc = (e & 63) * 2;
+        if (e < rend * 64) {
+          if (cc + 1 > r) v[u].y = 0.0;
+          *reinterpret_cast<double2 *>(Ls + r * D2_LD + cc) = v[u];
+        }
+      }
     }
-    *reinterpret_cast<double2 *>(Ls + r * D2_LD + cc) = v;
-  }
+  };
+  load_rows(0, 32, tid, DT);
+  if (tid == 0) s_ready = 0;
   __syncthreads();
   DIAG_STAMP(1);
 
@@ -461,11 +482,10 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__rest
     const int r0 = 32 * p;
     double *Dp = Dv + p * 32 * D2_ID;
     if (w == 0) {
-      // (a) lane l owns row l of the diagonal block
+      // (a) factor: lane l owns row l of the diagonal block
       double v[32];
 #pragma unroll
       for (int cc = 0; cc < 32; ++cc) v[cc] = Ls[(r0 + l) * D2_LD + r0 + cc];
-      double myrs = 0.0;
       double d = __shfl_sync(FULL, v[0], 0);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -475,33 +495,51 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__rest
         const double rs = rsqrt(d);
         double lij = (l == j) ? d * rs : v[j] * rs;  // final L[l][j]
         if (l < j) lij = 0.0;
-        v[j] = lij;
-        if (l == j) myrs = rs;
         if (j < 31) {
-          // the next pivot first: its own lane needs no shuffle for the update of its diagonal element
+          // the next pivot: its own lane needs nobody else's multiplier for the update of its diagonal element
           const double dn = fma(-lij, lij, v[j + 1]);
           d = __shfl_sync(FULL, dn, j + 1);
         }
+        Lc[j * 32 + l] = lij;
+        if (l == j) rsd[j] = rs;
+        __syncwarp();
+        if (l == 0) {
+          __threadfence_block();
+          *reinterpret_cast<volatile int *>(&s_ready) = j + 1;
+        }
+        // rank-1 update of the columns to the right, multipliers read back as broadcast pairs
 #pragma unroll
-        for (int cc = j + 1; cc < 32; ++cc) v[cc] = fma(-lij, __shfl_sync(FULL, lij, cc), v[cc]);
+        for (int cc = (j + 1) & ~1; cc < 32; cc += 2) {
+          const double2 lc = *reinterpret_cast<const double2 *>(Lc + j * 32 + cc);
+          if (cc > j) v[cc] = fma(-lij, lc.x, v[cc]);
+          v[cc + 1] = fma(-lij, lc.y, v[cc + 1]);
+        }
       }
-#pragma unroll
-      for (int cc = 0; cc < 32; ++cc) Ls[(r0 + l) * D2_LD + r0 + cc] = (cc <= l) ? v[cc] : 0.0;
-      __syncwarp();
-      // inverse of the diagonal block: lane l owns column l, forward substitution (rows above l stay zero)
+    } else if (w == 1) {
+      // (a') inverse of the diagonal block, one column behind the factor: lane l owns column l, forward substitution
       double x[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = (i == l) ? 1.0 : 0.0;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        x[k] *= __shfl_sync(FULL, myrs, k);
+        while (*reinterpret_cast<volatile int *>(&s_ready) <= k) {
+        }
+        __threadfence_block();
+        x[k] *= rsd[k];
 #pragma unroll
-        for (int i = k + 1; i < 32; ++i) x[i] = fma(-Ls[(r0 + i) * D2_LD + r0 + k], x[k], x[i]);
+        for (int i = (k + 1) & ~1; i < 32; i += 2) {
+          const double2 li = *reinterpret_cast<const double2 *>(Lc + k * 32 + i);
+          if (i > k) x[i] = fma(-li.x, x[k], x[i]);
+          x[i + 1] = fma(-li.y, x[k], x[i + 1]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) Dp[i * D2_ID + l] = x[i];
+    } else if (p == 0) {
+      load_rows(32, NB, tid - 64, DT - 64);  // the rest of the block arrives while the first diagonal block is factorised
     }
     __syncthreads();
+    if (tid == 0) s_ready = 0;  // (nobody reads it before the next barrier)
     if (p == 0) DIAG_STAMP(5);
     const int m = NB - r0 - 32;  // rows below the diagonal block
     if (m > 0) {
@@ -522,30 +560,43 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__rest
           *reinterpret_cast<double2 *>(Ls + (i0 + g) * D2_LD + r0 + ni * 8 + 2 * c) = make_double2(acc[ni][0], acc[ni][1]);
       }
       __syncthreads();
-      // (c) trailing update on the lower 8 x 8 tiles of the m x m block
+      // (c) trailing update on the lower 8 x 8 tiles of the m x m block, three independent tiles per round and warp
       const int T = m / 8, ntile = T * (T + 1) / 2;
-      for (int t = w; t < ntile; t += DT / 32) {
-        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-        while (ti * (ti + 1) / 2 > t) --ti;
-        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-        const int tj = t - ti * (ti + 1) / 2;
-        const int i0 = r0 + 32 + 8 * ti, j0 = r0 + 32 + 8 * tj;
-        double d0 = 0.0, d1 = 0.0;
+      for (int tb = 3 * w; tb < ntile; tb += 3 * (DT / 32)) {
+        int i0[3], j0[3];
+        double d0[3] = {}, d1[3] = {};
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          dmma(d0, d1, Ls[(i0 + g) * D2_LD + r0 + kk * 4 + c], Ls[(j0 + g) * D2_LD + r0 + kk * 4 + c]);
-        double2 *dst = reinterpret_cast<double2 *>(Ls + (i0 + g) * D2_LD + j0 + 2 * c);
-        double2 old = *dst;
-        old.x -= d0;
-        old.y -= d1;
-        *dst = old;
+        for (int u = 0; u < 3; ++u) {
+          const int t = min(tb + u, ntile - 1);
+          int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+          while (ti * (ti + 1) / 2 > t) --ti;
+          while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+          i0[u] = r0 + 32 + 8 * ti;
+          j0[u] = r0 + 32 + 8 * (t - ti * (ti + 1) / 2);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+          for (int u = 0; u < 3; ++u)
+            dmma(d0[u], d1[u], Ls[(i0[u] + g) * D2_LD + r0 + kk * 4 + c], Ls[(j0[u] + g) * D2_LD + r0 + kk * 4 + c]);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          if (tb + u < ntile) {
+            double2 *dst = reinterpret_cast<double2 *>(Ls + (i0[u] + g) * D2_LD + j0[u] + 2 * c);
+            double2 old = *dst;
+            old.x -= d0[u];
+            old.y -= d1[u];
+            *dst = old;
+          }
+        }
       }
       __syncthreads();
     }
   }
+  DIAG_STAMP(2);
 
   // ---------------- phase 2: X = L^-1 by recursive doubling on the 32-blocks ----------------
-  DIAG_STAMP(2);
   // level A: X[1][0] = -D1 (L[1][0] D0),  X[3][2] = -D3 (L[3][2] D2)   (D_b = inverse of diagonal block b)
   {
     const int q = w >> 3;                    // pair 0: blocks (0,1), pair 1: blocks (2,3)
@@ -553,68 +604,88 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__rest
     const double *Dlo = Dv + lo * 32 * D2_ID, *Dhi = Dv + hi * 32 * D2_ID;
     double *Wq = Ls + (32 * q) * D2_LD + 64;           // T of this pair: rows 32q.., columns 64..95 (upper workspace)
     double *Xq = Ls + (64 * q) * D2_LD + 64 * q + 32;  // X[hi][lo]: block (0,1) resp. (2,3) of the upper workspace
+    const int ti = (w & 7) >> 1, tj0 = 2 * (w & 1);    // this warp's two tiles: (ti, tj0) and (ti, tj0 + 1), one A fragment
+    {
+      // T = L[hi][lo] * Dlo, Dlo[k][j] = 0 for k < j
+      double d[2][2] = {};
+      for (int kk = 2 * tj0; kk < 8; ++kk) {
+        const double a = Ls[(32 * hi + 8 * ti + g) * D2_LD + 32 * lo + kk * 4 + c];
+        dmma(d[0][0], d[0][1], a, Dlo[(kk * 4 + c) * D2_ID + 8 * tj0 + g]);
+        if (kk >= 2 * tj0 + 2) dmma(d[1][0], d[1][1], a, Dlo[(kk * 4 + c) * D2_ID + 8 * tj0 + 8 + g]);
+      }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {            // T = L[hi][lo] * Dlo, Dlo[k][j] = 0 for k < j
-      const int t = (w & 7) * 2 + u, ti = t >> 2, tj = t & 3;
-      double d0 = 0.0, d1 = 0.0;
-      for (int kk = 2 * tj; kk < 8; ++kk)
-        dmma(d0, d1, Ls[(32 * hi + 8 * ti + g) * D2_LD + 32 * lo + kk * 4 + c], Dlo[(kk * 4 + c) * D2_ID + 8 * tj + g]);
-      *reinterpret_cast<double2 *>(Wq + (8 * ti + g) * D2_LD + 8 * tj + 2 * c) = make_double2(d0, d1);
+      for (int u = 0; u < 2; ++u)
+        *reinterpret_cast<double2 *>(Wq + (8 * ti + g) * D2_LD + 8 * (tj0 + u) + 2 * c) = make_double2(d[u][0], d[u][1]);
     }
     __syncthreads();
+    {
+      // X[hi][lo] = -Dhi * T, Dhi[i][k] = 0 for k > i
+      double d[2][2] = {};
+      for (int kk = 0; kk <= 2 * ti + 1; ++kk) {
+        const double a = Dhi[(8 * ti + g) * D2_ID + kk * 4 + c];
+        dmma(d[0][0], d[0][1], a, Wq[(kk * 4 + c) * D2_LD + 8 * tj0 + g]);
+        dmma(d[1][0], d[1][1], a, Wq[(kk * 4 + c) * D2_LD + 8 * tj0 + 8 + g]);
+      }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {            // X[hi][lo] = -Dhi * T, Dhi[i][k] = 0 for k > i
-      const int t = (w & 7) * 2 + u, ti = t >> 2, tj = t & 3;
-      double d0 = 0.0, d1 = 0.0;
-      for (int kk = 0; kk <= 2 * ti + 1; ++kk)
-        dmma(d0, d1, Dhi[(8 * ti + g) * D2_ID + kk * 4 + c], Wq[(kk * 4 + c) * D2_LD + 8 * tj + g]);
-      *reinterpret_cast<double2 *>(Xq + (8 * ti + g) * D2_LD + 8 * tj + 2 * c) = make_double2(-d0, -d1);
+      for (int u = 0; u < 2; ++u)
+        *reinterpret_cast<double2 *>(Xq + (8 * ti + g) * D2_LD + 8 * (tj0 + u) + 2 * c) = make_double2(-d[u][0], -d[u][1]);
     }
     __syncthreads();
   }
   // level B: X21 = -X22 (L21 X11) on the 64-blocks; X11 = [[D0, 0], [X10, D1]], X22 = [[D2, 0], [X32, D3]]
   double *Wb = Ls + 64;                      // T: rows 0..63, columns 64..127 of the upper workspace
   {
+    // T = L21 * X11: column tiles a4 and 7 - a4 (balanced k ranges), two row tiles each; four accumulator chains in flight
     const int a4 = w & 3, tib = (w >> 2) * 2;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {            // T = L21 * X11: column tiles a4 and 7 - a4 (balanced k ranges), two row tiles
-      const int ti = tib + (u & 1), tj = (u & 2) ? 7 - a4 : a4;
-      double d0 = 0.0, d1 = 0.0;
-      for (int kk = 2 * tj; kk < 16; ++kk) {
-        const double *bp;
-        if (kk < 8)
-          bp = Dv + (kk * 4 + c) * D2_ID + 8 * tj + g;                                   // D0 (tj < 4 here)
-        else if (tj < 4)
-          bp = Ls + (kk * 4 - 32 + c) * D2_LD + 32 + 8 * tj + g;                         // X10
-        else
-          bp = Dv + 32 * D2_ID + (kk * 4 - 32 + c) * D2_ID + 8 * tj - 32 + g;            // D1
-        dmma(d0, d1, Ls[(64 + 8 * ti + g) * D2_LD + kk * 4 + c], *bp);
+    const int tjA = a4, tjB = 7 - a4;
+    double d[4][2] = {};
+    for (int kk = 2 * tjA; kk < 16; ++kk) {
+      const double a0 = Ls[(64 + 8 * tib + g) * D2_LD + kk * 4 + c], a1 = Ls[(64 + 8 * tib + 8 + g) * D2_LD + kk * 4 + c];
+      {
+        const double *bp = (kk < 8) ? Dv + (kk * 4 + c) * D2_ID + 8 * tjA + g                 // D0
+                                    : Ls + (kk * 4 - 32 + c) * D2_LD + 32 + 8 * tjA + g;      // X10
+        const double b = *bp;
+        dmma(d[0][0], d[0][1], a0, b);
+        dmma(d[1][0], d[1][1], a1, b);
       }
-      *reinterpret_cast<double2 *>(Wb + (8 * ti + g) * D2_LD + 8 * tj + 2 * c) = make_double2(d0, d1);
+      if (kk >= 2 * tjB) {  // tjB >= 4: k >= 32, the D1 block
+        const double b = Dv[32 * D2_ID + (kk * 4 - 32 + c) * D2_ID + 8 * tjB - 32 + g];
+        dmma(d[2][0], d[2][1], a0, b);
+        dmma(d[3][0], d[3][1], a1, b);
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<double2 *>(Wb + (8 * (tib + (u & 1)) + g) * D2_LD + 8 * ((u & 2) ? tjB : tjA) + 2 * c) = make_double2(d[u][0], d[u][1]);
   }
   __syncthreads();
   {
+    // X21 = -X22 * T: row tiles a4 and 7 - a4, two column tiles each; straight to global memory
     const int a4 = w & 3, tjb = (w >> 2) * 2;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {            // X21 = -X22 * T: row tiles a4 and 7 - a4, two column tiles; straight to global memory
-      const int tj = tjb + (u & 1), ti = (u & 2) ? 7 - a4 : a4;
-      double d0 = 0.0, d1 = 0.0;
-      for (int kk = 0; kk <= 2 * ti + 1; ++kk) {
-        const double *ap;
-        if (ti < 4)
-          ap = Dv + 2 * 32 * D2_ID + (8 * ti + g) * D2_ID + kk * 4 + c;                  // D2 (kk < 8 here)
-        else if (kk < 8)
-          ap = Ls + (64 + 8 * ti - 32 + g) * D2_LD + 96 + kk * 4 + c;                    // X32
-        else
-          ap = Dv + 3 * 32 * D2_ID + (8 * ti - 32 + g) * D2_ID + kk * 4 - 32 + c;        // D3
-        dmma(d0, d1, *ap, Wb[(kk * 4 + c) * D2_LD + 8 * tj + g]);
+    const int tiA = a4, tiB = 7 - a4;
+    double d[4][2] = {};
+    for (int kk = 0; kk <= 2 * tiB + 1; ++kk) {
+      const double b0 = Wb[(kk * 4 + c) * D2_LD + 8 * tjb + g], b1 = Wb[(kk * 4 + c) * D2_LD + 8 * tjb + 8 + g];
+      if (kk <= 2 * tiA + 1) {  // tiA < 4: the D2 block
+        const double a = Dv[2 * 32 * D2_ID + (8 * tiA + g) * D2_ID + kk * 4 + c];
+        dmma(d[0][0], d[0][1], a, b0);
+        dmma(d[1][0], d[1][1], a, b1);
       }
-      *reinterpret_cast<double2 *>(Xkk + (long long)(64 + 8 * ti + g) * ldx + 8 * tj + 2 * c) = make_double2(-d0, -d1);
+      {
+        const double *ap = (kk < 8) ? Ls + (64 + 8 * tiB - 32 + g) * D2_LD + 96 + kk * 4 + c                    // X32
+                                    : Dv + 3 * 32 * D2_ID + (8 * tiB - 32 + g) * D2_ID + kk * 4 - 32 + c;       // D3
+        const double a = *ap;
+        dmma(d[2][0], d[2][1], a, b0);
+        dmma(d[3][0], d[3][1], a, b1);
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<double2 *>(Xkk + (long long)(64 + 8 * ((u & 2) ? tiB : tiA) + g) * ldx + 8 * (tjb + (u & 1)) + 2 * c) =
+          make_double2(-d[u][0], -d[u][1]);
   }
-  // the rest of X: the four inverted diagonal blocks, X10, X32, zeros elsewhere (rows 64.., columns 0..63 were written above)
   DIAG_STAMP(3);
+  // the rest of X: the four inverted diagonal blocks, X10, X32, zeros elsewhere (rows 64.., columns 0..63 were written above)
   for (int e = tid; e < NB * NB / 2; e += DT) {
     const int r = e >> 6, cc = (e & 63) * 2;
     if (r >= 64 && cc < 64) continue;
@@ -660,7 +731,7 @@ int32_t gemm(gdca_ctx *ctx, const GemmP &p_in, int batch, cudaStream_t stream = 
   const size_t smem = (size_t)GSTAGES * 2 * TILE_D * sizeof(double);
   GDCA_CUDA(ctx, cudaFuncSetAttribute(dgemm_kernel<AT, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)(p.n / NB), (unsigned)(p.m / NB), (unsigned)batch);
-  dgemm_kernel<AT, BT><<<grid, GTHREADS, smem, stream>>>(p);
+  GDCA_CUDA(ctx, gdca_launch_prio(dgemm_kernel<AT, BT>, grid, dim3(GTHREADS), smem, stream, p));
   GDCA_LAUNCH_CHECK(ctx);
   return GDCA_OK;
 }
@@ -671,15 +742,35 @@ int32_t gemm_small(gdca_ctx *ctx, const GemmP &p_in, cudaStream_t stream) {
   p.info = ctx->leader ? ctx->leader->dInfo : ctx->dInfo;
   const size_t smem = (size_t)(SG_M + NB) * SG_LD * sizeof(double);
   GDCA_CUDA(ctx, cudaFuncSetAttribute(dgemm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dgemm_small_kernel<<<NB / SG_M, 128, smem, stream>>>(p);
+  GDCA_CUDA(ctx, gdca_launch_prio(dgemm_small_kernel, dim3(NB / SG_M), dim3(128), smem, stream, p));
   GDCA_LAUNCH_CHECK(ctx);
   return GDCA_OK;
 }
 
 }  // namespace
 
-int32_t gdca_k_inverse(gdca_ctx *ctx) {
-  if (!ctx->have_cov) return gdca_fail(ctx, GDCA_ERR_STATE, "inverse: covariance not computed");
+// Stream capture of the single-GPU inversion: the ~900 launches, memsets and cross-stream event hand-shakes of one call become
+// two CUDA graphs (factorisation | inversion of the factor + X'X: the timing event between them stays a real event).
+struct InvCapture {
+  gdca_ctx *ctx;
+  cudaGraph_t graph[2] = {nullptr, nullptr};
+  int parts = 0;
+  bool failed = false;
+  // between the factorisation and the inversion: close the first graph, open the second
+  int32_t split() {
+    if (cudaStreamEndCapture(ctx->stream, &graph[0]) != cudaSuccess || !graph[0]) return fail();
+    parts = 1;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) return fail();
+    return GDCA_OK;
+  }
+  int32_t fail() {
+    failed = true;
+    cudaGetLastError();
+    return gdca_fail(ctx, GDCA_ERR_CUDA, "inverse: stream capture failed");
+  }
+};
+
+static int32_t inverse_enqueue(gdca_ctx *ctx, InvCapture *cap) {
   const long long np = ctx->npad, n = ctx->n;
   const int nb = (int)(np / NB);
   GDCA_TRY(gdca_reserve(ctx, ctx->dX, ctx->capX, (size_t)np * np));
@@ -779,15 +870,16 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
   // after OB inner steps one trailing update with K = OB*128 (C tiles read/written n/512 times, not n/128).
   cudaStream_t sA = ctx->stream, sB = ctx->stream2, sP = ctx->stream3;
   bool pending_trail = false;
+  bool prev_split = false;   // the previous bulk update was launched in two parts: the chain only waits for the first (ev_trail_a)
   bool p1b_pending = false;  // the panel stream still updates this outer block's columns below its first diagonal tile
   for (int K0 = 0; K0 < nb; K0 += OB) {
     const int Kend = (K0 + OB < nb) ? K0 + OB : nb;
     bool sp_pending = false;  // work of this outer block is still queued on the panel stream
     for (int k = K0; k < Kend; ++k) {
       if (diag2)
-        diag_block_kernel2<<<1, DT, D2_SMEM, sA>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
+        GDCA_CUDA(ctx, gdca_launch_prio(diag_block_kernel2, dim3(1), dim3(DT), D2_SMEM, sA, (const double *)blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo));
       else
-        diag_block_kernel<<<1, DT, dsmem, sA>>>(blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo);
+        GDCA_CUDA(ctx, gdca_launch_prio(diag_block_kernel, dim3(1), dim3(DT), dsmem, sA, (const double *)blk(A, k, k), np, blk(X, k, k), np, k * NB, (int)n, ctx->dInfo));
       GDCA_LAUNCH_CHECK(ctx);
       const int rem = nb - k - 1;
       if (rem == 0) break;
@@ -905,7 +997,9 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
       //   part 2 (helper stream, low priority): all columns >= Kn, overlapping the next panel's serial chain.
       const int Kn = (Kend + OB < nb) ? Kend + OB : nb;
       GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_fact, sA));          // panel [K0,Kend) is final
-      if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));  // columns >= Kend carry update K0-OB
+      // columns [Kend, Kn) carry the bulk update of panel K0-OB: all of it, or -- when it was launched in two parts -- its first part
+      cudaEvent_t ev_prev = prev_split ? ctx->ev_trail_a : ctx->ev_trail;
+      if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ev_prev, 0));
       if (share && rem < OZ_MIN_REM) {
         // The last few block columns: every owner hands its columns back and the leader finishes alone, on the same engines
         // as a single-GPU run (bit-identical results for every group size).
@@ -940,9 +1034,16 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
         GDCA_TRY(gdca_oz_slice(ctx, sA, blk(A, Kend, K0), np, 0, false, NB, kk, 1, NB, ctx->dDigP, ctx->dScaleP, &Pd));
         GDCA_TRY(gdca_oz_gemm(ctx, sA, Pd, Pd, blk(A, Kend, Kend), np, 0, NB, NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1, 0));
         GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, ctx->ev_fact, 0));
-        if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, ctx->ev_trail, 0));
+        if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sP, ev_prev, 0));
+        // One GPU: the bulk update goes out in two parts -- first the block columns of the outer block after next, which is all the
+        // chain waits for at the next boundary, then the rest -- so the chain never stalls behind a whole bulk update.  The panel
+        // digits alternate between two buffers: the second part of the previous bulk may still be reading the other one (it is
+        // complete once the first part of THIS bulk's predecessor has been waited for: the helper stream runs them in order).
+        const bool split = N == 1;
+        int8_t *pdig = (split && (sidx & 1)) ? ctx->dDigA : ctx->dDigB;
+        double *pscale = (split && (sidx & 1)) ? ctx->dScaleA : ctx->dScaleB;
         gdca_oz_operand P{};
-        GDCA_TRY(gdca_oz_slice(ctx, sP, blk(A, Kend, K0), np, 0, false, rem * NB, kk, 1, rem * NB, ctx->dDigB, ctx->dScaleB, &P));
+        GDCA_TRY(gdca_oz_slice(ctx, sP, blk(A, Kend, K0), np, 0, false, rem * NB, kk, 1, rem * NB, pdig, pscale, &P));
         GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_sliced, sP));
         if (rem > 1) {
           gdca_oz_operand P1 = P;   // rows from block Kend + 1 on
@@ -971,8 +1072,23 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
           cf.col_rank = 0;
           cf.col_unit0 = Kn * (NB / 64);
           cf.col_per = OB * (NB / 64);
-          GDCA_TRY(gdca_oz_gemm(ctx, sB, P2, P2, blk(A, Kn, Kn), np, 0, rem2 * NB, rem2 * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1,
-                                ctx->ozaki_tpc, share ? &cf : nullptr));
+          const int Kn2 = (Kn + OB < nb) ? Kn + OB : nb;
+          const int bulk_tpc = (cap && ctx->ozaki_tpc > 0) ? -(ctx->num_sms - 40) : ctx->ozaki_tpc;  // persistent grid, 40 SMs left to the chain and the panel products (measured: 9.24 ms against 9.85 / 9.99 ms with 16 / 64)
+          if (split && Kn2 < nb) {
+            // part a: block columns [Kn, Kn2) (rows >= Kn); part b: everything from Kn2 on
+            GDCA_TRY(gdca_oz_gemm(ctx, sB, P2, P2, blk(A, Kn, Kn), np, 0, rem2 * NB, (Kn2 - Kn) * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1, bulk_tpc));
+            GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_trail_a, sB));
+            gdca_oz_operand P3 = P2;
+            P3.dig += (long long)(Kn2 - Kn) * NB * P.pitch;
+            P3.scale += (long long)(Kn2 - Kn) * NB;
+            P3.rows_total = P3.rows_b = (long long)(nb - Kn2) * NB;
+            GDCA_TRY(gdca_oz_gemm(ctx, sB, P3, P3, blk(A, Kn2, Kn2), np, 0, (nb - Kn2) * NB, (nb - Kn2) * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1, bulk_tpc));
+            prev_split = true;
+          } else {
+            GDCA_TRY(gdca_oz_gemm(ctx, sB, P2, P2, blk(A, Kn, Kn), np, 0, rem2 * NB, rem2 * NB, kk, 1, GDCA_OZ_LOWER_OUT, -1.0, 1,
+                                  bulk_tpc, share ? &cf : nullptr));
+            prev_split = false;
+          }
           ctx->oz_fp64_flop += 2.0 * (double)kk * NB * NB * (0.5 * (double)rem2 * (rem2 + 1));
           GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_trail, sB));
           pending_trail = true;
@@ -1027,12 +1143,16 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
         GDCA_TRY((gemm<false, false>(ctx, u, 1, sB)));
         GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_trail, sB));
         pending_trail = true;
+        prev_split = false;
       }
     }
   }
   if (pending_trail) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_trail, 0));
   if (p1b_pending) GDCA_CUDA(ctx, cudaStreamWaitEvent(sA, ctx->ev_p1b, 0));
-  if (ctx->ev[GDCA_EV_POTRF]) GDCA_CUDA(ctx, cudaEventRecord(ctx->ev[GDCA_EV_POTRF], sA));
+  if (cap)
+    GDCA_TRY(cap->split());
+  else if (ctx->ev[GDCA_EV_POTRF])
+    GDCA_CUDA(ctx, cudaEventRecord(ctx->ev[GDCA_EV_POTRF], sA));
   for (int r = 1; r < N; ++r) {  // the members' compute streams continue once their copy of the factor is complete
     gdca_ctx *c = grp[r];
     GDCA_TRY(on_dev(c));
@@ -1149,6 +1269,127 @@ int32_t gdca_k_inverse(gdca_ctx *ctx) {
     mirror_lower_kernel<<<dim3(nt, nt), 256, 0, ctx->stream>>>(J, np, np);
     GDCA_LAUNCH_CHECK(ctx);
   }
+  return GDCA_OK;
+}
+
+namespace {
+struct InvGraphKey {
+  long long np, n;
+  int oz, diag_blocked, lookahead, tpc;
+  const void *ptr[12];
+  bool operator==(const InvGraphKey &o) const { return memcmp(this, &o, sizeof *this) == 0; }
+};
+struct InvGraph {
+  InvGraphKey key;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};
+  double int8_ops = 0.0, fp64_flop = 0.0;
+  long long launches = 0;
+  bool ozaki = false;
+};
+void inv_graph_destroy(InvGraph *g) {
+  if (!g) return;
+  for (cudaGraphExec_t e : g->exec)
+    if (e) cudaGraphExecDestroy(e);
+  delete g;
+}
+}  // namespace
+
+void gdca_k_inverse_release(gdca_ctx *ctx) {
+  inv_graph_destroy(static_cast<InvGraph *>(ctx->inv_graph));
+  ctx->inv_graph = nullptr;
+}
+
+int32_t gdca_k_inverse(gdca_ctx *ctx) {
+  if (!ctx->have_cov) return gdca_fail(ctx, GDCA_ERR_STATE, "inverse: covariance not computed");
+  const long long np = ctx->npad;
+  // One GPU: the launch sequence depends only on the shape and on the buffer addresses, so it is captured once and replayed as
+  // two CUDA graphs -- the serial chain of the factorisation (79 x diag -> panel tile -> diagonal update at n = 10 000) is bound by
+  // launch and cross-stream hand-shake latency, which a graph launch takes off the host.  (A device group keeps direct launches.)
+  const bool want_graph = ctx->inv_graph_mode != 0 && ctx->group_size <= 1 && !ctx->leader;
+  bool done = false;
+  if (want_graph) {
+    const bool oz = ctx->ozaki_mode != 0 && np / NB >= 16;
+    // every buffer the captured launches refer to exists (and keeps its address) before the capture starts
+    GDCA_TRY(gdca_reserve(ctx, ctx->dX, ctx->capX, (size_t)np * np));
+    GDCA_TRY(gdca_reserve(ctx, ctx->dT, ctx->capT, (size_t)np * np));
+    GDCA_TRY(gdca_reserve(ctx, ctx->dmJ, ctx->capmJ, (size_t)np * np));
+    if (oz) {
+      GDCA_TRY(gdca_reserve(ctx, ctx->dDigA, ctx->capDigA, (size_t)np * np * 8));
+      GDCA_TRY(gdca_reserve(ctx, ctx->dDigB, ctx->capDigB, (size_t)np * np * 8));
+      GDCA_TRY(gdca_reserve(ctx, ctx->dScaleA, ctx->capScaleA, (size_t)np));
+      GDCA_TRY(gdca_reserve(ctx, ctx->dScaleB, ctx->capScaleB, (size_t)np));
+      GDCA_TRY(gdca_reserve(ctx, ctx->dDigP, ctx->capDigP, (size_t)NB * 8 * 1024));
+      GDCA_TRY(gdca_reserve(ctx, ctx->dScaleP, ctx->capScaleP, (size_t)NB));
+      GDCA_TRY(gdca_reserve(ctx, ctx->dOzMax, ctx->capOzMax, (size_t)np));
+    }
+    InvGraphKey key;
+    memset(&key, 0, sizeof key);
+    key.np = np;
+    key.n = ctx->n;
+    key.oz = oz ? 1 : 0;
+    key.diag_blocked = ctx->diag_blocked;
+    key.lookahead = ctx->chol_inner_lookahead;
+    key.tpc = ctx->ozaki_tpc;
+    const void *ptrs[12] = {ctx->dC, ctx->dX, ctx->dT, ctx->dmJ, ctx->dDigA, ctx->dDigB, ctx->dScaleA, ctx->dScaleB, ctx->dDigP, ctx->dScaleP,
+                            ctx->dOzMax, ctx->dInfo};
+    memcpy(key.ptr, ptrs, sizeof ptrs);
+    InvGraph *g = static_cast<InvGraph *>(ctx->inv_graph);
+    if (g && !(g->key == key)) {
+      inv_graph_destroy(g);
+      g = nullptr;
+      ctx->inv_graph = nullptr;
+    }
+    if (!g) {
+      InvCapture cap;
+      cap.ctx = ctx;
+      const long long launches0 = ctx->launches;
+      int32_t st = GDCA_ERR_CUDA;
+      if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        st = inverse_enqueue(ctx, &cap);
+        cudaGraph_t last = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &last);  // also ends a capture the body left behind on an error
+        if (st == GDCA_OK && e == cudaSuccess && last && cap.parts == 1 && !cap.failed) {
+          cap.graph[1] = last;
+          g = new InvGraph();
+          g->key = key;
+          g->int8_ops = ctx->oz_int8_ops;
+          g->fp64_flop = ctx->oz_fp64_flop;
+          g->ozaki = ctx->last_inverse_ozaki;
+          g->launches = ctx->launches - launches0;
+          for (int i = 0; i < 2 && g; ++i)
+            if (cudaGraphInstantiate(&g->exec[i], cap.graph[i], 0) != cudaSuccess) {
+              inv_graph_destroy(g);
+              g = nullptr;
+            }
+        } else if (last) {
+          cudaGraphDestroy(last);
+          last = nullptr;
+        }
+        for (cudaGraph_t &gr : cap.graph)
+          if (gr) cudaGraphDestroy(gr);
+      }
+      cudaGetLastError();
+      ctx->launches = launches0;  // nothing has run yet
+      if (!g) {
+        // capture is not possible here (or the body failed): run the launches directly from now on
+        ctx->inv_graph_mode = 0;
+        ctx->err.clear();
+      }
+      ctx->inv_graph = g;
+    }
+    if (g) {
+      GDCA_CUDA(ctx, cudaGraphLaunch(g->exec[0], ctx->stream));
+      if (ctx->ev[GDCA_EV_POTRF]) GDCA_CUDA(ctx, cudaEventRecord(ctx->ev[GDCA_EV_POTRF], ctx->stream));
+      GDCA_CUDA(ctx, cudaGraphLaunch(g->exec[1], ctx->stream));
+      ctx->oz_int8_ops = g->int8_ops;
+      ctx->oz_fp64_flop = g->fp64_flop;
+      ctx->last_inverse_ozaki = g->ozaki;
+      ctx->last_inverse_shared = false;
+      ctx->launches += g->launches;
+      done = true;
+    }
+  }
+  if (!done) GDCA_TRY(inverse_enqueue(ctx, nullptr));
   int info = 0;
   GDCA_CUDA(ctx, cudaMemcpyAsync(&info, ctx->dInfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

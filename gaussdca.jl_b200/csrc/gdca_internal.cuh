@@ -22,8 +22,10 @@ struct gdca_ctx {
   cudaStream_t stream = nullptr;   // main stream (created with the highest priority: it carries every critical path)
   cudaStream_t stream2 = nullptr;  // helper stream: bulk trailing updates of the Cholesky (look-ahead)
   cudaStream_t stream3 = nullptr;  // panel stream of the Cholesky: rest of the panel + inner updates, beside the diagonal chain
-  cudaEvent_t ev_fact = nullptr, ev_trail = nullptr;  // look-ahead hand-shakes
+  cudaEvent_t ev_fact = nullptr, ev_trail = nullptr, ev_trail_a = nullptr;  // look-ahead hand-shakes (ev_trail_a: first part of a split bulk update)
   cudaEvent_t ev_diag = nullptr, ev_p1 = nullptr, ev_u2a = nullptr, ev_u2b = nullptr;  // inner look-ahead hand-shakes
+  int inv_graph_mode = 1;          // single GPU: the inversion's launch sequence is captured once per shape and replayed as CUDA graphs (env GDCA_INV_GRAPH=0: direct launches)
+  void *inv_graph = nullptr;       // chol.cu: the instantiated graphs and their key
   int diag_blocked = 1;            // env GDCA_DIAG_BLOCKED=0: the rank-1 diagonal-block kernel of round 1 (256 CTA barriers per block)
   int chol_inner_lookahead = 1;    // env GDCA_CHOL_LOOKAHEAD=0: serial inner steps (round-1 first version)
   std::string err;
@@ -184,6 +186,25 @@ static inline int32_t gdca_reserve(gdca_ctx *ctx, T *&ptr, size_t &cap, size_t c
   return GDCA_OK;
 }
 
+// Kernel launch that carries the PRIORITY of its stream as a launch attribute: a stream-captured graph node keeps it (plain <<<>>>
+// launches lose the stream priority in a captured graph, and the chain of the factorisation then queues behind the bulk update).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gdca_launch_prio(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  int prio = 0;
+  cudaStreamGetPriority(st, &prio);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePriority;
+  at[0].val.priority = prio;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int32_t gdca_fail(gdca_ctx *ctx, int32_t status, const char *msg) {
   if (ctx) ctx->err = msg;
   return status;
@@ -240,6 +261,7 @@ int32_t gdca_k_compute_C(gdca_ctx *ctx, const double *Pi, const double *Pij, lon
 int32_t gdca_k_symmetrize_C(gdca_ctx *ctx);               // cov.cu: mirror upper site blocks, save diag blocks
 int32_t gdca_k_extract_diag(gdca_ctx *ctx);               // cov.cu: save the s x s diagonal blocks of dC
 int32_t gdca_k_inverse(gdca_ctx *ctx);                    // chol.cu
+void gdca_k_inverse_release(gdca_ctx *ctx);               // chol.cu: drops the captured graphs of the inversion
 int32_t gdca_k_inverse_group(gdca_ctx *lead);             // chol.cu: potrf on the leader, trtri / lauum shared by the device group
 int32_t gdca_k_score(gdca_ctx *ctx, int score);           // score.cu
 int32_t gdca_k_apc(gdca_ctx *ctx);                        // rank.cu

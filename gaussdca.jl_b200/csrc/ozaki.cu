@@ -572,7 +572,7 @@ int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, lon
   const long long rows_total = (long long)(batch - 1) * rows_b + rows;
   if (!cols) {
     const long long warps = (long long)rows * batch;
-    slice_rows_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(src, ld, stride_b, rows, k, batch, rows_b, dig, pitch, scale);
+    GDCA_CUDA(ctx, gdca_launch_prio(slice_rows_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, src, ld, stride_b, rows, k, batch, rows_b, dig, pitch, scale));
     GDCA_LAUNCH_CHECK(ctx);
   } else {
     GDCA_TRY(gdca_reserve(ctx, ctx->dOzMax, ctx->capOzMax, (size_t)ctx->npad > (size_t)rows_total ? (size_t)ctx->npad : (size_t)rows_total));
@@ -646,7 +646,7 @@ int32_t gdca_oz_gemm(gdca_ctx *ctx, cudaStream_t stream, const gdca_oz_operand &
     GDCA_CUDA(ctx, cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
     ctx->oz_attr_set = true;
   }
-  ozaki_gemm_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, stream>>>(mapA, mapB, P);
+  GDCA_CUDA(ctx, gdca_launch_prio(ozaki_gemm_kernel, dim3((unsigned)grid), dim3(OZ_THREADS), OZ_SMEM, stream, mapA, mapB, P));
   GDCA_LAUNCH_CHECK(ctx);
   // INT8 operations this launch executes (valid tiles x their k ranges x 28 digit products), for the bench line
   double ops = 0.0;
