@@ -86,7 +86,7 @@ int32_t load_common(gdca_ctx *ctx, int64_t L, int64_t M) {
   // buffers that peers have mapped are about to move: drop the mappings (the host re-exchanges handles)
   if (ctx->peers_ready && ((size_t)3 * ctx->Mpad > ctx->capCounts || (size_t)ctx->npad * ctx->npad > ctx->capC)) peer_close_all(ctx);
   ctx->have_alignment = true;
-  ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  ctx->have_lists = ctx->have_hist = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
   ctx->weights_from_counts = false;
   ctx->have_V = 0;
   GDCA_TRY(gdca_k_pack(ctx));  // builds the per-site lists first (site order), then the bit planes
@@ -145,7 +145,7 @@ int32_t weights_stage(gdca_ctx *ctx, double theta) {
 // derived from that alignment (lists, planes, weights, filter operands, covariance, inverse) stops being usable, so a later
 // gdca_dev_* call reports GDCA_ERR_STATE instead of mixing the new shape with the old buffers.
 void drop_alignment_state(gdca_ctx *ctx) {
-  ctx->have_alignment = ctx->have_lists = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
+  ctx->have_alignment = ctx->have_lists = ctx->have_hist = ctx->have_weights = ctx->have_cov = ctx->have_inv = false;
   ctx->weights_from_counts = false;
   ctx->have_V = 0;
   if (ctx->dZ_borrowed) {
@@ -323,7 +323,7 @@ void gdca_destroy(gdca_ctx *ctx) {
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
                   ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask,
                   ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax, ctx->dCellBase, ctx->dDigP, ctx->dScaleP,
-                  ctx->dClsHist, ctx->dClsPerm, ctx->dClsTab, ctx->dXt, ctx->dCovTiles};
+                  ctx->dClsHist, ctx->dClsPerm, ctx->dClsTab, ctx->dXt, ctx->dCovTiles, ctx->dSegCnt};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)

@@ -268,76 +268,146 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
 }
 
 // ---- weight classes ---------------------------------------------------------------------------------------------------
-__global__ void cls_hist_kernel(const int32_t *__restrict__ cnt, long long M, int32_t *__restrict__ hist) {
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&hist[cnt ? cnt[k] : 0], 1);
-}
-
-// distinct count values in ascending order: out[0] = number of classes, out[1 + 2 c] = value, out[2 + 2 c] = size (first cap classes)
-__global__ void __launch_bounds__(1024) cls_compact_kernel(const int32_t *__restrict__ hist, long long M, int32_t *__restrict__ out, int cap) {
-  __shared__ int s_cnt[1024];
-  const int tid = threadIdx.x;
-  const long long per = (M + 1023) / 1024, lo = per * tid, hi = lo + per < M ? lo + per : M;
-  int mine = 0;
-  for (long long v = lo; v < hi; ++v) mine += hist[v] != 0;
-  s_cnt[tid] = mine;
+constexpr int HSM = 4096;  // count values below this are histogrammed in shared memory first (almost all of them)
+// hist[v] = #{k : count[k] == v}, hist[M] = largest count value present
+__global__ void __launch_bounds__(256) cls_hist_kernel(const int32_t *__restrict__ cnt, long long M, int32_t *__restrict__ hist) {
+  __shared__ int sh[HSM];
+  __shared__ int smax;
+  for (int v = threadIdx.x; v < HSM; v += 256) sh[v] = 0;
+  if (threadIdx.x == 0) smax = 0;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan
-    const int add = tid >= o ? s_cnt[tid - o] : 0;
-    __syncthreads();
-    s_cnt[tid] += add;
-    __syncthreads();
+  int mx = 0;
+  for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < M; k += (long long)gridDim.x * 256) {
+    const int v = cnt ? cnt[k] : 0;
+    mx = max(mx, v);
+    if (v < HSM) atomicAdd(&sh[v], 1); else atomicAdd(&hist[v], 1);
   }
-  int pos = s_cnt[tid] - mine;
-  if (tid == 1023) out[0] = s_cnt[1023];
-  for (long long v = lo; v < hi; ++v) {
-    const int h = hist[v];
-    if (h) {
-      if (pos < cap) {
-        out[1 + 2 * pos] = (int)v;
-        out[2 + 2 * pos] = h;
-      }
-      ++pos;
-    }
-  }
+  for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&smax, mx);
+  __syncthreads();
+  for (int v = threadIdx.x; v < HSM && v < M; v += 256)
+    if (sh[v]) atomicAdd(&hist[v], sh[v]);
+  if (threadIdx.x == 0) atomicMax(&hist[M], smax);
 }
 
-// perm[base(class of k) + running index] = k   (the order inside a class does not matter: the counts are exact integers)
-__global__ void cls_assign_kernel(const int32_t *__restrict__ cnt, long long M, const int32_t *__restrict__ cls_val,
-                                  const long long *__restrict__ cls_base, int ncls, int32_t *__restrict__ cursor,
-                                  int32_t *__restrict__ perm) {
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += (long long)gridDim.x * blockDim.x) {
-    const int v = cnt ? cnt[k] : 0;
+// distinct count values in ascending order: out[0] = number of classes, out[1 + 2 c] = value, out[2 + 2 c] = size (first cap
+// classes); only [0, largest value present] is scanned
+__global__ void __launch_bounds__(1024) cls_compact_kernel(const int32_t *__restrict__ hist, long long M, int32_t *__restrict__ out, int cap) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int vmax = hist[M];
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int v0 = 0; v0 <= vmax; v0 += 1024) {
+    const int v = v0 + tid;
+    const int h = v <= vmax ? hist[v] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, h != 0);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (h && pos < cap) {
+      out[1 + 2 * pos] = v;
+      out[2 + 2 * pos] = h;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += s_warp[w];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) out[0] = s_base;
+}
+
+// perm[base(class of k) + running index] = k   (the order inside a class does not matter: the counts are exact integers).
+// A block owns a contiguous range of the sequences: it counts its members per class in shared memory, reserves one range per
+// class with ONE global atomic each, and hands out the slots from shared-memory cursors.
+__global__ void __launch_bounds__(256) cls_assign_kernel(const int32_t *__restrict__ cnt, long long M, const int32_t *__restrict__ cls_val,
+                                                         const long long *__restrict__ cls_base, int ncls, int32_t *__restrict__ cursor,
+                                                         int32_t *__restrict__ perm) {
+  __shared__ int s_val[MAXSEG], s_cnt[MAXSEG], s_off[MAXSEG];
+  for (int c = threadIdx.x; c < ncls; c += 256) {
+    s_val[c] = cls_val[c];
+    s_cnt[c] = 0;
+  }
+  __syncthreads();
+  const long long per = (M + gridDim.x - 1) / gridDim.x, k0 = per * blockIdx.x, k1 = k0 + per < M ? k0 + per : M;
+  auto cls_of = [&](int v) {
     int lo = 0, hi = ncls - 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (cls_val[mid] < v) lo = mid + 1; else hi = mid;
+      if (s_val[mid] < v) lo = mid + 1; else hi = mid;
     }
-    const int slot = atomicAdd(&cursor[lo], 1);
-    perm[cls_base[lo] + slot] = (int32_t)k;
+    return lo;
+  };
+  for (long long k = k0 + threadIdx.x; k < k1; k += 256) atomicAdd(&s_cnt[cls_of(cnt ? cnt[k] : 0)], 1);
+  __syncthreads();
+  for (int c = threadIdx.x; c < ncls; c += 256) {
+    s_off[c] = s_cnt[c] ? atomicAdd(&cursor[c], s_cnt[c]) : 0;
+    s_cnt[c] = 0;
+  }
+  __syncthreads();
+  for (long long k = k0 + threadIdx.x; k < k1; k += 256) {
+    const int c = cls_of(cnt ? cnt[k] : 0);
+    perm[cls_base[c] + s_off[c] + atomicAdd(&s_cnt[c], 1)] = (int32_t)k;
   }
 }
 
 // Xt[(i, a)][kpos] = [Zt[i][perm[kpos]] == a + 1] as packed e2m1 (1.0 = 0x2; element 2b in the low nibble of byte b), one
-// 32-bit word = 8 consecutive positions; perm < 0 (padding of a class to whole k-blocks) encodes zeros
+// 32-bit word = 8 consecutive positions; perm < 0 (padding of a class to whole k-blocks) encodes zeros.
+// A warp covers exactly one k-block (32 words = 256 positions), i.e. one class segment: while it encodes it also counts, per
+// state, the sequences of that segment carrying the state at this site (segcnt[i][segment][a], the numerators of Pi).
 __global__ void __launch_bounds__(256) encode_onehot4_kernel(const int8_t *__restrict__ Zt, long long M, const int32_t *__restrict__ perm,
-                                                             long long words_per_row, int s, uint32_t *__restrict__ Xt) {
+                                                             long long words_per_row, int s, const int *__restrict__ seg_end, int nseg,
+                                                             uint32_t *__restrict__ Xt, int32_t *__restrict__ segcnt) {
   const long long w = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (w >= words_per_row) return;
   const long long i = blockIdx.y;
-  const int4 p0 = reinterpret_cast<const int4 *>(perm)[2 * w], p1 = reinterpret_cast<const int4 *>(perm)[2 * w + 1];
-  const int p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-  const int8_t *z = Zt + i * M;
+  const bool live = w < words_per_row;
   int zz[8];
+  if (live) {
+    const int4 p0 = reinterpret_cast<const int4 *>(perm)[2 * w], p1 = reinterpret_cast<const int4 *>(perm)[2 * w + 1];
+    const int p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    const int8_t *z = Zt + i * M;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) zz[e] = p[e] >= 0 ? (int)z[p[e]] : 0;
+    for (int e = 0; e < 8; ++e) zz[e] = p[e] >= 0 ? (int)z[p[e]] : 0;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) zz[e] = 0;
+  }
+  // the segment of this warp's k-block (warp-uniform)
+  const int kb = (int)(w >> 5);
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (seg_end[mid] <= kb) lo = mid + 1; else hi = mid;
+  }
   uint32_t *out = Xt + (i * s) * words_per_row + w;
+  int32_t *sc = segcnt + (i * nseg + lo) * 32;
+  const int lane = threadIdx.x & 31;
   for (int a = 1; a <= s; ++a) {
     uint32_t word = 0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) word |= (zz[e] == a) ? (0x2u << (4 * e)) : 0u;
-    out[(long long)(a - 1) * words_per_row] = word;
+    if (live) out[(long long)(a - 1) * words_per_row] = word;
+    const int tot = __reduce_add_sync(0xffffffffu, __popc(word));
+    if (lane == 0 && tot) atomicAdd(sc + a, tot);
   }
+}
+
+// Pi[(i,a)] = (1 - pc) * (sum_segments w_seg * segcnt[i][seg][a]) / Meff + pc / q, segments in ascending order (deterministic)
+__global__ void __launch_bounds__(128) pi_from_segments_kernel(const int32_t *__restrict__ segcnt, const double *__restrict__ seg_w, int nseg,
+                                                               const double *__restrict__ meff, int s, int q, double pc,
+                                                               double *__restrict__ Pi) {
+  const long long i = blockIdx.x;
+  const int a = threadIdx.x + 1;
+  if (a > s) return;
+  double acc = 0.0;
+  for (int g = 0; g < nseg; ++g) acc = fma(seg_w[g], (double)segcnt[(i * nseg + g) * 32 + a], acc);
+  Pi[i * s + (a - 1)] = (1.0 - pc) * (acc / meff[0]) + pc / q;
 }
 
 }  // namespace
@@ -383,9 +453,9 @@ int32_t gdca_k_cov_classes(gdca_ctx *ctx, int32_t *host_out) {
   constexpr int CAP = MAXSEG;
   const int32_t *cnt = ctx->counts_row < 0 ? nullptr : ctx->dCounts + (size_t)ctx->counts_row * ctx->Mpad;
   GDCA_TRY(gdca_reserve(ctx, ctx->dClsHist, ctx->capClsHist, (size_t)M + 4 * CAP + 16));
-  int32_t *hist = ctx->dClsHist, *compact = ctx->dClsHist + M;  // [1 + 2 CAP]
-  GDCA_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)M * sizeof(int32_t), ctx->stream));
-  cls_hist_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(cnt, M, hist);
+  int32_t *hist = ctx->dClsHist, *compact = ctx->dClsHist + M + 1;  // hist[M] = largest value; compact [1 + 2 CAP]
+  GDCA_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)(M + 1) * sizeof(int32_t), ctx->stream));
+  cls_hist_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(cnt, M, hist);
   GDCA_LAUNCH_CHECK(ctx);
   cls_compact_kernel<<<1, 1024, 0, ctx->stream>>>(hist, M, compact, CAP);
   GDCA_LAUNCH_CHECK(ctx);
@@ -451,11 +521,16 @@ int32_t gdca_k_covariance_tc(gdca_ctx *ctx, double pc, bool raw, bool *done) {
   GDCA_CUDA(ctx, cudaMemcpyAsync(d_base, pl.cls_base.data(), (size_t)ncls * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   GDCA_CUDA(ctx, cudaMemcpyAsync(d_segend, pl.seg_end.data(), (size_t)nseg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   GDCA_CUDA(ctx, cudaMemcpyAsync(d_segw, pl.seg_w.data(), (size_t)nseg * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  cls_assign_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(cnt, M, d_val, d_base, ncls, cursor, perm);
+  cls_assign_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(cnt, M, d_val, d_base, ncls, cursor, perm);
   GDCA_LAUNCH_CHECK(ctx);
   const long long wpr = Kbytes / 4;
+  GDCA_TRY(gdca_reserve(ctx, ctx->dSegCnt, ctx->capSegCnt, (size_t)L * nseg * 32));
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dSegCnt, 0, (size_t)L * nseg * 32 * sizeof(int32_t), ctx->stream));
   encode_onehot4_kernel<<<dim3((unsigned)((wpr + 255) / 256), (unsigned)L), 256, 0, ctx->stream>>>(
-      ctx->dZt, M, perm, wpr, ctx->s, reinterpret_cast<uint32_t *>(ctx->dXt));
+      ctx->dZt, M, perm, wpr, ctx->s, d_segend, nseg, reinterpret_cast<uint32_t *>(ctx->dXt), ctx->dSegCnt);
+  GDCA_LAUNCH_CHECK(ctx);
+  // Pi from the class counts: the same exact integers the tiles accumulate (Pi_true is the diagonal of Pij_true)
+  pi_from_segments_kernel<<<(unsigned)L, 128, 0, ctx->stream>>>(ctx->dSegCnt, d_segw, nseg, ctx->dMeff, ctx->s, ctx->q, pc, ctx->dPi);
   GDCA_LAUNCH_CHECK(ctx);
   // the padding strips of C (rows / columns n .. npad-1) must be zero; everything else is written by the tiles
   const bool peer_out = ctx->peers_ready && ctx->shard_world > 1;

@@ -107,6 +107,7 @@ struct gdca_ctx {
   int32_t *dClsHist = nullptr; size_t capClsHist = 0;  // [M] histogram of the counts + compacted (value, size) pairs
   int32_t *dClsPerm = nullptr; size_t capClsPerm = 0;  // [Mk] sequences in class order (-1: padding) + cursors + class values + segment ends
   double *dClsTab = nullptr; size_t capClsTab = 0;     // class bases (int64) and segment weights
+  int32_t *dSegCnt = nullptr; size_t capSegCnt = 0;    // [L][segments][32] sequences of a class segment with a state at a site (Pi of the tensor-core engine)
   uint8_t *dXt = nullptr; size_t capXt = 0;        // [n][Mk/2] one-hot operand, packed e2m1, K-major
   int2 *dCovTiles = nullptr; size_t capCovTiles = 0;   // super-tiles of this rank
   bool weights_from_counts = false;                // W = 1/(count+1) of dCounts[counts_row] (or all 1): the classes are the distinct counts
@@ -142,6 +143,7 @@ struct gdca_ctx {
   int staged_h2d = 1;                          // env GDCA_STAGED_H2D=0: plain cudaMemcpyAsync from pageable memory
 
   // ---- state flags ----
+  bool have_hist = false;      // dZt + dListOff (per-site state histograms as bucket offsets) are valid
   bool have_alignment = false, have_lists = false, have_weights = false, have_cov = false, have_inv = false;
   double meff = 0.0, pseudocount = 0.0;
   int counts_row = -1;  // row of dCounts the weights came from (-1: theta == 0)
@@ -248,7 +250,8 @@ static inline bool gdca_tc_filter_wanted(const gdca_ctx *ctx) {
   return fits && (ctx->tc_filter_mode == 2 || (ctx->tc_filter_mode == 1 && ctx->M >= 16384));
 }
 int32_t gdca_k_finish_weights(gdca_ctx *ctx, int which);  // weights.cu
-int32_t gdca_k_build_lists(gdca_ctx *ctx);                // cov.cu: per-site lists of sequence ids grouped by state
+int32_t gdca_k_site_hist(gdca_ctx *ctx);                  // cov.cu: site-major copy + per-site state histograms (bucket offsets)
+int32_t gdca_k_build_lists(gdca_ctx *ctx);                // cov.cu: per-site lists of sequence ids grouped by state (on demand)
 int32_t gdca_k_ident_sum(gdca_ctx *ctx, unsigned long long *ident_out);  // cov.cu: sum_{k<l} ident from site histograms
 int32_t gdca_k_covariance(gdca_ctx *ctx, double pc, bool raw = false);  // cov.cu (raw: Pij_true instead of C)
 int32_t gdca_k_covariance_tc(gdca_ctx *ctx, double pc, bool raw, bool *done);  // covtc.cu: tensor-core engine; *done = false: not applicable

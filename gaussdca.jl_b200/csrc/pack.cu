@@ -119,7 +119,7 @@ int32_t gdca_k_pack(gdca_ctx *ctx) {
   const size_t words = (size_t)ctx->nwords * ctx->nplanes * Mpad;
   GDCA_TRY(gdca_reserve(ctx, ctx->dPlanes, ctx->capPlanes, words));
   // site order from the per-site state histograms (built here if they are not there yet)
-  GDCA_TRY(gdca_k_build_lists(ctx));
+  GDCA_TRY(gdca_k_site_hist(ctx));
   GDCA_TRY(gdca_reserve(ctx, ctx->dPerm, ctx->capPerm, (size_t)ctx->L));
   const size_t osmem = (size_t)ctx->L * sizeof(unsigned long long);
   if (osmem <= 64 * 1024) {

@@ -44,7 +44,7 @@ def test_weighted_frequencies_on_tensor_cores_vs_oracle_and_scatter_engine(pkg, 
     Pi_s, Pij_s, _, _ = pkg.compute_weighted_frequencies(Z, q, theta, ctx=tc)
     assert tc.cov_info()["engine"] == 1
     tc.set_cov_engine(2)
-    assert np.array_equal(Pi_s, Pi_t)
+    assert normwise(Pi_t, Pi_s) <= 1e-15
     assert normwise(Pij_t, Pij_s) <= 1e-14
 
 
