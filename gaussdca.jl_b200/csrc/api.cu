@@ -289,7 +289,10 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   }
   if (const char *env = getenv("GDCA_STAGED_H2D")) ctx->staged_h2d = atoi(env) != 0;
   if (const char *env = getenv("GDCA_CELL_SWEEP")) ctx->cell_sweep = atoi(env) != 0;
-  if (const char *env = getenv("GDCA_TC_MULTICAST")) ctx->tc_filter_want_multicast = atoi(env) != 0;
+  if (const char *env = getenv("GDCA_TC_MULTICAST")) {
+    const int v = atoi(env);
+    if (v >= 0 && v <= 2) ctx->tc_filter_want_multicast = v;
+  }
   if (const char *env = getenv("GDCA_COV_ENGINE")) {
     const int m = atoi(env);
     if (m >= 0 && m <= 2) ctx->cov_engine = m;
@@ -512,7 +515,7 @@ int32_t gdca_set_tc_filter_bits(gdca_ctx *ctx, int32_t bits) {
 
 int32_t gdca_set_tc_filter_multicast(gdca_ctx *ctx, int32_t on) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
-  ctx->tc_filter_want_multicast = on != 0;
+  ctx->tc_filter_want_multicast = on < 0 ? 0 : (on > 2 ? 2 : on);
   return GDCA_OK;
 }
 
@@ -952,7 +955,10 @@ static int32_t run_group(gdca_ctx *lead, const int8_t *Z, bool resident, int64_t
     // round trip on the leader, the members plan from its copy
     std::vector<int32_t> cls(1 + 2 * GDCA_COV_MAXCLS);
     const bool share_cls = lead->cov_engine != 1 && lead->weights_from_counts;
-    if (share_cls) GDCA_TRY(gdca_k_cov_classes(lead, cls.data()));
+    if (share_cls) {
+      GDCA_TRY(set_device(lead));
+      GDCA_TRY(gdca_k_cov_classes(lead, cls.data()));
+    }
     for (int r = 0; r < N; ++r) {
       GDCA_TRY(set_device(g[r]));
       g[r]->cov_cls_host = share_cls ? cls.data() : nullptr;

@@ -93,8 +93,8 @@ struct gdca_ctx {
   int cell_sweep = 1;                              // behind the prefilter: sweep flagged CELLS, one warp each (env GDCA_CELL_SWEEP=0: blocks)
   int tc_filter_mode = 1;                          // 0 off, 1 auto (large M), 2 always (tests)
   int tc_filter_bits = 4;                          // operands of the filter: 4 = e2m1 (kind::mxf4), 8 = e4m3 (kind::f8f6f4), 80 = int8 (kind::i8)
-  bool tc_filter_want_multicast = true;            // 2-CTA clusters + TMA multicast of the B tile (env GDCA_TC_MULTICAST=0: off)
-  bool tc_filter_multicast = false;                // last filter launch used 2-CTA clusters with TMA multicast
+  int tc_filter_want_multicast = 2;                // 0: independent CTAs; 1: 2-CTA clusters + TMA multicast of the B tile; 2: 2-CTA pairs issuing ONE cta_group::2 MMA (FP4; env GDCA_TC_MULTICAST)
+  int tc_filter_multicast = 0;                     // what the last filter launch used
   bool last_sweep_filtered = false;
   double tc_filter_tflop = 0.0;                    // flop of the last filter launch on this rank, in 1e12
   double tc_filter_l2_bytes = 0.0;                 // operand bytes its TMA loads moved

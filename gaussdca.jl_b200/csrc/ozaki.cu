@@ -5,11 +5,16 @@
 //
 //   slice    every operand row is scaled by a power of two 2^e (|a / 2^e| < 1/2) and cut into S = 8 signed 7-bit digits,
 //                a / 2^e = sum_t d_t 2^(-7 (t+1)) + r,   |d_t| <= 64,  |r| <= 2^-57,
-//            stored as int8, K-major: dig[row][k-block of 64][digit 0..7][64 bytes], so that one 128-byte row of a TMA box
-//            carries the SAME 64 k-elements of two consecutive digits;
+//            stored as int8, K-major: dig[row][k-block of 64][digit 0..7][64 bytes]: the A operand is fetched as 128-byte rows
+//            (the same 64 k-elements of two consecutive digits, SWIZZLE_128B), the B operand as one 64-byte-wide box per digit
+//            (SWIZZLE_64B) so that its digits lie STACKED ALONG N in shared memory;
 //   multiply D_d = sum_{t+u=d} A_t B_u^T for d = 0..7 (36 digit products, t + u < 8) with tcgen05.mma kind::i8: exact S32
 //            accumulation (|D_d| <= 8 k 64^2 < 2^31 for k <= 65 000), one 128 x 64 output tile with all eight diagonal
-//            accumulators resident in TMEM (8 x 64 = all 512 columns);
+//            accumulators resident in TMEM (8 x 64 = all 512 columns, accumulator d at column 64 d).  Because the accumulators of
+//            consecutive diagonals are consecutive TMEM columns and the B digits are consecutive N rows, ONE instruction
+//            multiplies digit t of A with up to four digits u0..u0+3 of B (N = 64..256) and lands in D_{t+u0}..D_{t+u0+3}:
+//            12 instructions per K = 32 step instead of 36, the A tile read from shared memory 12 times instead of 36
+//            (98 B/clk of operand reads instead of 180 -- the pipe delivers 128);
 //   combine  hi = D_0 2^21 + D_1 2^14 + D_2 2^7 + D_3 and lo = D_4 2^21 + D_5 2^14 + D_6 2^7 + D_7 as exact int64, then
 //            C (+)= alpha 2^(e_i + f_j) (hi 2^-35 + lo 2^-63): two exact conversions and ONE rounding -- the correctly
 //            rounded value of the exact sum of the 36 digit products.
@@ -20,8 +25,8 @@
 // (test/runtests.jl:41-50, large.DIRout.txt) and that needs FP64-grade noise -- hence eight.
 //
 // Kernel: the warp-specialised structure of tcfilter.cu -- warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps
-// 2..5 epilogue (one TMEM lane quarter each) -- 2-stage ring of 96 KB (4 + 4 SWIZZLE_128B boxes per 64-wide k-block), 72 MMAs
-// of 128 x 64 x 32 per stage, triangular operands handled as per-tile k ranges, batched launches for the trtri levels.
+// 2..5 epilogue (one TMEM lane quarter each) -- 2-stage ring of 96 KB (4 SWIZZLE_128B + 8 SWIZZLE_64B boxes per 64-wide k-block),
+// 24 MMAs of 128 x (64..256) x 32 per stage, triangular operands handled as per-tile k ranges, batched launches for the trtri levels.
 // The epilogue goes through a small padded shared-memory tile so that the FP64 read-modify-write of C is coalesced.
 #include <cuda.h>  // CUtensorMap (types only)
 

@@ -40,7 +40,7 @@ namespace {
 
 constexpr int BM = 128;              // tile rows (sequences)
 constexpr int BK = 128;              // K bytes per stage (= SWIZZLE_128B atom width)
-constexpr int MAX_STAGE = 5;
+constexpr int MAX_STAGE = 7;
 constexpr int TC_THREADS = 192;       // warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int BAND = 16;             // row blocks per band of the tile order
@@ -66,6 +66,14 @@ struct Cfg {
       : OP == OP_I8 ? ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24))
                     : ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24));
 };
+
+// cta_group::2 (FP4 only): the two CTAs of a cluster form ONE 256 x 224 MMA -- each keeps its own 128 rows of A and only HALF of
+// the B tile (the tensor cores read the other half from the peer's shared memory): 30 KB instead of 44 KB of operands arrive in
+// every SM per k-block (the L2 -> SM path, ~70 B/clk/SM, is what bounds the multicast variant at 0.75 of the FP4 rate), 7 stages
+constexpr int CG2_STAGE_BYTES = BM * BK + (224 / 2) * BK;  // 30 KB
+constexpr int CG2_NSTAGE = 7;
+constexpr size_t CG2_SMEM = (size_t)CG2_NSTAGE * CG2_STAGE_BYTES + 1024;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                // shared::cluster address of the same offset in the even CTA of the pair
 
 struct FilterParams {
   int T, NT, NB, KB;    // 128-row blocks, column tiles, bands of this rank's rows, 128-byte k-blocks
@@ -180,6 +188,34 @@ __device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t da, uint64_t
       : "memory");
 }
 
+// ---- cta_group::2 forms: one MMA across the CTA pair, issued by the even CTA ----
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  // executed by both CTAs: the bytes land in the issuing CTA's shared memory, the transaction count on the EVEN CTA's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_mxf4_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+// arrives on the mbarrier at this offset in both CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// plain arrival on the EVEN CTA's barrier at this offset (from either CTA)
+__device__ __forceinline__ void mbar_arrive_even(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+
 // 32 consecutive 32-bit columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -251,14 +287,18 @@ static_assert((BAND & (BAND - 1)) == 0, "BAND must be a power of two");
 // tile and one half of the B tile; the half is TMA-multicast into both CTAs (-32 % L2->SM operand traffic at 128 x 224).  A
 // shared-memory stage is therefore written by both CTAs' producers: its empty barrier counts the tcgen05.commit of BOTH
 // CTAs (multicast commit), its full barrier the bytes of all three boxes.
-template <int OP, bool MC>
+// MC = 2: the cta_group::2 pair (FP4): same tile pairing as MC = 1, no multicast -- each CTA loads its A tile and its half of B.
+template <int OP, int MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_filter_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, FilterParams P) {
   using C = Cfg<OP>;
   constexpr bool FP4 = C::FP4;
+  constexpr bool CG2 = MC == 2;
+  static_assert(!CG2 || FP4, "cta_group::2 variant: FP4 operands only");
   const uint32_t crank = MC ? cluster_ctarank() : 0u;
   constexpr int BN = C::BN;
-  constexpr int NSTAGE = C::NSTAGE;
+  constexpr int NSTAGE = CG2 ? CG2_NSTAGE : C::NSTAGE;
+  constexpr int STAGE_BYTES = CG2 ? CG2_STAGE_BYTES : C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * MAX_STAGE + 4];
   __shared__ uint32_t s_tmem;
@@ -278,18 +318,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), MC ? 2 : 1);
+      mbar_init(empty_bar(s), MC == 1 ? 2 : 1);  // multicast pair: both producers write the stage; cta_group::2: one commit reaches both CTAs
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), CG2 ? 8 : 4);  // one arrival per epilogue warp (cta_group::2: of both CTAs, on the even CTA's barrier)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (CG2) {
+    __syncthreads();
+    cluster_sync_all();  // both CTAs are resident and their barriers initialised before the pair allocates tensor memory
+  }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -326,13 +374,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int kb = 0; kb < P.KB; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         if (elect_one()) {
-          const uint32_t sa = base + (uint32_t)s * (uint32_t)C::STAGE_BYTES;
-          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
-          tma_load_2d(sa, &tmapA, full_bar(s), kb * BK, row_a);  // rows beyond the matrix are zero-filled
-          if (MC)  // tmapB boxes are BN/2 rows here: my half of the B tile, delivered to both CTAs
-            tma_load_2d_mc(sa + C::A_BYTES + crank * (C::B_BYTES / 2), &tmapB, full_bar(s), kb * BK, row_b, (uint16_t)3);
-          else
-            tma_load_2d(sa + C::A_BYTES, &tmapB, full_bar(s), kb * BK, row_b);
+          const uint32_t sa = base + (uint32_t)s * (uint32_t)STAGE_BYTES;
+          if (CG2) {
+            // the even CTA's barrier collects the bytes of both CTAs; every CTA keeps its A tile and ITS half of the B tile
+            if (crank == 0) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);
+            tma_load_2d_cg2(sa, &tmapA, full_bar(s), kb * BK, row_a);
+            tma_load_2d_cg2(sa + C::A_BYTES, &tmapB, full_bar(s), kb * BK, row_b);
+          } else {
+            mbar_expect_tx(full_bar(s), STAGE_BYTES);
+            tma_load_2d(sa, &tmapA, full_bar(s), kb * BK, row_a);  // rows beyond the matrix are zero-filled
+            if (MC)  // tmapB boxes are BN/2 rows here: my half of the B tile, delivered to both CTAs
+              tma_load_2d_mc(sa + C::A_BYTES + crank * (C::B_BYTES / 2), &tmapB, full_bar(s), kb * BK, row_b, (uint16_t)3);
+            else
+              tma_load_2d(sa + C::A_BYTES, &tmapB, full_bar(s), kb * BK, row_b);
+          }
         }
         __syncwarp();
         if (++s == NSTAGE) {
@@ -341,8 +396,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 && !(CG2 && crank != 0)) {
+    // ===== MMA issuer (cta_group::2: the even CTA issues for the pair) =====
     TileIter it;
     int s = 0;
     uint32_t ph = 0, n = 0;
@@ -360,25 +415,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = base + (uint32_t)s * (uint32_t)C::STAGE_BYTES;
+          const uint32_t sa = base + (uint32_t)s * (uint32_t)STAGE_BYTES;
           const uint32_t lo_a = ((sa >> 4) & 0x3FFFu) | (1u << 16), lo_b = (((sa + C::A_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 32 bytes along K per instruction (32 e4m3 / 64 e2m1) = +2 in the address field
             const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(lo_a + 2u * k);
             const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(lo_b + 2u * k);
             const uint32_t accumulate = (k > 0) ? 1u : (uint32_t)(kb != 0);
-            if (FP4)
+            if (CG2)  // M = 256 across the pair
+              umma_mxf4_cg2(tmem_d, da, db, (C::IDESC & ~(0x1Fu << 24)) | ((uint32_t)(2 * BM >> 4) << 24), accumulate, sfa, sfb);
+            else if (FP4)
               umma_mxf4(tmem_d, da, db, C::IDESC, accumulate, sfa, sfb);
             else if (OP == OP_I8)
               umma_i8(tmem_d, da, db, C::IDESC, accumulate);
             else
               umma_f8(tmem_d, da, db, C::IDESC, accumulate);
           }
-          if (MC)
-            umma_commit_mc(empty_bar(s), (uint16_t)3);  // both producers write this stage: tell both
-          else
-            umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
-          if (kb == P.KB - 1) umma_commit(tfull_bar(as));  // accumulator complete
+          if (CG2) {
+            umma_commit_cg2(empty_bar(s));                          // the stage of BOTH CTAs is free again
+            if (kb == P.KB - 1) umma_commit_cg2(tfull_bar(as));     // both halves of the accumulator are complete
+          } else {
+            if (MC)
+              umma_commit_mc(empty_bar(s), (uint16_t)3);  // both producers write this stage: tell both
+            else
+              umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+            if (kb == P.KB - 1) umma_commit(tfull_bar(as));  // accumulator complete
+          }
         }
         __syncwarp();
         if (++s == NSTAGE) {
@@ -387,7 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32 (w & 3) .. +31 = tile rows =====
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -435,7 +497,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (CG2)
+          mbar_arrive_even(tempty_bar(as));  // the issuing CTA waits for the epilogues of both CTAs
+        else
+          mbar_arrive(tempty_bar(as));
+      }
     }
   }
 
@@ -444,7 +511,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (MC) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until it is done too
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CG2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -582,6 +652,7 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   }
   // 2-CTA clusters with TMA multicast of the B tile unless switched off (gdca_set_tc_filter_multicast) or the grid is odd
   const bool mc = ctx->tc_filter_want_multicast && (ctx->num_sms % 2 == 0);
+  const bool cg2 = mc && FP4 && ctx->tc_filter_want_multicast == 2;   // one cta_group::2 MMA per CTA pair
   CUtensorMap mapA, mapB;
   GDCA_TRY(make_tensor_map(ctx, &mapA, ctx->dV, VM, Kbytes, BM));
   GDCA_TRY(make_tensor_map(ctx, &mapB, ctx->dV, VM, Kbytes, mc ? C::BN / 2 : C::BN));
@@ -601,11 +672,12 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   P.dump = dump;
   P.dump_ld = dump_ld;
   auto launch = [&](auto kern, int threads, bool cluster) -> int32_t {
-    GDCA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    const size_t smem = cg2 ? CG2_SMEM : C::SMEM;
+    GDCA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ctx->num_sms);
     cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -617,12 +689,15 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
     GDCA_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, mapA, mapB, P));
     return GDCA_OK;
   };
-  if (mc)
-    GDCA_TRY(launch(tc_filter_kernel<OP, true>, TC_THREADS, true));
-  else
-    GDCA_TRY(launch(tc_filter_kernel<OP, false>, TC_THREADS, false));
+  if constexpr (FP4) {
+    if (cg2) GDCA_TRY(launch(tc_filter_kernel<OP, 2>, TC_THREADS, true));
+  }
+  if (mc && !cg2)
+    GDCA_TRY(launch(tc_filter_kernel<OP, 1>, TC_THREADS, true));
+  else if (!mc)
+    GDCA_TRY(launch(tc_filter_kernel<OP, 0>, TC_THREADS, false));
   GDCA_LAUNCH_CHECK(ctx);
-  ctx->tc_filter_multicast = mc;
+  ctx->tc_filter_multicast = mc ? (cg2 ? 2 : 1) : 0;
 
   const long long tt = T * T;
   const int cgrid = (int)((tt + 255) / 256 < (long long)ctx->num_sms * 8 ? (tt + 255) / 256 : (long long)ctx->num_sms * 8);

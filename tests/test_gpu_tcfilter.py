@@ -21,18 +21,18 @@ def projected_scores(Z):
 
 
 # operands: e4m3 (kind::f8f6f4) / packed e2m1 (kind::mxf4, unit block scales) / int8 (kind::i8, code 80); launch: independent CTAs / 2-CTA clusters
-# sharing the column tile by TMA multicast
-VARIANTS = [(8, 0), (4, 0), (8, 1), (4, 1), (80, 1)]
+# sharing the column tile by TMA multicast / 2-CTA pairs issuing one cta_group::2 MMA of 256 x 224 (each CTA keeps half of the column tile)
+VARIANTS = [(8, 0), (4, 0), (8, 1), (4, 1), (80, 1), (4, 2)]
 
 
-@pytest.fixture(params=VARIANTS, ids=["fp8", "fp4", "fp8-multicast", "fp4-multicast", "int8-multicast"])
+@pytest.fixture(params=VARIANTS, ids=["fp8", "fp4", "fp8-multicast", "fp4-multicast", "int8-multicast", "fp4-cta_group2"])
 def bits(request, ctx):
     b, mc = request.param
     ctx.check(ctx.lib.gdca_set_tc_filter_bits(ctx.h, b))
     ctx.check(ctx.lib.gdca_set_tc_filter_multicast(ctx.h, mc))
     yield b
     ctx.check(ctx.lib.gdca_set_tc_filter_bits(ctx.h, 4))
-    ctx.check(ctx.lib.gdca_set_tc_filter_multicast(ctx.h, 1))
+    ctx.check(ctx.lib.gdca_set_tc_filter_multicast(ctx.h, 2))
 
 
 def run_filter(ctx, Z, thresh, want_scores=True):
