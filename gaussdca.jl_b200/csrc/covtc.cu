@@ -39,21 +39,22 @@ using namespace tcptx;
 constexpr int CT = 128;            // output tile edge
 constexpr int CBK = 128;           // K bytes per stage = 256 packed e2m1 = 256 sequences
 constexpr int CSEQ = 2 * CBK;      // sequences per k-block
-constexpr int HALF_BYTES = 64 * CBK;     // one multicast box: 64 rows x 128 B
+constexpr int HALF_BYTES = 64 * CBK;     // one TMA box: 64 rows x 128 B
 constexpr int TILE_BYTES = CT * CBK;     // 16 KB
-constexpr int CSTAGE_BYTES = 2 * TILE_BYTES;
-constexpr int CNSTAGE = 6;
+constexpr int CSTAGE_BYTES = TILE_BYTES + HALF_BYTES;  // the CTA's own A tile + its half of the B tile: 24 KB
+constexpr int CNSTAGE = 9;
 constexpr int C_THREADS = 320;     // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int C_TMEM_COLS = 512;   // 2 x 128 accumulator columns + 64 scale-factor columns -> next power of two
 constexpr int C_SF_COL = 2 * CT;
 constexpr int MAXSEG = GDCA_COV_MAXCLS;
 constexpr size_t C_SMEM = (size_t)CNSTAGE * CSTAGE_BYTES + 1024;
-// kind::mxf4.block_scale.block32: A = B = E2M1 (1 at bits 7 and 10), scale format UE8M0 (bit 23), N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t C_IDESC = (1u << 7) | (1u << 10) | ((uint32_t)(CT >> 3) << 17) | (1u << 23) | ((uint32_t)(CT >> 4) << 24);
+// kind::mxf4.block_scale.block32: A = B = E2M1 (1 at bits 7 and 10), scale format UE8M0 (bit 23), N >> 3 at bit 17, M >> 4 at bit 24;
+// cta_group::2: M = 256 rows across the CTA pair
+constexpr uint32_t C_IDESC = (1u << 7) | (1u << 10) | ((uint32_t)(CT >> 3) << 17) | (1u << 23) | ((uint32_t)(2 * CT >> 4) << 24);
 constexpr long long SEG_MAX_SEQ = 1ll << 23;  // FP32 accumulation of ones stays exact
 
 struct CovTcParams {
-  const int2 *tiles;     // [ntiles] super-tiles (RB2, CB2), CB2 <= RB2, this rank's share
+  const int2 *tiles;     // [ntiles] pair tiles (RB2, CB): row blocks 2 RB2 and 2 RB2 + 1 x column block CB <= 2 RB2 + 1, this rank's share
   int ntiles;
   int nblk;              // 128-row blocks of the output
   int nseg;
@@ -82,8 +83,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
   volatile uint32_t *tmem_slot_ptr = &s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();   // 2 y + x: tile (2 RB2 + y, 2 CB2 + x)
-  const int cy = (int)(crank >> 1), cx = (int)(crank & 1u);
+  const uint32_t crank = cluster_ctarank();   // y: this CTA computes the tile (2 RB2 + y, CB); the even CTA issues the MMAs of the pair
+  const int cy = (int)crank;
   const int first = (int)cluster_id_x(), step = (int)cluster_nid_x();
 
   for (int i = threadIdx.x; i < P.nseg; i += C_THREADS) {
@@ -93,22 +94,24 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int s = 0; s < CNSTAGE; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 3);  // the MMA issuers of this CTA, of its row neighbour and of its column neighbour
+      mbar_init(full_bar(s), 1);   // even CTA: its producer's expect_tx; the bytes of BOTH CTAs are counted here
+      mbar_init(empty_bar(s), 1);  // one cta_group::2 commit reaches both CTAs
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), 16);  // even CTA: one arrival per epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  cluster_sync_all();  // both CTAs are resident, their barriers initialised, before the pair allocates tensor memory
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // the neighbours' barriers are initialised before anything of this CTA can arrive on them
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -127,22 +130,21 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
   const int KB = nseg > 0 ? s_seg_end[nseg - 1] : 0;
 
   if (warp == 0) {
-    // ===== TMA producer: my half of the A tile to my row neighbour and me, my half of the B tile to my column neighbour and me
-    const uint16_t mask_a = (uint16_t)(3u << (2 * cy));             // CTAs (cy, 0) and (cy, 1)
-    const uint16_t mask_b = (uint16_t)((1u << cx) | (4u << cx));    // CTAs (0, cx) and (1, cx)
+    // ===== TMA producer (both CTAs): my A tile (two 64-row boxes) and MY half of the B tile; the even CTA's barrier counts it all
     int s = 0;
     uint32_t ph = 0;
     for (int t = first; t < P.ntiles; t += step) {
       const int2 st = P.tiles[t];
-      const int row_a = (2 * st.x + cy) * CT + cx * 64;
-      const int row_b = (2 * st.y + cx) * CT + cy * 64;
+      const int row_a = (2 * st.x + cy) * CT;
+      const int row_b = st.y * CT + cy * 64;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         if (elect_one()) {
           const uint32_t sa = base + (uint32_t)s * (uint32_t)CSTAGE_BYTES;
-          mbar_expect_tx(full_bar(s), CSTAGE_BYTES);
-          tma_load_2d_mc(sa + (uint32_t)cx * HALF_BYTES, &tmap, full_bar(s), kb * CBK, row_a, mask_a);  // rows >= n are zero-filled
-          tma_load_2d_mc(sa + TILE_BYTES + (uint32_t)cy * HALF_BYTES, &tmap, full_bar(s), kb * CBK, row_b, mask_b);
+          if (cy == 0) mbar_expect_tx(full_bar(s), 2 * CSTAGE_BYTES);
+          tma_load_2d_cg2(sa, &tmap, full_bar(s), kb * CBK, row_a);  // rows >= n are zero-filled
+          tma_load_2d_cg2(sa + HALF_BYTES, &tmap, full_bar(s), kb * CBK, row_a + 64);
+          tma_load_2d_cg2(sa + TILE_BYTES, &tmap, full_bar(s), kb * CBK, row_b);
         }
         __syncwarp();
         if (++s == CNSTAGE) {
@@ -151,9 +153,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: one accumulator stage per (tile, class) =====
-    const uint16_t mask_e = (uint16_t)((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));
+  } else if (warp == 1 && cy == 0) {
+    // ===== MMA issuer (the even CTA, for the pair): one accumulator stage per (tile, class) =====
     int s = 0;
     uint32_t ph = 0, nacc = 0;
     const uint32_t sfa = tmem_base + (uint32_t)C_SF_COL, sfb = sfa + 32u;
@@ -177,10 +178,10 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
             for (int k = 0; k < 4; ++k) {  // 32 bytes = 64 e2m1 along K per instruction = +2 in the address field
               const uint64_t da = ((uint64_t)DESC_HI_SW128 << 32) | (uint64_t)(lo_a + 2u * k);
               const uint64_t db = ((uint64_t)DESC_HI_SW128 << 32) | (uint64_t)(lo_b + 2u * k);
-              umma_mxf4(tmem_d, da, db, C_IDESC, (k > 0) ? 1u : (uint32_t)(kb != kb0), sfa, sfb);
+              umma_mxf4_cg2(tmem_d, da, db, C_IDESC, (k > 0) ? 1u : (uint32_t)(kb != kb0), sfa, sfb);
             }
-            umma_commit_mc(empty_bar(s), mask_e);  // three producers write this stage: tell all of them
-            if (kb == kend - 1) umma_commit(tfull_bar(as));
+            umma_commit_cg2(empty_bar(s));                       // the stage is free again in both CTAs
+            if (kb == kend - 1) umma_commit_cg2(tfull_bar(as));  // both halves of the accumulator are complete
           }
           __syncwarp();
           if (++s == CNSTAGE) {
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
         }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===== epilogue: warps 2..9; warp w reads TMEM lanes 32 (w & 3) .. +31 (tile rows), columns 64 h .. 64 h + 63 =====
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const double Meff = P.meff[0];
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
     uint32_t nacc = 0;
     for (int t = first; t < P.ntiles; t += step) {
       const int2 st = P.tiles[t];
-      const int rb = 2 * st.x + cy, cb = 2 * st.y + cx;
+      const int rb = 2 * st.x + cy, cb = st.y;
       double acc[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) acc[j] = 0.0;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));  // the counts are in registers: the next class may overwrite the stage
+        if (lane == 0) mbar_arrive_even(tempty_bar(as));  // the counts are in registers: the next class may overwrite the stage
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[32 + j] = fma(w, (double)__uint_as_float(v[j]), acc[32 + j]);
       }
@@ -260,10 +261,10 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // a neighbour may still multicast into / arrive on this CTA's shared memory until it is done too
+  cluster_sync_all();  // the peer may still arrive on this CTA's barriers / read its shared memory until it is done too
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_TMEM_COLS) : "memory");
   }
 }
 
@@ -485,22 +486,23 @@ int32_t gdca_k_covariance_tc(gdca_ctx *ctx, double pc, bool raw, bool *done) {
     // auto: run on the tensor cores when the model says they win.  Scatter-add engine: M L^2 / 2 additions at the measured
     // 1.36e12 additions/s (18.4 ms at config C); this engine: super-tile rounds x clocks per tile at 1.9 GHz, plus the encode.
     const double t_sparse = 0.5 * (double)M * (double)L * (double)L / 1.36e12;
-    const double rounds = ceil((double)ns * (ns + 1) / 2.0 / (double)(ctx->num_sms / 4));
+    const double rounds = ceil((double)ns * (ns + 1) / (double)(ctx->num_sms / 2));
     const double t_tc = rounds * pl.cost_clk_per_tile * 1.5 / 1.9e9 + (double)n * (double)pl.kblocks * CBK / 3.0e12 + 60e-6;
     if (t_tc >= t_sparse) return GDCA_OK;
   }
   const long long Kbytes = pl.kblocks * CBK, Mk = pl.kblocks * CSEQ;
   const int nseg = (int)pl.seg_end.size();
-  // ---- super-tiles of the lower triangle, in bands of 6 super-rows with the row varying fastest (the clusters running at one
-  // time share a few row blocks: Xt streams from HBM about once per band); dealt round-robin to the members of a device group
+  // ---- pair tiles of the lower triangle: (RB2, CB) = row blocks 2 RB2, 2 RB2 + 1 x column block CB, in bands of 8 pair rows with the
+  // row varying fastest (the pairs running at one time share a few row and column blocks: Xt streams from HBM about once per band);
+  // dealt round-robin to the members of a device group
   std::vector<int2> tiles;
   {
-    constexpr int BH = 6;
+    constexpr int BH = 8;
     long long idx = 0;
     for (int r0 = 0; r0 < ns; r0 += BH) {
       const int r1 = std::min(ns, r0 + BH);
-      for (int c = 0; c < r1; ++c)
-        for (int r = std::max(r0, c); r < r1; ++r, ++idx)
+      for (int c = 0; c < std::min(nblk, 2 * r1); ++c)
+        for (int r = std::max(r0, c / 2); r < r1; ++r, ++idx)
           if (idx % ctx->shard_world == ctx->shard_rank) tiles.push_back(make_int2(r, c));
     }
   }
@@ -563,17 +565,17 @@ int32_t gdca_k_covariance_tc(gdca_ctx *ctx, double pc, bool raw, bool *done) {
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cfg.gridDim = dim3((unsigned)(ctx->num_sms / 4 * 4));
+  cfg.gridDim = dim3((unsigned)(ctx->num_sms / 2 * 2));
   int max_clusters = 0;
   GDCA_CUDA(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, cov_tc_kernel, &cfg));
-  int nclusters = std::min(std::min(max_clusters, ctx->num_sms / 4), std::max(ntiles, 1));
-  if (nclusters < 1) return gdca_fail(ctx, GDCA_ERR_CUDA, "covariance (tensor cores): no 4-CTA cluster fits on this device");
-  cfg.gridDim = dim3((unsigned)(4 * nclusters));
+  int nclusters = std::min(std::min(max_clusters, ctx->num_sms / 2), std::max(ntiles, 1));
+  if (nclusters < 1) return gdca_fail(ctx, GDCA_ERR_CUDA, "covariance (tensor cores): no CTA pair fits on this device");
+  cfg.gridDim = dim3((unsigned)(2 * nclusters));
   GDCA_CUDA(ctx, cudaEventRecord(ctx->ev_cov0, ctx->stream));
   GDCA_CUDA(ctx, cudaLaunchKernelEx(&cfg, cov_tc_kernel, map, P));
   GDCA_LAUNCH_CHECK(ctx);
@@ -582,8 +584,8 @@ int32_t gdca_k_covariance_tc(gdca_ctx *ctx, double pc, bool raw, bool *done) {
   ctx->cov_tc_segments = nseg;
   ctx->cov_tc_clusters = nclusters;
   // 128 x 128 x 256 MMA work of every CTA tile visited (incl. the padded / mirrored tiles of diagonal super-tiles)
-  ctx->cov_tc_tflop = 2.0 * CT * CT * (double)Mk * 4.0 * (double)ntiles * 1e-12;
-  ctx->cov_tc_l2_bytes = (double)ntiles * 4.0 * (double)pl.kblocks * (CSTAGE_BYTES / 2);
+  ctx->cov_tc_tflop = 2.0 * CT * CT * (double)Mk * 2.0 * (double)ntiles * 1e-12;
+  ctx->cov_tc_l2_bytes = (double)ntiles * 2.0 * (double)pl.kblocks * CSTAGE_BYTES;
   *done = true;
   return GDCA_OK;
 }

@@ -99,6 +99,35 @@ __device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t da, uint64_t
       : "memory");
 }
 
+// ---- cta_group::2: one MMA across a CTA pair (M = 256), issued by the even CTA ----
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
+// executed by both CTAs: the bytes land in the issuing CTA's shared memory, the transaction count on the EVEN CTA's barrier
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_mxf4_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+// arrives on the mbarrier at this offset in both CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// plain arrival on the EVEN CTA's barrier at this offset (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_even(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+
 // 32 consecutive 32-bit columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
