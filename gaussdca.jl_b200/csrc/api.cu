@@ -279,6 +279,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaEventCreate(&ctx->ev_cov0)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreate(&ctx->ev_cov1)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dNItems, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dCovSync, sizeof(unsigned int))) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_TC_FILTER")) {
     const int m = atoi(env);
     if (m >= 0 && m <= 2) ctx->tc_filter_mode = m;
@@ -293,6 +294,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
     const int v = atoi(env);
     if (v >= 0 && v <= 2) ctx->tc_filter_want_multicast = v;
   }
+  if (const char *env = getenv("GDCA_COV_ROUND_SYNC")) ctx->cov_round_sync = atoi(env);
   if (const char *env = getenv("GDCA_COV_ENGINE")) {
     const int m = atoi(env);
     if (m >= 0 && m <= 2) ctx->cov_engine = m;
@@ -326,7 +328,7 @@ void gdca_destroy(gdca_ctx *ctx) {
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
                   ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask,
                   ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax, ctx->dCellBase, ctx->dDigP, ctx->dScaleP,
-                  ctx->dClsHist, ctx->dClsPerm, ctx->dClsTab, ctx->dXt, ctx->dCovTiles, ctx->dSegCnt};
+                  ctx->dClsHist, ctx->dClsPerm, ctx->dClsTab, ctx->dXt, ctx->dCovTiles, ctx->dSegCnt, ctx->dCovSync};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)

@@ -17,15 +17,21 @@
 // Pieces:
 //   * classes: histogram of the counts, compacted on the device, planned on the host (a few hundred bytes cross PCIe): class c
 //     gets a run of whole 256-sequence k-blocks, padded with empty columns; `perm` lists the sequences in that order;
-//   * operand: Xt[(i,a)][kpos] = [Z[i, perm[kpos]] == a] as packed e2m1 (1.0 = 0x2), K-major, n x Mk/2 bytes (1.03 GB at C);
-//   * GEMM: Xt Xt' over the lower triangle of 128 x 128 output tiles.  Clusters of 2 x 2 CTAs own 256 x 256 super-tiles: every
-//     CTA fetches HALF of its A tile and HALF of its B tile and TMA-multicasts them to its row / column neighbour, so one
-//     k-block costs 16 KB of L2 reads per CTA instead of 32 KB (the kernel is L2-bandwidth bound without it: 120 B/clk/SM).
-//     Per CTA: warp 0 = TMA producer (6-stage ring of 32 KB), warp 1 = tcgen05.mma issuer, warps 2..9 = epilogue.  Two
+//   * operand: Xt[(i,a)][kpos] = [Z[i, perm[kpos]] == a] as packed e2m1 (1.0 = 0x2), K-major, n x Mk/2 bytes (1.03 GB at C).
+//     While a warp encodes a k-block it also counts, per state, the sequences of that class segment carrying the state at the
+//     site: Pi = sum_c w_c n_c(i,a) / Meff comes from the same exact integers (no per-site lists on this path at all);
+//   * GEMM: Xt Xt' over the lower triangle of 128 x 128 output tiles.  CTA PAIRS (clusters of 2) issue ONE
+//     tcgen05.mma.cta_group::2 of 256 x 128: the even CTA issues for both, every CTA keeps its own A tile (its 128 output rows)
+//     and only HALF of the B tile -- the tensor cores read the other half from the peer's shared memory -- so 24 KB instead of
+//     32 KB of operands arrive in every SM per k-block (the L2 -> SM path delivers ~64-70 B/clk/SM, which capped the first,
+//     2 x 2-cluster multicast version of this kernel at 0.42 of the FP4 rate).  The barriers of the pair live in the even CTA:
+//     both producers' TMA bytes are counted there (cp.async.bulk.tensor.cta_group::2), one tcgen05.commit.cta_group::2 frees
+//     a stage in both CTAs, the epilogue warps of both CTAs release the accumulator stage there.
+//     Per CTA: warp 0 = TMA producer (9-stage ring of 24 KB), warp 1 = MMA issuer (even CTA), warps 2..9 = epilogue.  Two
 //     accumulator stages of 128 TMEM columns: while the MMAs of class c+1 run, the epilogue drains class c
 //     (tcgen05.ld -> FP64 -> acc += w_c * N_c, 64 FP64 accumulators per thread in registers).  After the last class the fused
 //     epilogue of cov.cu (1/Meff, pseudocount, - Pi Pi') writes the tile and its mirror image.
-//   * device groups: super-tiles dealt round-robin, stored straight into the leader's C (disjoint, no reduction).
+//   * device groups: pair tiles dealt round-robin, stored straight into the leader's C (disjoint, no reduction).
 #include <algorithm>
 #include <vector>
 
@@ -65,6 +71,7 @@ struct CovTcParams {
   long long n, ld;
   int s, q, raw;
   double pc;
+  unsigned int *round_sync;  // producers that have started their j-th tile (nullptr: free running)
 };
 
 __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_constant__ CUtensorMap tmap, CovTcParams P) {
@@ -133,7 +140,21 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
     // ===== TMA producer (both CTAs): my A tile (two 64-row boxes) and MY half of the B tile; the even CTA's barrier counts it all
     int s = 0;
     uint32_t ph = 0;
+    unsigned round = 0;
     for (int t = first; t < P.ntiles; t += step) {
+      if (P.round_sync) {
+        // Long operand rows (K in the millions): the pairs running at one time share a few row and column blocks, but only pairs
+        // that walk K TOGETHER find each other's rows in L2.  Every producer checks in when it starts its j-th tile and waits
+        // -- for a bounded time: this is a hint, never a dependency -- until the others have started theirs.
+        if (lane == 0) {
+          atomicAdd(P.round_sync, 1u);
+          const unsigned target = (round + 1) * gridDim.x;
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile unsigned int *>(P.round_sync) < target && clock64() - t0 < 200000) __nanosleep(200);
+        }
+        __syncwarp();
+        ++round;
+      }
       const int2 st = P.tiles[t];
       const int row_a = (2 * st.x + cy) * CT;
       const int row_b = st.y * CT + cy * 64;
@@ -558,6 +579,12 @@ int32_t gdca_k_covariance_tc(gdca_ctx *ctx, double pc, bool raw, bool *done) {
   P.q = ctx->q;
   P.raw = raw ? 1 : 0;
   P.pc = pc;
+  // round hint of the producers: when the operand is several times the size of the L2 cache (1 GB at config C, 15 GB at E: kernel 350 -> 146 ms there)
+  P.round_sync = nullptr;
+  if (ctx->cov_round_sync == 1 || (ctx->cov_round_sync < 0 && (double)n * (double)Kbytes > 5.0e8)) {
+    P.round_sync = ctx->dCovSync;
+    GDCA_CUDA(ctx, cudaMemsetAsync(P.round_sync, 0, sizeof(unsigned int), ctx->stream));
+  }
   GDCA_CUDA(ctx, cudaFuncSetAttribute(cov_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(C_THREADS);
