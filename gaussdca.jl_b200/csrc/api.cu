@@ -321,6 +321,7 @@ void gdca_destroy(gdca_ctx *ctx) {
     if (m) cudaIpcCloseMemHandle(m);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   gdca_k_inverse_release(ctx);
+  if (ctx->hostTab) cudaFreeHost(ctx->hostTab);
   gdca_h2d_release(ctx);
   if (!ctx->dZ_borrowed) cudaFree(ctx->dZ);
   void *bufs[] = {ctx->dZt,  ctx->dZq, ctx->dPerm, ctx->dPlanes, ctx->dCounts, ctx->dHam,  ctx->dQ,   ctx->dW,    ctx->dMeff, ctx->dList,
