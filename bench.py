@@ -530,8 +530,10 @@ def main():
         tc_peak = 9000.0 if fp4 else 4500.0     # nominal dense FP4 / FP8 = INT8 (B200_PROFILING.md table)
         scaled = (4.0 if fp4 else 2.0) * bf16 if bf16 else None
         t_f = ms_f.value / 1e3
+        fmode = int(lib.gdca_dev_tc_filter_launch_mode(ctx.h))
         sweep_entry = {
-            "kernel": ("tc_filter_kernel<fp4> (tcgen05 kind::mxf4.block_scale 128x224x64" if fp4 else
+            "kernel": ("tc_filter_kernel<fp4> (one tcgen05.mma.cta_group::2 kind::mxf4.block_scale 256x224x64 per CTA pair" if fp4 and fmode == 2 else
+                       "tc_filter_kernel<fp4> (tcgen05 kind::mxf4.block_scale 128x224x64" if fp4 else
                        "tc_filter_kernel<int8> (tcgen05 kind::i8 128x256x32" if filt.value == 80 else
                        "tc_filter_kernel<fp8> (tcgen05 kind::f8f6f4 128x256x32") + ", TMA ring, TMEM epilogue)"
                       + ("" if world == 1 else f", shard {rank} of {world}"),
@@ -544,7 +546,10 @@ def main():
                                           if scaled else None),
             "ms_per_launch": t_f * 1e3, "tiles": int(f_tiles.value), "flop_per_launch": f_tflop.value * 1e12,
             "l2_operand_bytes_per_launch": f_l2.value, "l2_operand_tb_per_s": f_l2.value / t_f / 1e12,
-            "traffic": (ncu_traffic(f"tc_filter_kernel<{int(fp4)}, 1>") or ncu_traffic(f"tc_filter_kernel<{int(fp4)}, 0>"))
+            "tensor_pipe_note": ("ncu (profiles/r2_top_kernels.md): sm__pipe_tensor_cycles_active 99.9 % -- the pipe is saturated; "
+                                 "the nominal 9 PFLOP/s is not reachable with 128x224x64 MMAs at this clock") if fp4 and fmode == 2 else None,
+            "traffic": (ncu_traffic(f"tc_filter_kernel<{int(fp4)}, {fmode}>") or ncu_traffic(f"tc_filter_kernel<{int(fp4)}, 1>") or
+                        ncu_traffic(f"tc_filter_kernel<{int(fp4)}, 0>"))
                        if world == 1 and name == "C" else None,
             "exact_sweep": exact, **common,
         }

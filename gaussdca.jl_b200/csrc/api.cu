@@ -580,6 +580,8 @@ int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_ti
   return GDCA_OK;
 }
 
+int32_t gdca_dev_tc_filter_launch_mode(gdca_ctx *ctx) { return ctx ? ctx->tc_filter_multicast : -1; }
+
 int32_t gdca_dev_cov_kernel_ms(gdca_ctx *ctx, float *ms) {
   if (!ctx || !ms) return GDCA_ERR_INVALID_ARG;
   GDCA_TRY(set_device(ctx));

@@ -175,6 +175,9 @@ int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t rank, int32_t
  * flop (1e12) and TMA operand bytes; 128x128 blocks that went through the exact sweep; device ms of the two parts. */
 int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
                             int64_t *swept_blocks, float *ms_filter, float *ms_exact, double *filter_l2_bytes);
+/* how the last prefilter launch ran: 0 independent CTAs, 1 2-CTA clusters with TMA multicast of the column tile, 2 CTA pairs issuing
+ * one tcgen05.mma.cta_group::2 of 256 x 224 (FP4 operands; the default) */
+int32_t gdca_dev_tc_filter_launch_mode(gdca_ctx *ctx);
 /* device ms of the last cov_rows_kernel / cov_tc_kernel launch alone (the covariance stage also runs small preparation kernels) */
 int32_t gdca_dev_cov_kernel_ms(gdca_ctx *ctx, float *ms);
 /* Engine of the frequency / covariance stage (DCAUtils compute_weighted_frequencies, call site src/GaussDCA.jl:28):
