@@ -1039,7 +1039,7 @@ static int32_t inverse_enqueue(gdca_ctx *ctx, InvCapture *cap) {
         // chain waits for at the next boundary, then the rest -- so the chain never stalls behind a whole bulk update.  The panel
         // digits alternate between two buffers: the second part of the previous bulk may still be reading the other one (it is
         // complete once the first part of THIS bulk's predecessor has been waited for: the helper stream runs them in order).
-        const bool split = N == 1;
+        const bool split = !share;  // also on the leader of a device group while the factorisation itself is not shared
         int8_t *pdig = (split && (sidx & 1)) ? ctx->dDigA : ctx->dDigB;
         double *pscale = (split && (sidx & 1)) ? ctx->dScaleA : ctx->dScaleB;
         gdca_oz_operand P{};

@@ -138,7 +138,7 @@ struct gdca_ctx {
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev_sent = nullptr;               // this member's block columns have arrived at the leader (shared factorisation)
   cudaEvent_t ev_upd = nullptr;                // this member's compute stream has finished the columns it is about to send
-  int share_min_nb = 128;                      // the trailing update of the factorisation is shared by the group from this many 128-blocks on (env GDCA_SHARE_MIN_NB)
+  int share_min_nb = 64;                       // the trailing update of the factorisation is shared by the group from this many 128-blocks on (env GDCA_SHARE_MIN_NB)
 
   // ---- pageable host memory: pipelined H2D through a pinned ring (stage_copy.cpp) ----
   void *stage_buf[GDCA_STAGE_SLOTS] = {};

@@ -94,6 +94,32 @@ def test_small_alphabets_and_q31(pkg, orc, tc):
         assert np.array_equal(Pij_t, Pij_t.T) and normwise(Pij_t, Pij_o) <= 1e-14, (q, normwise(Pij_t, Pij_o))
 
 
+def test_degenerate_shapes_on_tensor_cores(pkg, orc, tc):
+    """One site, two sequences, a single class, a class per sequence, M far below one k-block: the engine pads, never mixes."""
+    rng = np.random.default_rng(5)
+    for L, M, theta in [(1, 5, 0.0), (2, 2, 0.3), (3, 40, "auto"), (9, 257, 0.2), (31, 513, 0.9), (5, 1000, 1.0)]:
+        Z = rng.integers(1, 22, size=(M, L), dtype=np.int8)
+        Z[0, 0] = 21
+        q = int(Z.max())
+        Pi_o, Pij_o, Meff_o, W_o, _ = orc.compute_weighted_frequencies(Z, q, theta)
+        Pi_t, Pij_t, Meff, W = pkg.compute_weighted_frequencies(Z, q, theta, ctx=tc)
+        assert tc.cov_info()["engine"] == 2, (L, M)
+        assert Meff == Meff_o and np.array_equal(W, W_o)
+        assert np.array_equal(Pij_t, Pij_t.T)
+        assert normwise(Pi_t, Pi_o) <= 1e-14 and normwise(Pij_t, Pij_o) <= 1e-14, (L, M, theta)
+
+
+def test_prefilter_and_inversion_report_how_they_ran(pkg, orc, ctx):
+    """The default launch modes of this build: CTA pairs with cta_group::2 for the prefilter, the sliced INT8 engine for n >= 2048."""
+    Z = orc.synth_alignment(128, 17000, seed=3)        # M >= 16384: prefilter on; n = 2560: sliced inversion
+    pkg.gdca_from_alignment(Z, ctx=ctx)
+    assert ctx.lib.gdca_dev_tc_filter_launch_mode(ctx.h) == 2
+    import ctypes
+    mode = ctypes.c_int32()
+    ctx.check(ctx.lib.gdca_dev_inverse_info(ctx.h, ctypes.byref(mode), None, None))
+    assert mode.value == 1
+
+
 def test_many_weight_classes_fall_back_to_the_scatter_engine(pkg, orc, tc):
     """More than 512 distinct neighbour counts: engine 2 is a request, the scatter-add engine still answers."""
     L, groups = 24, 560
