@@ -82,6 +82,8 @@ SIGNATURES = {
     "gdca_dev_tc_filter": (_i32, [_p, _i64, _p, _p, _i64]),
     "gdca_dev_cov_kernel_ms": (_i32, [_p, ctypes.POINTER(ctypes.c_float)]),
     "gdca_dev_tc_filter_launch_mode": (_i32, [_p]),
+    "gdca_set_pair_list": (_i32, [_p, _i32]),
+    "gdca_dev_pair_list_info": (_i32, [_p, _pi64, _pi64]),
     "gdca_set_cov_engine": (_i32, [_p, _i32]),
     "gdca_dev_cov_info": (_i32, [_p, _pi32, _pi32, _pi32, _pi64, _pi32, _pdbl, _pdbl]),
     "gdca_set_tc_filter_bits": (_i32, [_p, _i32]),

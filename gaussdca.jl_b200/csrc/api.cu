@@ -280,6 +280,8 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if ((e = cudaEventCreate(&ctx->ev_cov1)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dNItems, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void **)&ctx->dCovSync, sizeof(unsigned int))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void **)&ctx->dNPairs, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(ctx->dNPairs, 0, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
   if (const char *env = getenv("GDCA_TC_FILTER")) {
     const int m = atoi(env);
     if (m >= 0 && m <= 2) ctx->tc_filter_mode = m;
@@ -290,6 +292,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   }
   if (const char *env = getenv("GDCA_STAGED_H2D")) ctx->staged_h2d = atoi(env) != 0;
   if (const char *env = getenv("GDCA_CELL_SWEEP")) ctx->cell_sweep = atoi(env) != 0;
+  if (const char *env = getenv("GDCA_PAIR_LIST")) ctx->pair_list = atoi(env) != 0;
   if (const char *env = getenv("GDCA_TC_MULTICAST")) {
     const int v = atoi(env);
     if (v >= 0 && v <= 2) ctx->tc_filter_want_multicast = v;
@@ -329,7 +332,7 @@ void gdca_destroy(gdca_ctx *ctx) {
                   ctx->dS,   ctx->dS2,     ctx->dRed, ctx->dKeys, ctx->dVals, ctx->dR,
                   ctx->dV,   ctx->dFlags,  ctx->dItems, ctx->dNItems, ctx->dItemMask,
                   ctx->dDigA, ctx->dDigB,  ctx->dScaleA, ctx->dScaleB, ctx->dOzMax, ctx->dCellBase, ctx->dDigP, ctx->dScaleP,
-                  ctx->dClsHist, ctx->dClsPerm, ctx->dClsTab, ctx->dXt, ctx->dCovTiles, ctx->dSegCnt, ctx->dCovSync};
+                  ctx->dClsHist, ctx->dClsPerm, ctx->dClsTab, ctx->dXt, ctx->dCovTiles, ctx->dSegCnt, ctx->dCovSync, ctx->dPairs, ctx->dNPairs};
   for (void *b : bufs)
     if (b) cudaFree(b);
   for (int i = 0; i < 16; ++i)
@@ -505,6 +508,23 @@ int32_t gdca_set_tc_filter(gdca_ctx *ctx, int32_t mode) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   if (mode < 0 || mode > 2) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_tc_filter: mode must be 0, 1 or 2");
   ctx->tc_filter_mode = mode;
+  return GDCA_OK;
+}
+
+int32_t gdca_set_pair_list(gdca_ctx *ctx, int32_t on) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  ctx->pair_list = on != 0;
+  return GDCA_OK;
+}
+
+int32_t gdca_dev_pair_list_info(gdca_ctx *ctx, int64_t *candidates, int64_t *capacity) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  GDCA_TRY(set_device(ctx));
+  unsigned long long n = 0;
+  GDCA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  GDCA_CUDA(ctx, cudaMemcpy(&n, ctx->dNPairs, sizeof n, cudaMemcpyDeviceToHost));
+  if (candidates) *candidates = (int64_t)n;
+  if (capacity) *capacity = (int64_t)ctx->pair_cap;
   return GDCA_OK;
 }
 

@@ -90,6 +90,10 @@ struct gdca_ctx {
   unsigned long long *dNItems = nullptr;           // [1] low word: its length; high word: flagged 32 x 32 cells in it
   uint32_t *dCellBase = nullptr; size_t capCellBase = 0;  // flagged cells in front of every listed block
   int have_V = 0;                                  // 0: dV stale; 8 / 4 / 80: dV holds the FP8 / FP4 / INT8 encoding of the loaded alignment
+  int pair_list = 1;                               // the prefilter lists the candidate PAIRS (projected distance below thresh) and the exact stage checks those alone (env GDCA_PAIR_LIST=0: sweep the flagged cells)
+  int2 *dPairs = nullptr; size_t capPairs = 0;     // candidate pairs (k < l)
+  unsigned long long *dNPairs = nullptr;           // [1] candidates found (keeps counting past the capacity)
+  unsigned long long pair_cap = 0;                 // capacity of dPairs in the last filter launch (0: no list)
   int cell_sweep = 1;                              // behind the prefilter: sweep flagged CELLS, one warp each (env GDCA_CELL_SWEEP=0: blocks)
   int tc_filter_mode = 1;                          // 0 off, 1 auto (large M), 2 always (tests)
   int tc_filter_bits = 4;                          // operands of the filter: 4 = e2m1 (kind::mxf4), 8 = e4m3 (kind::f8f6f4), 80 = int8 (kind::i8)

@@ -73,6 +73,7 @@ struct Cfg {
 constexpr int CG2_STAGE_BYTES = BM * BK + (224 / 2) * BK;  // 30 KB
 constexpr int CG2_NSTAGE = 7;
 constexpr size_t CG2_SMEM = (size_t)CG2_NSTAGE * CG2_STAGE_BYTES + 1024;
+constexpr int PAIR_CHUNK = 256;                            // candidate pairs an epilogue warp reserves at a time
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                // shared::cluster address of the same offset in the even CTA of the pair
 
 struct FilterParams {
@@ -82,6 +83,13 @@ struct FilterParams {
   uint32_t *flags;      // [T][T] cell masks: bit 4*(row/32) + (col/32) of block (bi, bj)
   float *dump;          // tests only: S of every visited tile, [T*128][dump_ld]
   long long dump_ld;
+  // candidate PAIRS: every (k, l), k < l < M, whose projected distance is below thresh (S > bound) is appended here; the exact
+  // stage then checks these pairs alone (pairs.cu: pair_list_kernel).  The counter keeps counting past the capacity: a list
+  // that overflowed is ignored and the flagged cells are swept instead.
+  int2 *pairs;
+  unsigned long long *npairs;
+  unsigned long long pair_cap;
+  long long M;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -455,6 +463,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int row = quarter * 32 + lane;
     TileIter it;
     uint32_t n = 0;
+    // this warp's chunk of the candidate-pair list (warp-uniform)
+    unsigned long long chunk_base = 0;
+    int chunk_used = PAIR_CHUNK;   // "full": the first candidates reserve a chunk
+    bool chunk_ok = false;
     for (it.start(P, BN, first); !it.done(); it.advance(step)) {
       if (!(it.valid() || (MC && it.peer_valid()))) continue;
       const int bi = it.bi(), cj = it.cj();
@@ -487,13 +499,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int cb = (int)(col0 >> 7);
         if (hit && lane == 0 && mine && cb >= bi && cb < P.T)
           atomicOr(P.flags + (long long)bi * P.T + cb, 1u << (quarter * 4 + (int)((col0 >> 5) & 3)));
+        if (hit && mine && P.pairs) {  // rare: one warp-aggregated reservation, then every lane writes its own candidates
+          const int k = bi * BM + row;
+          unsigned m = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sv = OP == OP_I8 ? (float)(int)v[j] : __uint_as_float(v[j]);
+            m |= (unsigned)(sv > P.bound) << j;
+          }
+          // columns l = col0 + j with k < l < M: the bits [lo, hi)
+          const int c0i = (int)col0;
+          const int lo = max(0, k + 1 - c0i), hi = min(32, (int)P.M - c0i);
+          m = (lo < hi) ? (m >> lo << lo) & (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) : 0u;
+          const int mine_n = __popc(m);
+          // exclusive prefix over the lanes that hold candidates (usually one or two of them)
+          unsigned holders = __ballot_sync(0xffffffffu, m != 0);
+          int total = 0, before = 0;
+          while (holders) {
+            const int src = __ffs(holders) - 1;
+            holders &= holders - 1;
+            const int cnt = __shfl_sync(0xffffffffu, mine_n, src);
+            if (lane == src) before = total;
+            total += cnt;
+          }
+          const int incl = before + mine_n;
+          if (total) {
+            // slots come out of this warp's current CHUNK of the list; a new chunk costs one global atomic (a single counter cannot
+            // take one atomic per flagged cell: 4.3 M of them on the shuffled config C cost 9 ms), the rest of the old chunk is
+            // marked empty (k = -1)
+            if (total > PAIR_CHUNK / 2) {
+              // a dense cell (up to 1024 candidates): its own run of the list, exactly as long as needed
+              unsigned long long nb = 0;
+              if (lane == 0) nb = atomicAdd(P.npairs, (unsigned long long)total);
+              nb = __shfl_sync(0xffffffffu, nb, 0);
+              if (nb + (unsigned long long)total <= P.pair_cap) {
+                unsigned long long at = nb + (unsigned long long)(incl - mine_n);
+                while (m) {
+                  const int j = __ffs(m) - 1;
+                  m &= m - 1;
+                  P.pairs[at++] = make_int2(k, c0i + j);
+                }
+              }
+              return;
+            }
+            if (chunk_used + total > PAIR_CHUNK) {
+              if (chunk_ok)
+                for (int i = chunk_used + lane; i < PAIR_CHUNK; i += 32) P.pairs[chunk_base + i] = make_int2(-1, -1);
+              unsigned long long nb = 0;
+              if (lane == 0) nb = atomicAdd(P.npairs, (unsigned long long)PAIR_CHUNK);
+              chunk_base = __shfl_sync(0xffffffffu, nb, 0);
+              chunk_ok = chunk_base + PAIR_CHUNK <= P.pair_cap;
+              chunk_used = 0;
+            }
+            if (chunk_ok) {
+              unsigned long long at = chunk_base + (unsigned long long)(chunk_used + incl - mine_n);
+              while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                P.pairs[at++] = make_int2(k, c0i + j);
+              }
+            }
+            chunk_used += total;
+          }
+        }
       };
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+      // two register buffers: the tcgen05.ld of the next cell is in flight while this one is reduced (with candidate pairs to
+      // emit the epilogue of a tile no longer hides behind the MMAs of the next by itself when the flags are dense)
+      constexpr int NC = BN / 32;
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, va);
+#pragma unroll
+      for (int c = 0; c < NC; c += 2) {
         tmem_ld_wait();
-        reduce_cell(v, c);
+        if (c + 1 < NC) tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vb);
+        reduce_cell(va, c);
+        if (c + 1 < NC) {
+          tmem_ld_wait();
+          if (c + 2 < NC) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
+          reduce_cell(vb, c + 1);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -504,6 +588,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           mbar_arrive(tempty_bar(as));
       }
     }
+    if (chunk_ok)  // the unused rest of this warp's last chunk
+      for (int i = chunk_used + lane; i < PAIR_CHUNK; i += 32) P.pairs[chunk_base + i] = make_int2(-1, -1);
   }
 
   tc_fence_before();
@@ -671,6 +757,22 @@ int32_t run_filter(gdca_ctx *ctx, int thresh, float *dump, long long dump_ld) {
   P.flags = ctx->dFlags;
   P.dump = dump;
   P.dump_ld = dump_ld;
+  P.M = ctx->M;
+  P.pairs = nullptr;
+  P.npairs = ctx->dNPairs;
+  P.pair_cap = 0;
+  if (ctx->pair_list) {
+    // capacity: 32 candidates per sequence (16 M at least, 256 M at most): far above what a weighted alignment produces; an
+    // alignment of near-duplicates overflows it and takes the cell sweep
+    unsigned long long cap = 32ull * (unsigned long long)ctx->M;
+    if (cap < (1ull << 24)) cap = 1ull << 24;
+    if (cap > (1ull << 28)) cap = 1ull << 28;
+    GDCA_TRY(gdca_reserve(ctx, ctx->dPairs, ctx->capPairs, (size_t)cap));
+    P.pairs = ctx->dPairs;
+    P.pair_cap = cap;
+  }
+  ctx->pair_cap = P.pair_cap;
+  GDCA_CUDA(ctx, cudaMemsetAsync(ctx->dNPairs, 0, sizeof(unsigned long long), ctx->stream));
   auto launch = [&](auto kern, int threads, bool cluster) -> int32_t {
     const size_t smem = cg2 ? CG2_SMEM : C::SMEM;
     GDCA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -175,6 +175,13 @@ int32_t gdca_tc_filter_tile_order(int32_t T, int32_t bits, int32_t rank, int32_t
  * flop (1e12) and TMA operand bytes; 128x128 blocks that went through the exact sweep; device ms of the two parts. */
 int32_t gdca_dev_sweep_info(gdca_ctx *ctx, int32_t *filtered, int64_t *filter_tiles, double *filter_tflop,
                             int64_t *swept_blocks, float *ms_filter, float *ms_exact, double *filter_l2_bytes);
+/* Exact stage behind the prefilter: 1 (default; env GDCA_PAIR_LIST) = the prefilter lists every candidate PAIR (projected distance
+ * below the threshold) and the exact stage checks those pairs alone, byte by byte on the alignment itself -- the cost no longer
+ * depends on how the sequences are ordered; 0 = sweep the flagged 32 x 32 cells on the bit planes.  A list that overflows its
+ * capacity (32 candidates per sequence) is dropped on the device and the cells are swept.  Counts are identical either way.
+ * gdca_dev_pair_list_info: candidates found by the last sweep and the capacity of the list (0: no list). */
+int32_t gdca_set_pair_list(gdca_ctx *ctx, int32_t on);
+int32_t gdca_dev_pair_list_info(gdca_ctx *ctx, int64_t *candidates, int64_t *capacity);
 /* how the last prefilter launch ran: 0 independent CTAs, 1 2-CTA clusters with TMA multicast of the column tile, 2 CTA pairs issuing
  * one tcgen05.mma.cta_group::2 of 256 x 224 (FP4 operands; the default) */
 int32_t gdca_dev_tc_filter_launch_mode(gdca_ctx *ctx);
