@@ -507,8 +507,19 @@ def main():
     Mpad = (M + 127) // 128 * 128
     hbm_bytes = 4 * nwords * 5 * Mpad + 4 * M     # packed planes once + counts
     t_exact = (ms_x.value / 1e3) if filt.value else t_pair
+    cand, pcap = ctypes.c_int64(), ctypes.c_int64()
+    ctx.check(lib.gdca_dev_pair_list_info(ctx.h, ctypes.byref(cand), ctypes.byref(pcap)))
+    pair_path = bool(filt.value) and pcap.value > 0 and cand.value <= pcap.value
     exact = {
-        "kernel": "pair_sweep_kernel<5,1> (exact neighbour counts, per-warp early exit)",
+        "kernel": "pair_list_kernel (exact Hamming distance of the candidate pairs the prefilter lists: one warp per pair, byte compares on the alignment itself) + compact_flags_kernel",
+        "bound": "hbm", "achieved": cand.value * 2.0 * L / t_exact / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+        "frac": (cand.value * 2.0 * L / t_exact / 1e9 / pk["hbm_gbs"]) if pk.get("hbm_gbs") else None,
+        "ms_per_launch": t_exact * 1e3, "candidate_pairs": int(cand.value), "list_capacity": int(pcap.value),
+        "note": "2 L bytes per candidate, mostly L2 hits (the alignment is 100 MB); the stage is latency / launch bound at this size "
+                "(< 1 ms): its cost follows the number of candidates -- true neighbour pairs plus what the 4-class projection cannot "
+                "tell apart -- not their spread over the pair matrix",
+    } if pair_path else {
+        "kernel": "cell_sweep_kernel<5> / pair_sweep_kernel<5,1> (exact neighbour counts on the bit planes, per-warp early exit)",
         "bound": "int32_alu", "achieved": alu_ops / t_exact / 1e12, "peak": lop3.value, "unit": "Tlop3/s",
         "frac": (alu_ops / t_exact / 1e12) / lop3.value, "ms_per_launch": t_exact * 1e3,
         "blocks_swept": int(s_blocks.value), "blocks_total": (Mpad // 128) * (Mpad // 128 + 1) // 2 // world,
