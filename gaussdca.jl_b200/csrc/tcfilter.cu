@@ -17,7 +17,7 @@
 //
 // The M x M x 3L contraction runs as  V V^T  with V = [rows][3L padded to whole 128-byte k-blocks], K-major:
 //   * one persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane),
-//     warps 2..5 = epilogue (one TMEM lane quarter each);
+//     warps 2..9 = epilogue (two per TMEM lane quarter, alternate 32 x 32 cells);
 //   * operand variants of one kernel template:
 //       FP4 (default)  packed e2m1 +-1.0, kind::mxf4.block_scale.block32, UMMA 128 x 224 x 64, two accumulator stages of
 //                      224 TMEM columns + 64 columns of UE8M0 scale factors that are all 1.0 (written once with tcgen05.st:
@@ -41,7 +41,7 @@ namespace {
 constexpr int BM = 128;              // tile rows (sequences)
 constexpr int BK = 128;              // K bytes per stage (= SWIZZLE_128B atom width)
 constexpr int MAX_STAGE = 7;
-constexpr int TC_THREADS = 192;       // warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue
+constexpr int TC_THREADS = 320;       // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter: alternate cells)
 constexpr int TMEM_COLS = 512;
 constexpr int BAND = 16;             // row blocks per band of the tile order
 
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), CG2 ? 8 : 4);  // one arrival per epilogue warp (cta_group::2: of both CTAs, on the even CTA's barrier)
+      mbar_init(tempty_bar(a), CG2 ? 16 : 8);  // one arrival per epilogue warp (cta_group::2: of both CTAs, on the even CTA's barrier)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (FP4 && warp >= 2) {
+  if (FP4 && warp >= 2 && warp < 6) {
     // UE8M0 scale factors, all 2^0: every byte of the 64 scale columns of all 128 lanes is 0x7F
     const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)C::SF_COL;
     tmem_st32_fill(t, 0x7F7F7F7Fu);
@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if (warp >= 2) {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32 (w & 3) .. +31 = tile rows =====
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;  // this warp reduces the cells half, half + 2, ... of its lane quarter
     const int row = quarter * 32 + lane;
     TileIter it;
     uint32_t n = 0;
@@ -567,16 +568,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // emit the epilogue of a tile no longer hides behind the MMAs of the next by itself when the flags are dense)
       constexpr int NC = BN / 32;
       uint32_t va[32], vb[32];
-      tmem_ld32(taddr, va);
+      tmem_ld32(taddr + (uint32_t)(half * 32), va);
 #pragma unroll
-      for (int c = 0; c < NC; c += 2) {
-        tmem_ld_wait();
-        if (c + 1 < NC) tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vb);
-        reduce_cell(va, c);
-        if (c + 1 < NC) {
+      for (int i = 0; i < (NC + 1) / 2; i += 2) {
+        const int c0 = half + 2 * i, c1 = c0 + 2, c2 = c0 + 4;  // warp-uniform
+        if (c0 < NC) {
           tmem_ld_wait();
-          if (c + 2 < NC) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
-          reduce_cell(vb, c + 1);
+          if (c1 < NC) tmem_ld32(taddr + (uint32_t)(c1 * 32), vb);
+          reduce_cell(va, c0);
+        }
+        if (c1 < NC) {
+          tmem_ld_wait();
+          if (c2 < NC) tmem_ld32(taddr + (uint32_t)(c2 * 32), va);
+          reduce_cell(vb, c1);
         }
       }
       tc_fence_before();
