@@ -31,13 +31,20 @@ extern "C" {
 /* Size limits (every violation is reported as GDCA_ERR_INVALID_ARG with a message, never as a CUDA fault):
  *   L <= GDCA_MAX_L = 11616     the bit-plane packer keeps ceil(L/32) x 5 planes of 32 sequences in shared memory
  *   M <  2^31 - 128
- *   M * roundup(L,128) < 2^32   32-bit row offsets of the recoded alignment in the covariance kernel
- *                               (L=500: M < 8.3e6; L=1500: M < 2.7e6)
+ *   M * roundup(L,128) < 2^32   32-bit row offsets of the recoded alignment in the scatter-add covariance engine
+ *                               (L=500: M < 8.3e6; L=1500: M < 2.7e6); the tensor-core engine (weights = 1/count) has no such limit
+ *                               but needs n * (M/2 + 128 * classes) bytes for its one-hot operand (1.03 GB at L=500, M=200k)
  *   M <= 2 097 152 for the tensor-core prefilter (its T x T block-mask array, T = ceil(M/128) <= 16384); above that the
  *                               neighbour-count sweep still runs, unfiltered
  *   residue codes 1 <= Z <= 31  (q = max(Z) <= 31, src/GaussDCA.jl:25-26; a code < 1 is rejected)
  *   n = (q-1) L: four n x n FP64 buffers must fit in HBM (n = 30 000 -> 29 GB; n ~ 70 000 on one 180 GB B200) */
 #define GDCA_MAX_L 11616
+/* Numerical conventions that differ from DCAUtils in the last place only (both are documented deviations, not errors):
+ *   theta = :auto   meanfracid = (ident_sum / L) / (M (M-1) / 2) from the EXACT integer identity sum; DCAUtils accumulates the
+ *                   per-row fractions in floating point.  The two agree to a few ulp; thresh = floor(theta * L) can differ only when
+ *                   theta * L lies within that rounding of an integer (none of the reference's golden cases does).
+ *   Meff            the correctly rounded value of the exact rational sum of 1/count (double-double), independent of the order of
+ *                   summation and of the number of GPUs; Julia's sum(W) is a pairwise float sum of the same W[k]. */
 
 typedef enum {
   GDCA_OK = 0,
