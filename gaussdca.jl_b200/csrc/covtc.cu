@@ -641,8 +641,11 @@ int32_t gdca_k_covariance_tc(gdca_ctx *ctx, double pc, bool raw, bool *done) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cfg.gridDim = dim3((unsigned)(ctx->num_sms / 2 * 2));
-  int max_clusters = 0;
-  GDCA_CUDA(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, cov_tc_kernel, &cfg));
+  int max_clusters = ctx->cov_max_clusters;  // per device: asked once
+  if (max_clusters <= 0) {
+    GDCA_CUDA(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, cov_tc_kernel, &cfg));
+    ctx->cov_max_clusters = max_clusters;
+  }
   int nclusters = std::min(std::min(max_clusters, ctx->num_sms / 2), std::max(ntiles, 1));
   if (nclusters < 1) return gdca_fail(ctx, GDCA_ERR_CUDA, "covariance (tensor cores): no CTA pair fits on this device");
   cfg.gridDim = dim3((unsigned)(2 * nclusters));

@@ -108,6 +108,7 @@ struct gdca_ctx {
 
   // ---- covariance on the tensor cores: co-occurrence counts per weight class (covtc.cu) ----
   void *hostTab = nullptr; size_t capHostTab = 0;   // pinned host staging of the small planning tables
+  int cov_max_clusters = 0;                        // cudaOccupancyMaxActiveClusters of cov_tc_kernel on this device
   unsigned int *dCovSync = nullptr;                // [1] round counter of the covariance producers
   int cov_round_sync = -1;                         // -1 auto (operand > 0.5 GB), 0 off, 1 on: the TMA producers of the covariance pairs start their tiles together (env GDCA_COV_ROUND_SYNC)
   int cov_engine = 0;                              // 0 auto (cost model), 1 scatter-add engine (cov.cu), 2 tensor cores whenever the weights are count classes (env GDCA_COV_ENGINE)
