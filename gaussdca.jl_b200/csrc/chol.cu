@@ -487,25 +487,29 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__rest
 #pragma unroll
       for (int cc = 0; cc < 32; ++cc) v[cc] = Ls[(r0 + l) * D2_LD + r0 + cc];
       double d = __shfl_sync(FULL, v[0], 0);
+      double rs = rsqrt(d);
+      int first_bad = (d > 0.0) ? 0 : 1;  // 1-based column of the first non-positive pivot of this block (also catches NaN)
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (!(d > 0.0)) {  // also catches NaN
-          if (l == 0 && col0 + r0 + j < n_true) atomicCAS(info, 0, col0 + r0 + j + 1);
-        }
-        const double rs = rsqrt(d);
         double lij = (l == j) ? d * rs : v[j] * rs;  // final L[l][j]
         if (l < j) lij = 0.0;
+        const double rs_j = rs;
         if (j < 31) {
-          // the next pivot: its own lane needs nobody else's multiplier for the update of its diagonal element
+          // the next pivot: its own lane needs nobody else's multiplier for the update of its diagonal element.  Its rsqrt --
+          // the long dependent chain of the column -- starts HERE, so that it runs under the rank-1 update below
           const double dn = fma(-lij, lij, v[j + 1]);
           d = __shfl_sync(FULL, dn, j + 1);
+          rs = rsqrt(d);
+          if (first_bad == 0 && !(d > 0.0)) first_bad = j + 2;
         }
         Lc[j * 32 + l] = lij;
-        if (l == j) rsd[j] = rs;
+        if (l == j) rsd[j] = rs_j;
         __syncwarp();
-        if (l == 0) {
-          __threadfence_block();
-          *reinterpret_cast<volatile int *>(&s_ready) = j + 1;
+        if ((j & 3) == 3) {  // the inverse (warp 1) follows at most four columns behind
+          if (l == 0) {
+            __threadfence_block();
+            *reinterpret_cast<volatile int *>(&s_ready) = j + 1;
+          }
         }
         // rank-1 update of the columns to the right, multipliers read back as broadcast pairs
 #pragma unroll
@@ -515,6 +519,7 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__rest
           v[cc + 1] = fma(-lij, lc.y, v[cc + 1]);
         }
       }
+      if (first_bad && l == 0 && col0 + r0 + first_bad - 1 < n_true) atomicCAS(info, 0, col0 + r0 + first_bad);
     } else if (w == 1) {
       // (a') inverse of the diagonal block, one column behind the factor: lane l owns column l, forward substitution
       double x[32];
@@ -522,9 +527,11 @@ __global__ void __launch_bounds__(DT, 1) diag_block_kernel2(const double *__rest
       for (int i = 0; i < 32; ++i) x[i] = (i == l) ? 1.0 : 0.0;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        while (*reinterpret_cast<volatile int *>(&s_ready) <= k) {
+        if ((k & 3) == 0) {  // columns are published four at a time
+          while (*reinterpret_cast<volatile int *>(&s_ready) <= k + 3) {
+          }
+          __threadfence_block();
         }
-        __threadfence_block();
         x[k] *= rsd[k];
 #pragma unroll
         for (int i = (k + 1) & ~1; i < 32; i += 2) {
