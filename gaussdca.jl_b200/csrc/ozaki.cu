@@ -416,15 +416,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------- slicing
-// digits of one value already scaled to |x| < 1/2:  d_t = rint(rem 2^(7 (t+1))), rem -= d_t 2^(-7 (t+1))  (every step exact)
+// digits of one value already scaled to |x| < 1/2:  d_t = rint(rem 2^(7 (t+1))), rem -= d_t 2^(-7 (t+1))  (every step exact).
+// rint() and the double -> int conversion are quarter-rate conversion instructions (FRND.F64, F2I.F64: 16 per clock and SM) and
+// bound the slicing kernels; the same values come out of the full-rate FP64 pipe: x 2^(7 (t+1)) is exact, so ONE rounding of
+// fma(x, scale, 1.5 2^52) is the round-to-nearest-even of rint(), the integer sits in the low word of that sum's bit pattern, and
+// the remainder is one exact fma.  Bit-for-bit the digits of the rint() formulation (|d_t| <= 64).
 __device__ __forceinline__ void digits8(double x, int (&d)[S]) {
-  double scale = 128.0;
+  constexpr double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  double scale = 128.0, inv = 1.0 / 128.0;
 #pragma unroll
   for (int t = 0; t < S; ++t) {
-    const double q = rint(x * scale);
-    x -= q / scale;
-    d[t] = (int)q;
+    const double s = fma(x, scale, MAGIC);
+    d[t] = __double2loint(s);
+    x = fma(MAGIC - s, inv, x);  // x - q / scale with q = s - MAGIC (exact)
     scale *= 128.0;
+    inv *= 1.0 / 128.0;
   }
 }
 // exponent e with |mx / 2^e| < 1/2 (0 for an all-zero row) and the two powers of two that go with it
@@ -490,8 +496,15 @@ __global__ void __launch_bounds__(256) col_absmax_kernel(const double *__restric
   if (lower_only) k0 = max(k0, (blockIdx.x * 32 / 128) * 128);
   const double *a = src + b * stride_b + r;
   double mx = 0.0;
-  if (r < rows)
-    for (int kk = k0 + y; kk < k1; kk += 8) mx = fmax(mx, fabs(a[(long long)kk * ld]));
+  if (r < rows) {
+    double m2 = 0.0;  // two chains, eight loads in flight per thread
+#pragma unroll 4
+    for (int kk = k0 + y; kk < k1; kk += 16) {
+      mx = fmax(mx, fabs(a[(long long)kk * ld]));
+      if (kk + 8 < k1) m2 = fmax(m2, fabs(a[(long long)(kk + 8) * ld]));
+    }
+    mx = fmax(mx, m2);
+  }
   sh[y][x] = mx;
   __syncthreads();
   if (y == 0 && r < rows) {
