@@ -1203,10 +1203,12 @@ static int32_t inverse_enqueue(gdca_ctx *ctx, InvCapture *cap) {
         gdca_oz_operand oa{}, ob{};
         // T[bottom, top] = L[bottom, top] * X[top, top]: rows of L21 against the COLUMNS of the lower-triangular X11 (k >= n0)
         GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(A, g0 + h, g0), np, gstride, false, mb * NB, h * NB, batch, mb * NB, c->dDigA, c->dScaleA, &oa)));
-        GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(X, g0, g0) + col0, np, gstride, true, w, h * NB, batch, w, c->dDigB, c->dScaleB, &ob)));
+        // (X11 is lower triangular: column col0 + r is zero above row col0 + r, so the zero-skipping of the slice, which goes by the
+        // local column r, stays on the safe side for any col0; the product below starts at k = 128 floor((col0 + n0) / 128))
+        GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(X, g0, g0) + col0, np, gstride, true, w, h * NB, batch, w, c->dDigB, c->dScaleB, &ob, /*lower_only=*/true)));
         GDCA_TRY(mtry(c, gdca_oz_gemm(c, st, oa, ob, blk(T, g0 + h, g0) + col0, np, gstride, mb * NB, w, h * NB, batch, GDCA_OZ_KBEG_N, 1.0, 0, 0, &sh)));
         // X[bottom, top] = - X[bottom, bottom] * T[bottom, top]: rows of the lower-triangular X22 (k < m0 + 128) against columns of T
-        GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(X, g0 + h, g0 + h), np, gstride, false, mb * NB, mb * NB, batch, mb * NB, c->dDigA, c->dScaleA, &oa)));
+        GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(X, g0 + h, g0 + h), np, gstride, false, mb * NB, mb * NB, batch, mb * NB, c->dDigA, c->dScaleA, &oa, /*lower_only=*/true)));
         GDCA_TRY(mtry(c, gdca_oz_slice(c, st, blk(T, g0 + h, g0) + col0, np, gstride, true, w, mb * NB, batch, w, c->dDigB, c->dScaleB, &ob)));
         sh.n_off = 0;
         if (shared) {

@@ -443,13 +443,16 @@ __device__ __forceinline__ void row_exponent(double mx, double &inv_scale, doubl
 }
 
 // operand element (r, kk) = src[r * ld + kk]: one warp per row; lanes take 4 consecutive k each
+// lower_only: the source is lower triangular in 128-blocks (X22 of a trtri level): row r is zero from column 128 (floor(r / 128) + 1)
+// on, and the product that consumes the digits (k < m0 + 128) never reads them there -- neither scanned nor sliced
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double *__restrict__ src, long long ld, long long stride_b, int rows,
                                                          int k, int batch, long long rows_b, int8_t *__restrict__ dig,
-                                                         long long pitch, double *__restrict__ scale_out) {
+                                                         long long pitch, double *__restrict__ scale_out, int lower_only) {
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (wid >= (long long)rows * batch) return;
   const int b = (int)(wid / rows), r = (int)(wid - (long long)b * rows);
+  if (lower_only) k = min(k, (r / 128 + 1) * 128);
   const double *a = src + b * stride_b + (long long)r * ld;
   const long long R = b * rows_b + r;
   double mx = 0.0;
@@ -600,7 +603,7 @@ int32_t gdca_oz_slice(gdca_ctx *ctx, cudaStream_t stream, const double *src, lon
   const long long rows_total = (long long)(batch - 1) * rows_b + rows;
   if (!cols) {
     const long long warps = (long long)rows * batch;
-    GDCA_CUDA(ctx, gdca_launch_prio(slice_rows_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, src, ld, stride_b, rows, k, batch, rows_b, dig, pitch, scale));
+    GDCA_CUDA(ctx, gdca_launch_prio(slice_rows_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, src, ld, stride_b, rows, k, batch, rows_b, dig, pitch, scale, lower_only ? 1 : 0));
     GDCA_LAUNCH_CHECK(ctx);
   } else {
     GDCA_TRY(gdca_reserve(ctx, ctx->dOzMax, ctx->capOzMax, (size_t)ctx->npad > (size_t)rows_total ? (size_t)ctx->npad : (size_t)rows_total));
