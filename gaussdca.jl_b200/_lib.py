@@ -106,6 +106,7 @@ SIGNATURES = {
     "gdca_dev_inverse": (_i32, [_p, _pi32]),
     "gdca_dev_mJ_ptr": (_p, [_p]),
     "gdca_set_ozaki": (_i32, [_p, _i32]),
+    "gdca_set_di_engine": (_i32, [_p, _i32]),
     "gdca_dev_inverse_info": (_i32, [_p, _pi32, _pdbl, _pdbl]),
     "gdca_dev_inverse_shared": (_i32, [_p]),
     "gdca_test_fp64_gemm": (_i32, [_p, _i32, _p, _i32, _p, _i32, _p, _i64, _i64, _i64, _i32, _dbl, _dbl]),
@@ -220,6 +221,10 @@ class Context:
     def set_cov_engine(self, mode: int):
         """0 auto, 1 scatter-add engine, 2 co-occurrence counts per weight class on the FP4 tensor cores (gdca_set_cov_engine)."""
         self.check(self.lib.gdca_set_cov_engine(self.h, int(mode)))
+
+    def set_di_engine(self, mode: int):
+        """1 (default) tridiagonalisation + implicit QL, one lane per site pair; 0 one-sided Jacobi (gdca_set_di_engine)."""
+        self.check(self.lib.gdca_set_di_engine(self.h, int(mode)))
 
     def cov_info(self) -> dict:
         """What the last covariance stage ran on (gdca_dev_cov_info)."""

@@ -247,6 +247,7 @@ int32_t gdca_create(gdca_ctx **out, int32_t device) {
   if (const char *env = getenv("GDCA_CHOL_LOOKAHEAD")) ctx->chol_inner_lookahead = atoi(env) != 0;
   if (const char *env = getenv("GDCA_DIAG_BLOCKED")) ctx->diag_blocked = atoi(env) != 0;
   if (const char *env = getenv("GDCA_INV_GRAPH")) ctx->inv_graph_mode = atoi(env) != 0;
+  if (const char *env = getenv("GDCA_DI_ENGINE")) ctx->di_engine = atoi(env) != 0;
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fact, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trail_a, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
@@ -700,6 +701,14 @@ int32_t gdca_set_ozaki(gdca_ctx *ctx, int32_t mode) {
   if (!ctx) return GDCA_ERR_INVALID_ARG;
   if (mode != 0 && mode != 1) return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_ozaki: mode must be 0 (DMMA only) or 1 (INT8-sliced tcgen05 GEMMs)");
   ctx->ozaki_mode = mode;
+  return GDCA_OK;
+}
+
+int32_t gdca_set_di_engine(gdca_ctx *ctx, int32_t mode) {
+  if (!ctx) return GDCA_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1)
+    return gdca_fail(ctx, GDCA_ERR_INVALID_ARG, "set_di_engine: mode must be 0 (one-sided Jacobi) or 1 (tridiagonalisation + implicit QL)");
+  ctx->di_engine = mode;
   return GDCA_OK;
 }
 

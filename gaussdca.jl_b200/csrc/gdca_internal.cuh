@@ -59,6 +59,7 @@ struct gdca_ctx {
   double *dT = nullptr; size_t capT = 0;       // [npad][npad] GEMM workspace (trtri)
   int *dInfo = nullptr;                        // [1] not-SPD info
   // ---- INT8-sliced FP64 GEMMs of the inversion (ozaki.cu) ----
+  int di_engine = 1;                           // 1 (default): DI eigenvalues by tridiagonalisation + implicit QL, one lane per block; 0: one-sided Jacobi (env GDCA_DI_ENGINE)
   int ozaki_mode = 1;                          // 1 (default): big products of potrf / trtri / lauum on tcgen05 kind::i8; 0: DMMA only (env GDCA_OZAKI)
   int ozaki_tpc = 4;                           // tiles per CTA of the bulk trailing update (short CTAs: the look-ahead chain keeps getting SMs)
   int8_t *dDigA = nullptr; size_t capDigA = 0; // digit matrices [rows][k/64][8][64] int8

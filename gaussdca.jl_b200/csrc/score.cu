@@ -235,6 +235,200 @@ __global__ void __launch_bounds__(SW * 32) di_kernel(const double *__restrict__ 
   }
 }
 
+
+// ---- K7, second engine: eigenvalues of V = G'G by Householder tridiagonalisation + implicit QL ------------------------------------
+// The one-sided Jacobi iteration above spends ~2e5 flop per 20 x 20 block with every operand in shared memory (ncu: l1tex at 91 %,
+// half of the wavefronts bank conflicts; 11.8 ms at L = 500).  DI only needs the eigenvalues of the symmetric V (DCAUtils takes
+// lambda_k(V) of exactly this product), so a warp takes 32 consecutive blocks (i, j0..j0+31) and, one block after the other with all
+// lanes: forms G = Lc_i' mJ_ij Lc_j and V = G'G, reduces V to tridiagonal form by Householder reflections (lane k owns element k of
+// the reflector, row k of the matrix-vector product and column k of the rank-2 update: three warp sums per step, no divergence) and
+// parks the 2 s numbers (d, e) in an interleaved store (entry k of block m at [k * 33 + m]).  Then EVERY LANE runs the implicit QL
+// iteration on ITS OWN tridiagonal matrix -- O(s^2) scalar recurrences, 32 matrices per warp in lock step instead of one lane
+// working while 31 wait.  The classical EISPACK tred1 / tql1 pair, restated: ~2.5e4 flop per block, ~21 KB of shared memory per warp
+// (eight warps per SM), absolute eigenvalue error ~ eps ||V||, which is what the log(1 + sqrt(1 + 4 lambda)) sum needs.
+constexpr int DI_W = 4;    // warps per CTA
+constexpr int DI_IL = 33;  // interleave stride of the (d, e) store (doubles)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;  // the butterfly leaves the same bits on every lane
+}
+
+__host__ __device__ inline size_t di_eig_warp_doubles(int s) {
+  return (size_t)2 * s * s + (size_t)s * (s | 1) + (size_t)2 * s * DI_IL + 64;  // B/G, Lj, T1/V (odd row stride), (d, e), x, q
+}
+
+__global__ void __launch_bounds__(DI_W * 32) di_eig_kernel(const double *__restrict__ mJ, long long ld, const double *__restrict__ Lc,
+                                                           int L, int s, double *__restrict__ S) {
+  extern __shared__ double sm[];  // Li[s*s] + DI_W * di_eig_warp_doubles(s)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.y;
+  const int j0 = (blockIdx.x * DI_W + warp) * 32;
+  const int ss = s * s, ldv = s | 1;  // odd row stride: lanes that walk down a column of V hit distinct banks
+  double *Li = sm;
+  for (int e = threadIdx.x; e < ss; e += blockDim.x) Li[e] = Lc[(long long)i * ss + e];
+  __syncthreads();
+  if (j0 + 31 <= i || j0 >= L) return;  // no block of this warp lies in the upper triangle
+  double *Bm = sm + ss + (size_t)warp * di_eig_warp_doubles(s);
+  double *Lj = Bm + ss, *Vm = Lj + ss, *DE = Vm + (size_t)s * ldv, *xs = DE + (size_t)2 * s * DI_IL, *qs = xs + 32;
+  const int m_lo = max(0, i + 1 - j0), m_hi = min(32, L - j0);  // active slots [m_lo, m_hi)
+  const int da = 32 / s, db = 32 - da * s;                      // (row, column) advance of an element index that grows by 32
+  const int a0 = lane / s, b0 = lane - a0 * s;
+
+  for (int m = m_lo; m < m_hi; ++m) {
+    const int j = j0 + m;
+    {
+      int a = a0, b = b0;
+      for (int e = lane; e < ss; e += 32) {
+        Bm[e] = mJ[((long long)i * s + a) * ld + (long long)j * s + b];
+        Lj[e] = Lc[(long long)j * ss + e];
+        a += da; b += db;
+        if (b >= s) { b -= s; ++a; }
+      }
+    }
+    __syncwarp();
+    {  // T1 = B * Lj      (Lj lower: k >= b), into the V buffer
+      int a = a0, b = b0;
+      for (int e = lane; e < ss; e += 32) {
+        double t = 0.0;
+        for (int k = b; k < s; ++k) t = fma(Bm[a * s + k], Lj[k * s + b], t);
+        Vm[e] = t;
+        a += da; b += db;
+        if (b >= s) { b -= s; ++a; }
+      }
+    }
+    __syncwarp();
+    {  // G = Li' * T1     (Li lower: k >= a), row-major over B
+      int a = a0, b = b0;
+      for (int e = lane; e < ss; e += 32) {
+        double t = 0.0;
+        for (int k = a; k < s; ++k) t = fma(Li[k * s + a], Vm[k * s + b], t);
+        Bm[e] = t;
+        a += da; b += db;
+        if (b >= s) { b -= s; ++a; }
+      }
+    }
+    __syncwarp();
+    {  // V = G' G, full symmetric storage with row stride ldv
+      int a = a0, b = b0;
+      for (int e = lane; e < ss; e += 32) {
+        double t0 = 0.0, t1 = 0.0;
+        int k = 0;
+        for (; k + 1 < s; k += 2) {
+          t0 = fma(Bm[k * s + a], Bm[k * s + b], t0);
+          t1 = fma(Bm[(k + 1) * s + a], Bm[(k + 1) * s + b], t1);
+        }
+        if (k < s) t0 = fma(Bm[k * s + a], Bm[k * s + b], t0);
+        Vm[a * ldv + b] = t0 + t1;
+        a += da; b += db;
+        if (b >= s) { b -= s; ++a; }
+      }
+    }
+    __syncwarp();
+    // Householder reduction, rows s-1 .. 1: u = scaled row r (columns 0..l, l = r-1) with u_l -= g, H = u'u / 2,
+    // p = V u / H, K = u'p / (2H), q = p - K u, V -= u q' + q u'.  The sub-diagonal entry of row r is scale * g.
+    for (int r = s - 1; r >= 1; --r) {
+      const int l = r - 1;
+      double *esub = DE + (size_t)(s + r - 1) * DI_IL + m;  // e[r-1] (already shifted for the QL iteration)
+      if (l == 0) {
+        if (lane == 0) *esub = Vm[r * ldv];
+        continue;
+      }
+      double x = (lane <= l) ? Vm[r * ldv + lane] : 0.0;
+      const double scale = warp_sum(fabs(x));
+      if (scale == 0.0) {  // warp-uniform
+        if (lane == 0) *esub = 0.0;
+        continue;
+      }
+      x *= 1.0 / scale;
+      double h = warp_sum(x * x);
+      const double f = __shfl_sync(0xffffffffu, x, l);
+      const double g = (f >= 0.0) ? -sqrt(h) : sqrt(h);
+      if (lane == 0) *esub = scale * g;
+      h -= f * g;
+      if (lane == l) x = f - g;
+      xs[lane] = x;
+      __syncwarp();
+      double pv = 0.0;
+      if (lane <= l) {
+        const double *row = Vm + lane * ldv;
+        double p0 = 0.0, p1 = 0.0;
+        int k = 0;
+        for (; k + 1 <= l; k += 2) {
+          p0 = fma(row[k], xs[k], p0);
+          p1 = fma(row[k + 1], xs[k + 1], p1);
+        }
+        if (k <= l) p0 = fma(row[k], xs[k], p0);
+        pv = (p0 + p1) / h;
+      }
+      const double K = warp_sum(pv * x) / (h + h);
+      const double q = pv - K * x;  // 0 on the lanes beyond l
+      qs[lane] = q;
+      __syncwarp();
+      if (lane <= l) {
+        for (int jj = 0; jj <= l; ++jj) Vm[jj * ldv + lane] -= fma(xs[jj], q, qs[jj] * x);
+      }
+      __syncwarp();
+    }
+    if (lane < s) DE[(size_t)lane * DI_IL + m] = Vm[lane * ldv + lane];
+    if (lane == 0) DE[(size_t)(2 * s - 1) * DI_IL + m] = 0.0;
+    __syncwarp();
+  }
+
+  // ---- implicit QL on (d, e), eigenvalues only: lane m owns the tridiagonal matrix in slot m ----
+  const int j = j0 + lane;
+  if (j <= i || j >= L) return;
+#define D_(k) DE[(size_t)(k) * DI_IL + lane]
+#define E_(k) DE[(size_t)(s + (k)) * DI_IL + lane]
+  for (int l = 0; l < s; ++l) {
+    for (int iter = 0; iter < 60; ++iter) {
+      int m = l;
+      for (; m < s - 1; ++m) {
+        const double dd = fabs(D_(m)) + fabs(D_(m + 1));
+        if (fabs(E_(m)) <= 2.220446049250313e-16 * dd) break;
+      }
+      if (m == l) break;
+      const double el = E_(l), dl = D_(l);
+      double g = (D_(l + 1) - dl) / (2.0 * el);
+      double r = sqrt(fma(g, g, 1.0));
+      g = D_(m) - dl + el / (g + copysign(r, g));
+      double sn = 1.0, cs = 1.0, p = 0.0;
+      int k = m - 1;
+      for (; k >= l; --k) {
+        const double ek = E_(k);
+        const double f = sn * ek, b = cs * ek;
+        r = sqrt(fma(f, f, g * g));
+        E_(k + 1) = r;
+        if (r == 0.0) {
+          D_(k + 1) -= p;
+          E_(m) = 0.0;
+          break;
+        }
+        const double rinv = 1.0 / r;
+        sn = f * rinv;
+        cs = g * rinv;
+        g = D_(k + 1) - p;
+        r = fma(D_(k) - g, sn, 2.0 * cs * b);
+        p = sn * r;
+        D_(k + 1) = g + p;
+        g = fma(cs, r, -b);
+      }
+      if (r == 0.0 && k >= l) continue;
+      D_(l) -= p;
+      E_(l) = g;
+      E_(m) = 0.0;
+    }
+  }
+  double part = 0.0;
+  for (int k = 0; k < s; ++k) part += log(1.0 + sqrt(fma(4.0, fmax(D_(k), 0.0), 1.0)));
+#undef E_
+#undef D_
+  const double di = 0.5 * s * log(0.5) + 0.5 * part;
+  S[(long long)i * L + j] = di;
+  S[(long long)j * L + i] = di;
+}
+
 }  // namespace
 
 int32_t gdca_k_score(gdca_ctx *ctx, int score) {
@@ -252,6 +446,17 @@ int32_t gdca_k_score(gdca_ctx *ctx, int score) {
     double *Lc = ctx->dRed;
     site_chol_kernel<<<(unsigned)L, 32, (size_t)s * s * sizeof(double), ctx->stream>>>(ctx->dCdiag, s, Lc);
     GDCA_LAUNCH_CHECK(ctx);
+    if (ctx->di_engine != 0) {
+      // tridiagonalisation by the warp, implicit QL by the lane: 32 site pairs per warp, DI_W warps per CTA
+      const size_t smem = ((size_t)s * s + (size_t)DI_W * di_eig_warp_doubles(s)) * sizeof(double);
+      GDCA_CUDA(ctx, cudaFuncSetAttribute(di_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 egrid((unsigned)((L + DI_W * 32 - 1) / (DI_W * 32)), (unsigned)L);
+      di_eig_kernel<<<egrid, DI_W * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, Lc, L, s, ctx->dS);
+      GDCA_LAUNCH_CHECK(ctx);
+      zero_diag_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->dS, L);
+      GDCA_LAUNCH_CHECK(ctx);
+      return GDCA_OK;
+    }
     const int half = (s + 1) / 2;
     const int nsub = (32 / half) < 3 ? (32 / half) : 3;
     const size_t smem = ((size_t)s * s + (size_t)SW * ((size_t)nsub * s * (s + 1) + 2 * s * s)) * sizeof(double);

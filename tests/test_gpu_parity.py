@@ -279,7 +279,41 @@ def test_scores_vs_oracle_random_spd(pkg, orc, ctx, q):
     C = A @ A.T / (3 * n) + 0.1 * np.eye(n)
     mJ = orc.inv_cholesky(C)
     assert normwise(pkg.compute_FN(mJ, q, ctx=ctx), orc.compute_FN(mJ, q)) <= 1e-12
-    assert normwise(pkg.compute_DI_gauss(mJ, C, q, ctx=ctx), orc.compute_DI_gauss(mJ, C, q)) <= 1e-11
+    ref = orc.compute_DI_gauss(mJ, C, q)
+    di_ql = pkg.compute_DI_gauss(mJ, C, q, ctx=ctx)     # default engine: tridiagonalisation + implicit QL, one lane per site pair
+    assert normwise(di_ql, ref) <= 1e-11
+    ctx.set_di_engine(0)                                  # the one-sided Jacobi engine, kept as the cross-check
+    try:
+        di_jac = pkg.compute_DI_gauss(mJ, C, q, ctx=ctx)
+    finally:
+        ctx.set_di_engine(1)
+    assert normwise(di_jac, ref) <= 1e-11
+    assert normwise(di_ql, di_jac) <= 1e-12
+    assert np.array_equal(di_ql, di_ql.T) and not np.diag(di_ql).any()
+
+
+def test_di_engines_agree_on_ragged_site_counts(pkg, orc, ctx):
+    """L not a multiple of the 32 pairs a warp takes (and of the 96 of a CTA), rank-deficient couplings, a zero coupling block."""
+    q, s = 21, 20
+    for L in (33, 97, 130):
+        n = s * L
+        rng = np.random.default_rng(L)
+        A = rng.standard_normal((n, 2 * n))
+        C = A @ A.T / (2 * n) + 0.05 * np.eye(n)
+        mJ = orc.inv_cholesky(C)
+        mJ[0:s, s:2 * s] = 0.0; mJ[s:2 * s, 0:s] = 0.0                       # zero block: all eigenvalues 0
+        mJ[2 * s:3 * s, 5 * s:6 * s][:, s // 2:] = 0.0                       # rank-deficient block
+        mJ[5 * s:6 * s, 2 * s:3 * s] = mJ[2 * s:3 * s, 5 * s:6 * s].T
+        di_ql = pkg.compute_DI_gauss(mJ, C, q, ctx=ctx)
+        ctx.set_di_engine(0)
+        try:
+            di_jac = pkg.compute_DI_gauss(mJ, C, q, ctx=ctx)
+        finally:
+            ctx.set_di_engine(1)
+        assert normwise(di_ql, di_jac) <= 1e-12, L
+        assert abs(di_ql[0, 1]) <= 1e-13 and abs(di_ql[1, 0]) <= 1e-13     # s/2 log(1/2) + 1/2 s log 2 = 0
+        if L == 33:
+            assert normwise(di_ql, orc.compute_DI_gauss(mJ, C, q)) <= 1e-11
 
 
 def test_apc_and_ranking_ties_are_stable(pkg, orc, ctx):
