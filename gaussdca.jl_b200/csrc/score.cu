@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(SW * 32) di_kernel(const double *__restrict__ 
 // iteration on ITS OWN tridiagonal matrix -- O(s^2) scalar recurrences, 32 matrices per warp in lock step instead of one lane
 // working while 31 wait.  The classical EISPACK tred1 / tql1 pair, restated: ~2.5e4 flop per block, ~21 KB of shared memory per warp
 // (eight warps per SM), absolute eigenvalue error ~ eps ||V||, which is what the log(1 + sqrt(1 + 4 lambda)) sum needs.
-constexpr int DI_W = 4;    // warps per CTA
+constexpr int DI_W = 5;    // warps per CTA (two CTAs per SM at s = 20)
 constexpr int DI_IL = 33;  // interleave stride of the (d, e) store (doubles)
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -256,12 +256,19 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 __host__ __device__ inline size_t di_eig_warp_doubles(int s) {
-  return (size_t)2 * s * s + (size_t)s * (s | 1) + (size_t)2 * s * DI_IL + 64;  // B/G, Lj, T1/V (odd row stride), (d, e), x, q
+  // (x, q) pairs first (16-byte aligned), then B/G, Lj, T1/V (odd row stride), (d, e); rounded to an even number of doubles
+  return (64 + (size_t)2 * s * s + (size_t)s * (s | 1) + (size_t)2 * s * DI_IL + 1) & ~(size_t)1;
 }
+__host__ __device__ inline size_t di_eig_li_doubles(int s) { return ((size_t)s * s + 1) & ~(size_t)1; }
 
+// S > 0: the number of states is a compile-time constant (S = 20, proteins: q = 21) -- the inner loops of the three products unroll
+// into loads with immediate offsets and run over the full k range (the zero triangles of Lc_i, Lc_j are stored); S = 0: any s.
+template <int S>
 __global__ void __launch_bounds__(DI_W * 32) di_eig_kernel(const double *__restrict__ mJ, long long ld, const double *__restrict__ Lc,
-                                                           int L, int s, double *__restrict__ S) {
-  extern __shared__ double sm[];  // Li[s*s] + DI_W * di_eig_warp_doubles(s)
+                                                           int L, int s_rt, double *__restrict__ S_out) {
+  extern __shared__ __align__(16) double sm_di[];  // Li + DI_W * di_eig_warp_doubles(s)
+  double *sm = sm_di;
+  const int s = S > 0 ? S : s_rt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.y;
   const int j0 = (blockIdx.x * DI_W + warp) * 32;
@@ -270,8 +277,9 @@ __global__ void __launch_bounds__(DI_W * 32) di_eig_kernel(const double *__restr
   for (int e = threadIdx.x; e < ss; e += blockDim.x) Li[e] = Lc[(long long)i * ss + e];
   __syncthreads();
   if (j0 + 31 <= i || j0 >= L) return;  // no block of this warp lies in the upper triangle
-  double *Bm = sm + ss + (size_t)warp * di_eig_warp_doubles(s);
-  double *Lj = Bm + ss, *Vm = Lj + ss, *DE = Vm + (size_t)s * ldv, *xs = DE + (size_t)2 * s * DI_IL, *qs = xs + 32;
+  double *wbase = sm + di_eig_li_doubles(s) + (size_t)warp * di_eig_warp_doubles(s);
+  double2 *xq = reinterpret_cast<double2 *>(wbase);  // (x_k, q_k) of the current reflector
+  double *Bm = wbase + 64, *Lj = Bm + ss, *Vm = Lj + ss, *DE = Vm + (size_t)s * ldv;
   const int m_lo = max(0, i + 1 - j0), m_hi = min(32, L - j0);  // active slots [m_lo, m_hi)
   const int da = 32 / s, db = 32 - da * s;                      // (row, column) advance of an element index that grows by 32
   const int a0 = lane / s, b0 = lane - a0 * s;
@@ -288,23 +296,43 @@ __global__ void __launch_bounds__(DI_W * 32) di_eig_kernel(const double *__restr
       }
     }
     __syncwarp();
-    {  // T1 = B * Lj      (Lj lower: k >= b), into the V buffer
+    {  // T1 = B * Lj      (Lj lower: only k >= b contributes), into the V buffer
       int a = a0, b = b0;
       for (int e = lane; e < ss; e += 32) {
-        double t = 0.0;
-        for (int k = b; k < s; ++k) t = fma(Bm[a * s + k], Lj[k * s + b], t);
-        Vm[e] = t;
+        const double *bp = Bm + a * s, *lp = Lj + b;
+        double t0 = 0.0, t1 = 0.0;
+        if (S > 0) {
+#pragma unroll
+          for (int k = 0; k + 1 < S; k += 2) {
+            t0 = fma(bp[k], lp[k * S], t0);
+            t1 = fma(bp[k + 1], lp[(k + 1) * S], t1);
+          }
+          if (S & 1) t0 = fma(bp[S - 1], lp[(S - 1) * S], t0);
+        } else {
+          for (int k = b; k < s; ++k) t0 = fma(bp[k], lp[k * s], t0);
+        }
+        Vm[e] = t0 + t1;
         a += da; b += db;
         if (b >= s) { b -= s; ++a; }
       }
     }
     __syncwarp();
-    {  // G = Li' * T1     (Li lower: k >= a), row-major over B
+    {  // G = Li' * T1     (Li lower: only k >= a contributes), row-major over B
       int a = a0, b = b0;
       for (int e = lane; e < ss; e += 32) {
-        double t = 0.0;
-        for (int k = a; k < s; ++k) t = fma(Li[k * s + a], Vm[k * s + b], t);
-        Bm[e] = t;
+        const double *lp = Li + a, *tp = Vm + b;
+        double t0 = 0.0, t1 = 0.0;
+        if (S > 0) {
+#pragma unroll
+          for (int k = 0; k + 1 < S; k += 2) {
+            t0 = fma(lp[k * S], tp[k * S], t0);
+            t1 = fma(lp[(k + 1) * S], tp[(k + 1) * S], t1);
+          }
+          if (S & 1) t0 = fma(lp[(S - 1) * S], tp[(S - 1) * S], t0);
+        } else {
+          for (int k = a; k < s; ++k) t0 = fma(lp[k * s], tp[k * s], t0);
+        }
+        Bm[e] = t0 + t1;
         a += da; b += db;
         if (b >= s) { b -= s; ++a; }
       }
@@ -313,21 +341,34 @@ __global__ void __launch_bounds__(DI_W * 32) di_eig_kernel(const double *__restr
     {  // V = G' G, full symmetric storage with row stride ldv
       int a = a0, b = b0;
       for (int e = lane; e < ss; e += 32) {
+        const double *ga = Bm + a, *gb = Bm + b;
         double t0 = 0.0, t1 = 0.0;
-        int k = 0;
-        for (; k + 1 < s; k += 2) {
-          t0 = fma(Bm[k * s + a], Bm[k * s + b], t0);
-          t1 = fma(Bm[(k + 1) * s + a], Bm[(k + 1) * s + b], t1);
+        if (S > 0) {
+#pragma unroll
+          for (int k = 0; k + 1 < S; k += 2) {
+            t0 = fma(ga[k * S], gb[k * S], t0);
+            t1 = fma(ga[(k + 1) * S], gb[(k + 1) * S], t1);
+          }
+          if (S & 1) t0 = fma(ga[(S - 1) * S], gb[(S - 1) * S], t0);
+        } else {
+          int k = 0;
+          for (; k + 1 < s; k += 2) {
+            t0 = fma(ga[k * s], gb[k * s], t0);
+            t1 = fma(ga[(k + 1) * s], gb[(k + 1) * s], t1);
+          }
+          if (k < s) t0 = fma(ga[k * s], gb[k * s], t0);
         }
-        if (k < s) t0 = fma(Bm[k * s + a], Bm[k * s + b], t0);
         Vm[a * ldv + b] = t0 + t1;
         a += da; b += db;
         if (b >= s) { b -= s; ++a; }
       }
     }
     __syncwarp();
-    // Householder reduction, rows s-1 .. 1: u = scaled row r (columns 0..l, l = r-1) with u_l -= g, H = u'u / 2,
-    // p = V u / H, K = u'p / (2H), q = p - K u, V -= u q' + q u'.  The sub-diagonal entry of row r is scale * g.
+    // Householder reduction, rows s-1 .. 1: u = row r (columns 0..l, l = r-1) with u_l -= g, g = -sign(u_l) ||u||, H = u'u / 2,
+    // p = V u / H, K = u'p / (2H), q = p - K u, V -= u q' + q u'.  The sub-diagonal entry of row r is g.  (No rescaling of the
+    // row: the entries of V are squares of couplings, far from the over/underflow thresholds; a row whose squares underflow to
+    // zero is treated as zero -- its eigenvalue contribution is below 1e-300 either way.)
+#pragma unroll 1
     for (int r = s - 1; r >= 1; --r) {
       const int l = r - 1;
       double *esub = DE + (size_t)(s + r - 1) * DI_IL + m;  // e[r-1] (already shifted for the QL iteration)
@@ -336,38 +377,44 @@ __global__ void __launch_bounds__(DI_W * 32) di_eig_kernel(const double *__restr
         continue;
       }
       double x = (lane <= l) ? Vm[r * ldv + lane] : 0.0;
-      const double scale = warp_sum(fabs(x));
-      if (scale == 0.0) {  // warp-uniform
+      double h = warp_sum(x * x);
+      if (!(h >= 1e-290)) {  // warp-uniform (also a NaN row: the NaN reaches the result through the diagonal)
         if (lane == 0) *esub = 0.0;
         continue;
       }
-      x *= 1.0 / scale;
-      double h = warp_sum(x * x);
       const double f = __shfl_sync(0xffffffffu, x, l);
       const double g = (f >= 0.0) ? -sqrt(h) : sqrt(h);
-      if (lane == 0) *esub = scale * g;
+      if (lane == 0) *esub = g;
       h -= f * g;
+      const double rh = 1.0 / h;
       if (lane == l) x = f - g;
-      xs[lane] = x;
+      xq[lane].x = x;
       __syncwarp();
       double pv = 0.0;
       if (lane <= l) {
         const double *row = Vm + lane * ldv;
         double p0 = 0.0, p1 = 0.0;
         int k = 0;
+#pragma unroll 4
         for (; k + 1 <= l; k += 2) {
-          p0 = fma(row[k], xs[k], p0);
-          p1 = fma(row[k + 1], xs[k + 1], p1);
+          p0 = fma(row[k], xq[k].x, p0);
+          p1 = fma(row[k + 1], xq[k + 1].x, p1);
         }
-        if (k <= l) p0 = fma(row[k], xs[k], p0);
-        pv = (p0 + p1) / h;
+        if (k <= l) p0 = fma(row[k], xq[k].x, p0);
+        pv = (p0 + p1) * rh;
       }
-      const double K = warp_sum(pv * x) / (h + h);
-      const double q = pv - K * x;  // 0 on the lanes beyond l
-      qs[lane] = q;
+      const double K = warp_sum(pv * x) * (0.5 * rh);
+      const double q = fma(-K, x, pv);  // 0 on the lanes beyond l
+      xq[lane].y = q;
       __syncwarp();
       if (lane <= l) {
-        for (int jj = 0; jj <= l; ++jj) Vm[jj * ldv + lane] -= fma(xs[jj], q, qs[jj] * x);
+        double *vp = Vm + lane;
+#pragma unroll 4
+        for (int jj = 0; jj <= l; ++jj) {
+          const double2 w = xq[jj];
+          *vp -= fma(w.x, q, w.y * x);
+          vp += (S > 0 ? (S | 1) : ldv);
+        }
       }
       __syncwarp();
     }
@@ -425,8 +472,8 @@ __global__ void __launch_bounds__(DI_W * 32) di_eig_kernel(const double *__restr
 #undef E_
 #undef D_
   const double di = 0.5 * s * log(0.5) + 0.5 * part;
-  S[(long long)i * L + j] = di;
-  S[(long long)j * L + i] = di;
+  S_out[(long long)i * L + j] = di;
+  S_out[(long long)j * L + i] = di;
 }
 
 }  // namespace
@@ -448,10 +495,15 @@ int32_t gdca_k_score(gdca_ctx *ctx, int score) {
     GDCA_LAUNCH_CHECK(ctx);
     if (ctx->di_engine != 0) {
       // tridiagonalisation by the warp, implicit QL by the lane: 32 site pairs per warp, DI_W warps per CTA
-      const size_t smem = ((size_t)s * s + (size_t)DI_W * di_eig_warp_doubles(s)) * sizeof(double);
-      GDCA_CUDA(ctx, cudaFuncSetAttribute(di_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const size_t smem = (di_eig_li_doubles(s) + (size_t)DI_W * di_eig_warp_doubles(s)) * sizeof(double);
       dim3 egrid((unsigned)((L + DI_W * 32 - 1) / (DI_W * 32)), (unsigned)L);
-      di_eig_kernel<<<egrid, DI_W * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, Lc, L, s, ctx->dS);
+      if (s == 20) {
+        GDCA_CUDA(ctx, cudaFuncSetAttribute(di_eig_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        di_eig_kernel<20><<<egrid, DI_W * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, Lc, L, s, ctx->dS);
+      } else {
+        GDCA_CUDA(ctx, cudaFuncSetAttribute(di_eig_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        di_eig_kernel<0><<<egrid, DI_W * 32, smem, ctx->stream>>>(ctx->dmJ, ctx->npad, Lc, L, s, ctx->dS);
+      }
       GDCA_LAUNCH_CHECK(ctx);
       zero_diag_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->dS, L);
       GDCA_LAUNCH_CHECK(ctx);
