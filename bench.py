@@ -577,8 +577,9 @@ def main():
         inv_info = _inverse_info(ctx, lib)
         roof = {
             "kernel": inv_info.get("kernel", "Cholesky + inverse") + f"; factorisation on the leading GPU, trtri / lauum shared by {world} GPUs",
-            "bound": "fp64_tensor", "achieved": n ** 3 / t_chol / 1e12, "peak": dmma.value * world, "unit": "TFLOP/s",
-            "frac": (n ** 3 / t_chol / 1e12) / (dmma.value * world),
+            "bound": "tensor", "bound_detail": "fp64_tensor (SURVEY 8(d): n^3 FP64 flop against the DMMA rate)",
+            "achieved": n ** 3 / t_chol / 1e12, "peak": dmma.value * world, "unit": "TFLOP/s",
+            "frac": (n ** 3 / t_chol / 1e12) / (dmma.value * world), "traffic": None,
             "peak_source": f"{world} x the FP64 tensor (DMMA) rate measured live by gdca_probe_peaks on the leading GPU",
             "ms_per_step": t_chol * 1e3, "share_of_step": t_chol * 1e3 / ms_step,
             "sweep_shard_on_leader": sweep_entry,
@@ -651,8 +652,12 @@ def main():
         inv_info = _inverse_info(ctx, lib)
         inv_entry = {
             "kernel": inv_info.get("kernel", "dgemm_kernel<*> + diag_block_kernel (blocked Cholesky, trtri by recursive doubling, lauum)"),
-            "bound": "fp64_tensor", "achieved": n ** 3 / t_chol / 1e12, "peak": dmma.value, "unit": "TFLOP/s",
+            "bound": "tensor", "bound_detail": "fp64_tensor (SURVEY 8(d): n^3 FP64 flop against the DMMA rate; the big products "
+                                               "themselves run as INT8 tcgen05 digit products, see int8_ops_per_step)",
+            "achieved": n ** 3 / t_chol / 1e12, "peak": dmma.value, "unit": "TFLOP/s",
             "frac": (n ** 3 / t_chol / 1e12) / dmma.value,
+            "traffic": ncu_traffic("ozaki_gemm_kernel") if name == "C" else None,
+            "traffic_note": "DRAM bytes of the longest ozaki_gemm_kernel launch (the lauum product) in the committed ncu --set full capture",
             "peak_source": "FP64 tensor (DMMA.8x8x4) rate measured live by gdca_probe_peaks (MEASURED_PEAKS.json has HBM and bf16 "
                            f"only); committed probe run profiles/r2_probe_peaks.json: {probe_file.get('dmma_tflops')} TFLOP/s",
             "ms_per_step": t_chol * 1e3, "flop_per_step": float(n) ** 3,

@@ -234,8 +234,9 @@ int32_t gdca_dev_inverse(gdca_ctx *ctx, int32_t *info); /* C -> mJ on this devic
  * in FP64 with one rounding (csrc/ozaki.cu; mJ stays within ~1e-12 normwise of the DMMA path);  0: FP64 tensor cores (DMMA) only. */
 int32_t gdca_set_ozaki(gdca_ctx *ctx, int32_t mode);
 /* Eigenvalue engine of the DI score (compute_DI_gauss, reference src/GaussDCA.jl:37).  1 (default): V = G'G per site pair, reduced to
- * tridiagonal form and solved by implicit QL, one lane per pair (csrc/score.cu di_eig_kernel);  0: one-sided Jacobi on G, three
- * pairs per warp (di_kernel, the round-1 engine; agrees to ~1e-13 normwise, kept as the cross-check). */
+ * tridiagonal form by Householder reflections (one warp, 32 pairs in turn) and solved by implicit QL (one lane per pair)
+ * (csrc/score.cu di_eig_kernel; env GDCA_DI_ENGINE);  0: one-sided Jacobi on G, three pairs per warp (di_kernel, the round-1 engine;
+ * the two agree to ~1e-13 normwise, the Jacobi engine is kept as the cross-check). */
 int32_t gdca_set_di_engine(gdca_ctx *ctx, int32_t mode);
 /* what the last inversion ran: *ozaki 0/1, the INT8 operations executed and the FP64 flop they stand for */
 int32_t gdca_dev_inverse_info(gdca_ctx *ctx, int32_t *ozaki, double *int8_ops, double *fp64_flop_on_int8);
