@@ -58,7 +58,7 @@ constexpr size_t C_SMEM = (size_t)CNSTAGE * CSTAGE_BYTES + 1024;
 // kind::mxf4.block_scale.block32: A = B = E2M1 (1 at bits 7 and 10), scale format UE8M0 (bit 23), N >> 3 at bit 17, M >> 4 at bit 24;
 // cta_group::2: M = 256 rows across the CTA pair
 constexpr uint32_t C_IDESC = (1u << 7) | (1u << 10) | ((uint32_t)(CT >> 3) << 17) | (1u << 23) | ((uint32_t)(2 * CT >> 4) << 24);
-constexpr long long SEG_MAX_SEQ = 1ll << 23;  // FP32 accumulation of ones stays exact
+constexpr long long SEG_MAX_SEQ = (1ll << 23) - 256;  // FP32 accumulation of ones stays exact, and count + 2^23 keeps the count in its mantissa
 
 struct CovTcParams {
   const int2 *tiles;     // [ntiles] pair tiles (RB2, CB): row blocks 2 RB2 and 2 RB2 + 1 x column block CB <= 2 RB2 + 1, this rank's share
@@ -74,6 +74,15 @@ struct CovTcParams {
   double pc;
   unsigned int *round_sync;  // producers that have started their j-th tile (nullptr: free running)
 };
+
+// FP32 accumulator -> FP64 without a conversion instruction (F2F.F64.F32 issues at 16 lanes per clock and SM: 64 of them per
+// thread and class made the drain of a class ~1000 clocks, the floor of the plan's cost model).  The accumulator holds an exact
+// integer count < 2^23: count + 2^23 (one FADD, exact) carries it in its mantissa field, and 2^52 + count - 2^52 (one DADD on the
+// full-rate FP64 pipe, exact) is the same double the conversion gives.
+__device__ __forceinline__ double count_to_double(uint32_t fbits) {
+  const uint32_t u = __float_as_uint(__uint_as_float(fbits) + 8388608.0f) & 0x007fffffu;
+  return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0;
+}
 
 __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_constant__ CUtensorMap tmap, CovTcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -236,14 +245,14 @@ __global__ void __launch_bounds__(C_THREADS, 1) cov_tc_kernel(const __grid_const
         tmem_ld32(taddr, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = fma(w, (double)__uint_as_float(v[j]), acc[j]);
+        for (int j = 0; j < 32; ++j) acc[j] = fma(w, count_to_double(v[j]), acc[j]);
         tmem_ld32(taddr + 32u, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_even(tempty_bar(as));  // the counts are in registers: the next class may overwrite the stage
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[32 + j] = fma(w, (double)__uint_as_float(v[j]), acc[32 + j]);
+        for (int j = 0; j < 32; ++j) acc[32 + j] = fma(w, count_to_double(v[j]), acc[32 + j]);
       }
       // ---- fused epilogue of the tile: 1/Meff, pseudocount, - Pi Pi'; the tile and (off the diagonal) its mirror image
       if (rb >= P.nblk || cb > rb) continue;  // computed for the neighbours' sake only
