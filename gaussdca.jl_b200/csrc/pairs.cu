@@ -435,23 +435,32 @@ __global__ void __launch_bounds__(256) pair_list_kernel(PairListParams P) {
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
   const bool words = (P.L & 3) == 0 && (reinterpret_cast<uintptr_t>(P.Z) & 3) == 0;
-  for (unsigned long long p = (unsigned long long)gw; p < n; p += (unsigned long long)nw) {
-    const int2 kl = P.pairs[p];
-    if (kl.x < 0) continue;  // unused slot of a warp's chunk
-    const int8_t *za = P.Z + (long long)kl.x * P.L, *zb = P.Z + (long long)kl.y * P.L;
-    int ham = 0;
-    if (words) {
-      const uint32_t *wa = reinterpret_cast<const uint32_t *>(za), *wb = reinterpret_cast<const uint32_t *>(zb);
-      for (int w = lane; w < (int)(P.L >> 2); w += 32) ham += __popc(__vcmpne4(__ldg(wa + w), __ldg(wb + w))) >> 3;
-    } else {
-      for (int i = lane; i < (int)P.L; i += 32) ham += za[i] != zb[i];
-    }
-    ham = __reduce_add_sync(0xffffffffu, ham);
-    if (lane == 0 && ham < P.thresh)
-      for (int pr = 0; pr < P.npeers; ++pr) {  // own buffer and, over NVLink, the peers'
-        atomicAdd(P.counts[pr] + kl.x, 1);
-        atomicAdd(P.counts[pr] + kl.y, 1);
+  // A pair costs two dependent trips to L2 (its list entry, then the two sequences): the entry of the warp's NEXT pair is fetched
+  // before the current pair is compared, so only the sequence reads remain on the critical path of the loop.
+  unsigned long long p = (unsigned long long)gw;
+  int2 kl = p < n ? P.pairs[p] : make_int2(-1, -1);
+  for (; p < n; p += (unsigned long long)nw) {
+    const unsigned long long pn = p + (unsigned long long)nw;
+    const int2 kl_next = pn < n ? P.pairs[pn] : make_int2(-1, -1);
+    if (kl.x >= 0) {  // else: unused slot of a warp's chunk
+      const int8_t *za = P.Z + (long long)kl.x * P.L, *zb = P.Z + (long long)kl.y * P.L;
+      int ham = 0;
+      if (words) {
+        const uint32_t *wa = reinterpret_cast<const uint32_t *>(za), *wb = reinterpret_cast<const uint32_t *>(zb);
+#pragma unroll 4
+        for (int w = lane; w < (int)(P.L >> 2); w += 32) ham += __popc(__vcmpne4(__ldg(wa + w), __ldg(wb + w))) >> 3;
+      } else {
+#pragma unroll 4
+        for (int i = lane; i < (int)P.L; i += 32) ham += za[i] != zb[i];
       }
+      ham = __reduce_add_sync(0xffffffffu, ham);
+      if (lane == 0 && ham < P.thresh)
+        for (int pr = 0; pr < P.npeers; ++pr) {  // own buffer and, over NVLink, the peers'
+          atomicAdd(P.counts[pr] + kl.x, 1);
+          atomicAdd(P.counts[pr] + kl.y, 1);
+        }
+    }
+    kl = kl_next;
   }
   if (gw == 0 && lane == 0) atomicAdd(P.ham_sum + 1, n * (unsigned long long)P.nwords);  // executed pair-words (roofline evidence)
 }
