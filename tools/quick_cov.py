@@ -1,3 +1,4 @@
+"""Covariance stage alone at config C, both engines (developer timing loop)."""
 import sys, time, ctypes, numpy as np
 sys.path.insert(0, '/root/repo')
 import __graft_entry__ as g

@@ -1,3 +1,5 @@
+"""Stage times of a few resident steps of config C (no argument) or config D (argument 1: DI score, pseudocount 0.2) on one GPU:
+   python tools/quick_step.py [0|1]      (developer loop: one gpurun call of ~25 s)"""
 import sys, ctypes, numpy as np
 sys.path.insert(0, '/root/repo')
 import __graft_entry__ as g
